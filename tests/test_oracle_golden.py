@@ -1,0 +1,72 @@
+"""Pin the oracle: oracle/vispec_oracle.py must reproduce what the unmodified reference returned
+(tests/golden/*.pt, written by tests/golden/make_golden.py) on the same seeded inputs."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import synth
+from oracle import vispec_oracle as vo
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
+
+
+def load_case(name):
+    g = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    m = g["meta"]
+    tcfg, dcfg = synth.TINY_T, synth.TINY_D
+    if m["kind"] == "random":
+        tw = synth.make_target_weights(tcfg, m["seed"])
+        dw = synth.make_draft_weights(dcfg, m["seed"] + 1)
+    else:
+        tw, dw = synth.make_bigram_fixture(tcfg, dcfg, m["seed"], fc_noise=m["fc_noise"])
+    ids, emb, mask = synth.make_prompt(tcfg, tw, m["seed"] + 7, m["n_pre"], m["n_img"], m["n_post"])
+    return g, tcfg, dcfg, tw, dw, ids, (emb if mask is not None else None), mask
+
+
+def test_golden_files_present():
+    assert len(CASES) >= 5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(name):
+    torch.set_num_threads(8)
+    g, tcfg, dcfg, tw, dw, ids, emb, mask = load_case(name)
+    target, draft = vo.TargetOracle(tcfg, tw), vo.DraftOracle(dcfg, dw)
+    trace = vo.SpecTrace()
+    n_cycles = g["meta"]["n_cycles"]
+    out, new_token, idx, acc = vo.spec_generate(target, draft, ids, emb, mask, max_new_tokens=10 ** 9,
+                                                max_cycles=n_cycles, trace=trace)
+    assert acc == [c["accept_length"] for c in g["cycles"]]
+    assert torch.equal(out, g["output_ids"])
+    assert new_token == g["new_token"]
+    # per-cycle tree structures: cycle i verified the tree built at the end of cycle i-1 (first: prefill)
+    trees = [g["first"]] + g["cycles"][:-1]
+    for tr, ref in zip(trace.cycles, trees):
+        assert torch.equal(tr["draft_tokens"], ref["draft_tokens"])
+        assert torch.equal(tr["retrieve"], ref["retrieve_indices"])
+        assert torch.equal(tr["tree_mask"], ref["tree_mask"])
+        assert torch.equal(tr["tree_pos"], ref["tree_position_ids"])
+    for tr, ref in zip(trace.cycles, g["cycles"]):
+        assert tr["best"] == ref["best_candidate"]
+        assert tr["token"] == int(ref["sample_token"])
+        assert torch.equal(tr["logits_root"], ref["tree_logits_root"])       # same ATen ops -> exact on CPU
+    assert target.cur_len == g["cycles"][-1]["kv_len"]
+    assert draft.stable_kv[0].shape[2] == g["cycles"][-1]["draft_kv_len"]
+    assert draft.stable_kv[2] == g["cycles"][-1]["draft_real_len"]
+    kv_sum = target.kv[..., :target.cur_len, :].float().sum(dim=(1, 2, 3, 4))
+    assert torch.equal(kv_sum, g["kv_checksum"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_spec_equals_greedy(name):
+    """The invariant of SURVEY.md 7.2: speculative output == plain greedy decode of the target."""
+    g, tcfg, dcfg, tw, dw, ids, emb, mask = load_case(name)
+    assert g["spec_equals_greedy"]
+    target = vo.TargetOracle(tcfg, tw)
+    n_new = g["output_ids"].shape[1] - ids.shape[1]
+    out = vo.greedy_generate(target, ids, emb, n_new)
+    assert torch.equal(out, g["greedy_ids"])
+    assert torch.equal(out, g["output_ids"])
