@@ -1,0 +1,143 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every declared symbol; host-side packing and
+tables agree with the oracle; the KV-cache mirror behaves like the reference's; prompt sharding works at
+world_size 2 over gloo."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    import __graft_entry__ as g
+    g.build()
+    from vispec_b200 import _lib, build
+    assert os.path.exists(build.LIB_PATH)
+    lib = ctypes.CDLL(build.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "vispec_b200.h")).read()
+    declared = set(re.findall(r"\b(vs_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vispec_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib.vs_abi_version.restype = ctypes.c_int
+    assert lib.vs_abi_version() == 1
+
+
+def test_sass_is_sm100a():
+    from vispec_b200 import build
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", build.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_ctypes_struct_layout_matches_c():
+    """sizeof() of every struct passed across the ABI, against a C translation unit compiled with gcc."""
+    import subprocess
+    import tempfile
+    from vispec_b200 import _lib as L
+    names = {"vs_linear_args": L.LinearArgs, "vs_attn_args": L.AttnArgs, "vs_tree_bufs": L.TreeBufs, "vs_dims": L.Dims,
+             "vs_layer": L.Layer, "vs_scratch": L.Scratch, "vs_rope": L.Rope, "vs_target": L.Target, "vs_draft": L.Draft}
+    src = '#include <stdio.h>\n#include "vispec_b200.h"\nint main(){' + "".join(
+        f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        out = subprocess.check_output([exe], text=True)
+    sizes = dict(line.split() for line in out.strip().splitlines())
+    for n, cls in names.items():
+        assert int(sizes[n]) == ctypes.sizeof(cls), n
+
+
+def test_split_k_policy_is_bounded():
+    from vispec_b200 import _lib as L
+    lib = L.load()
+    for n, k in [(12288, 4096), (4096, 4096), (22016, 4096), (4096, 11008), (32064, 4096), (4096, 8192), (256, 256)]:
+        s = lib.vs_linear_splits(n, k, 30)
+        assert 1 <= s <= 16 and (s == 1 or (k // 64) // s >= 8)
+        assert lib.vs_linear_partials_floats(n, 30, s) == (0 if s == 1 else s * ((n + 127) // 128) * 32 * 128)
+
+
+def test_pack_gate_up_and_rope_tables_match_oracle():
+    from oracle import vispec_oracle as vo
+    from vispec_b200.engine import pack_gate_up, rope_tables
+    g, u = torch.randn(640, 256), torch.randn(640, 256)
+    w = pack_gate_up(g, u)
+    assert w.shape == (1280, 256)
+    for j in range(10):
+        assert torch.equal(w[128 * j:128 * j + 64], g[64 * j:64 * j + 64])
+        assert torch.equal(w[128 * j + 64:128 * j + 128], u[64 * j:64 * j + 64])
+    c, s = rope_tables(128, 512, 10000.0, torch.bfloat16, "cpu")
+    co, so = vo.rope_tables(128, 512, 10000.0, torch.bfloat16)
+    assert torch.equal(c, co) and torch.equal(s, so)
+
+
+def test_kv_cache_mirror_semantics():
+    from vispec_b200.model.kv_cache import KVCache
+    data = torch.zeros(1, 2, 16, 4)
+    lens = torch.zeros(2, dtype=torch.long)
+    kv = KVCache(data, lens[0])
+    out = kv.cat(torch.ones(1, 2, 3, 4))
+    assert out.shape == (1, 2, 3, 4) and kv.shape == (1, 2, 3, 4) and int(lens[0]) == 3
+    kv.cat(2 * torch.ones(1, 2, 2, 4))
+    kv.copy(torch.tensor([4, 0]), 1)
+    assert int(lens[0]) == 3 and float(data[0, 0, 1, 0]) == 2.0 and float(data[0, 0, 2, 0]) == 1.0
+
+
+def test_product_fails_loudly_without_cuda():
+    from vispec_b200.engine import TargetConfig, TargetEngine
+    with pytest.raises(RuntimeError):
+        TargetEngine(TargetConfig(), {}, device="cpu")
+
+
+def test_no_oracle_import_in_product():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "vispec_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_shard_prompts_partition():
+    from vispec_b200.replicas import shard_prompts
+    for n in (0, 1, 7, 100):
+        for world in (1, 2, 3, 8):
+            parts = [list(shard_prompts(n, r, world)) for r in range(world)]
+            assert sorted(x for p in parts for x in p) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from vispec_b200.replicas import aggregate_throughput, gather_results, shard_prompts
+    mine = [dict(question_id=i, new_tokens=[10 + i], wall_time=[1.0 + rank], acceptance_length=[i % 3])
+            for i in shard_prompts(7, rank, world)]
+    allr = gather_results(mine)
+    q.put((rank, [r["question_id"] for r in allr], aggregate_throughput(allr)))
+    dist.destroy_process_group()
+
+
+def test_replicas_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
+    [p.join(timeout=60) for p in ps]
+    for rank, ids, agg in res:
+        assert ids == list(range(7)) and agg["n_prompts"] == 7
+    assert res[0][2] == res[1][2]

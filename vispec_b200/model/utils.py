@@ -1,0 +1,138 @@
+"""Spec-decode cycle functions -- mirror of vispec/model/utils.py (same names, arguments and return tuples).
+
+These are the host-visible, one-stage-at-a-time entry points (`initialize_tree`, `tree_decoding`,
+`evaluate_posterior`, `update_inference_inputs`, `reset_tree_mode`, `prepare_logits_processor`, `Timer`).
+Each stage runs in the CUDA kernels behind the C ABI and, like the reference, hands host-visible tensors
+back to the caller (which costs a sync per stage).  `SpecModel.specgenerate` does not use them: it runs
+the fused, sync-free `vs_spec_cycle`.  Both routes execute the same kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import List
+
+import torch
+
+from .. import _lib as L
+from ..engine import _stream
+
+
+class Timer:
+    """utils.py:25-36."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.synchronize()
+        self.start = time.perf_counter()
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        torch.cuda.synchronize()
+        print(f"{self.name} took {time.perf_counter() - self.start} seconds")
+
+
+def prepare_logits_processor(temperature: float = 0.0, repetition_penalty: float = 0.0, top_p: float = 0.0,
+                             top_k: int = 0):
+    """utils.py:39-55.  Only greedy decoding (T=0) is on the B200 path; T>0 is SURVEY.md section 8f rank 2."""
+    if temperature > 1e-5:
+        raise NotImplementedError("temperature > 0 (sampling acceptance, utils.py:453-493) is not implemented on "
+                                  "the B200 path yet")
+    return None
+
+
+def reset_tree_mode(model):
+    """utils.py:330-339."""
+    lm = model.base_model
+    lm = getattr(lm, "language_model", lm)
+    lm.model.tree_mask = None
+    lm.model.tree_mode = None
+
+
+def reset_past_key_values(passed_key_values: List[torch.Tensor]) -> List[torch.Tensor]:
+    """utils.py:342-360."""
+    for i in range(len(passed_key_values)):
+        for j in range(2):
+            passed_key_values[i][j].current_length.fill_(0)
+    return passed_key_values
+
+
+def _lm_head(model):
+    lm = model.base_model
+    return getattr(lm, "language_model", lm).lm_head
+
+
+def initialize_tree(input_ids, model, past_key_values, logits_processor, inputs_embeds=None, embed_weights=None,
+                    image_mask=None, **kwargs):
+    """utils.py:266-327: target prefill, first token, first draft tree."""
+    outputs, orig, hidden_states = model(input_ids, past_key_values=past_key_values, output_orig=True,
+                                         inputs_embeds=inputs_embeds)
+    if logits_processor is not None:
+        raise NotImplementedError("T>0 is not on the B200 path yet")
+    token = torch.argmax(orig[:, -1])[None, None]
+    input_ids = torch.cat((input_ids, token.to(input_ids.device)), dim=1)
+    draft_tokens, retrieve_indices, tree_mask, tree_position_ids = model.spec_layer.topK_genrate(
+        hidden_states, input_ids, _lm_head(model), logits_processor, inputs_embeds=inputs_embeds,
+        image_mask=image_mask)
+    return draft_tokens, retrieve_indices, tree_mask, tree_position_ids, orig, hidden_states, token
+
+
+def tree_decoding(model, tree_candidates, past_key_values, tree_position_ids, input_ids, retrieve_indices):
+    """utils.py:389-412: verify the tree with the target (tree mask taken from `base_model.model.tree_mask`)."""
+    position_ids = tree_position_ids + input_ids.shape[1]
+    outputs, tree_logits, hidden_state = model(tree_candidates, output_orig=True, past_key_values=past_key_values,
+                                               position_ids=position_ids)
+    logits = tree_logits[0, retrieve_indices.to(tree_logits.device)]
+    logits._vs_model = model                 # lets evaluate_posterior use the device-side arg-max of this verify
+    return logits, hidden_state, outputs
+
+
+def evaluate_posterior(logits: torch.Tensor, candidates: torch.Tensor, logits_processor):
+    """utils.py:415-493, greedy branch (:438-451) through vs_accept_greedy."""
+    if logits_processor is not None:
+        raise NotImplementedError("T>0 acceptance is not on the B200 path yet")
+    model = getattr(logits, "_vs_model", None)
+    if model is None:
+        raise TypeError("evaluate_posterior expects the logits returned by vispec_b200's tree_decoding")
+    eng_t, eng_d = model.base_model_engine, model.spec_layer.engine
+    L.check(eng_d.lib.vs_accept_greedy(C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.amax), L.ptr(eng_d.out_rec),
+                                       _stream()), "vs_accept_greedy")
+    st = eng_t.state.tolist()
+    accept_length, best = st[L.ST_ACCEPT], st[L.ST_BEST]
+    best_candidate = torch.tensor(best, dtype=torch.long, device=candidates.device)
+    sample_p = logits[best, accept_length]
+    sample_p._vs_next_token = st[L.ST_NEXT_TOKEN]
+    return best_candidate, torch.tensor(accept_length, device=logits.device), sample_p
+
+
+@torch.no_grad()
+def update_inference_inputs(input_ids, candidates, best_candidate, accept_length, retrieve_indices, logits_processor,
+                            new_token, past_key_values_data_list, current_length_data, model, hidden_state_new,
+                            sample_p):
+    """utils.py:497-593: append the accepted tokens, splice the KV cache, build the next draft tree."""
+    if logits_processor is not None:
+        raise NotImplementedError("T>0 is not on the B200 path yet")
+    eng_t = model.base_model_engine
+    prev_input_len = input_ids.shape[1]
+    a = int(accept_length)
+    best = int(best_candidate)
+    sel = retrieve_indices[best, :a + 1]
+    input_ids = torch.cat([input_ids, candidates[None, best, :a + 1].to(input_ids.device)], dim=-1)
+    sel_host = (C.c_int32 * L.VS_MAX_ACCEPT)(*[int(x) for x in sel.tolist()])
+    for slab in past_key_values_data_list:                                   # utils.py:529-541
+        n_slabs, _, n_kv, max_pos, _ = slab.shape
+        L.check(eng_t.lib.vs_kv_splice(L.ptr(slab), n_slabs, n_kv, max_pos, None, None, prev_input_len, a + 1,
+                                       sel_host, _stream()), "vs_kv_splice")
+    current_length_data.fill_(prev_input_len + a + 1)
+    eng_t.set_len(prev_input_len + a + 1)
+    accept_hidden_state_new = hidden_state_new[:, sel.to(hidden_state_new.device)]      # utils.py:543-546
+    tok = getattr(sample_p, "_vs_next_token", None)
+    if tok is None:
+        raise TypeError("update_inference_inputs expects the sample_p returned by vispec_b200's evaluate_posterior")
+    token = torch.tensor(tok, device=input_ids.device)[None, None]
+    draft_tokens, retrieve_indices, tree_mask, tree_position_ids = model.spec_layer.topK_genrate(
+        accept_hidden_state_new, input_ids=torch.cat((input_ids, token.to(input_ids.device)), dim=1),
+        head=_lm_head(model), logits_processor=logits_processor)
+    new_token += a + 1
+    return input_ids, draft_tokens, retrieve_indices, tree_mask, tree_position_ids, new_token, None, token
