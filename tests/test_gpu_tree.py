@@ -121,7 +121,7 @@ def test_tree_build_matches_oracle(seed, shape):
     sim = simulate_expansion(seed, k=k, depth=depth)
     # tie-free selection scores (unique fp32 values); tree_build only ranks them
     g = torch.Generator().manual_seed(100 + seed)
-    scores = sim["scores_flat"] + torch.rand(sim["scores_flat"].shape, generator=g) * 1e-3
+    scores = sim["scores_flat"] + torch.randperm(sim["scores_flat"].numel(), generator=g).float() * 2e-5
     assert scores.unique().numel() == scores.numel()
     ts.t["scores_flat"].copy_(scores.to(DEV))
     ts.t["tokens_flat"].copy_(sim["tokens_flat"].to(DEV, torch.int32))
@@ -162,7 +162,7 @@ def test_accept_greedy_matches_oracle(seed):
     ts = TreeState()
     sim = simulate_expansion(seed)
     g = torch.Generator().manual_seed(200 + seed)
-    ts.t["scores_flat"].copy_((sim["scores_flat"] + torch.rand(200, generator=g) * 1e-3).to(DEV))
+    ts.t["scores_flat"].copy_((sim["scores_flat"] + torch.randperm(200, generator=g).float() * 2e-5).to(DEV))
     # small vocabulary so that draft tokens match the target's arg-max often (accept lengths 0..depth+1)
     tokens = torch.randint(0, 3, (200,), generator=g)
     ts.t["tokens_flat"].copy_(tokens.to(DEV, torch.int32))
