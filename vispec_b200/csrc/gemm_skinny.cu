@@ -8,6 +8,7 @@
 // the N operand, a 4-stage cp.async pipeline keeps 80 KB per block in flight, split-K fills the 148
 // SMs, and a deterministic last-block reduction feeds a fused epilogue that reproduces the
 // reference's bf16 rounding points (bias, residual add, SiLU*up, RoPE + in-place KV append).
+#include "gemm_epilogue.cuh"
 #include "kernels.h"
 #include "profile.h"
 
@@ -22,76 +23,8 @@ constexpr int W_STAGE = BM * BK * 2;          // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;      // 4096
 constexpr int STAGE_BYTES = W_STAGE + X_STAGE;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES;   // 81920
-constexpr int CT_LD = BM + 4;                 // fp32 tile [32][132] staged in the pipeline smem afterwards
+constexpr int CT_LD = EPI_CT_LD;              // fp32 tile [32][132] staged in the pipeline smem afterwards
 constexpr int THREADS = 256;
-
-struct Tile {
-  const float* ct;   // [32][CT_LD] fp32, ct[t*CT_LD + r] = acc(token t, tile row r)
-  int tile, n0, t0, tb_rows;
-};
-
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
-
-template <int EPI>
-__device__ __forceinline__ void epilogue(const GemmArgs& p, const Tile& tl) {
-  const int tid = threadIdx.x;
-  if (EPI == EPI_STORE || EPI == EPI_RESID) {
-    for (int i = tid; i < VS_TOK * BM; i += THREADS) {
-      int t = i >> 7, r = i & 127;
-      int n = tl.n0 + r;
-      if (t >= tl.tb_rows || n >= p.N) continue;
-      float v = tl.ct[t * CT_LD + r];
-      if (p.bias) v += bf2f(p.bias[n]);
-      long row = tl.t0 + t;
-      if (EPI == EPI_RESID) {
-        float o = rbf(v);                                         // Linear output rounds to bf16 ...
-        v = bf2f(p.R[row * p.ldr + n]) + o;                       // ... then the residual add rounds again
-      }
-      p.Y[row * p.ldy + n] = f2bf(v);
-    }
-  } else if (EPI == EPI_SWIGLU) {
-    // tile rows [0,64) = gate features j0..j0+63, rows [64,128) = the matching up features
-    const int j0 = tl.tile * 64;
-    for (int i = tid; i < VS_TOK * 64; i += THREADS) {
-      int t = i >> 6, r = i & 63;
-      if (t >= tl.tb_rows) continue;
-      float g = rbf(tl.ct[t * CT_LD + r]);
-      float u = rbf(tl.ct[t * CT_LD + 64 + r]);
-      float a = rbf(silu_f(g));                                   // act_fn(gate) rounds, then * up rounds
-      p.Y[(long)(tl.t0 + t) * p.ldy + j0 + r] = f2bf(a * u);
-    }
-  } else {  // EPI_HEADS
-    const int tile = tl.tile;
-    const bool is_q = tile < p.n_q_tiles;
-    const bool is_k = !is_q && tile < p.n_q_tiles + p.n_k_tiles;
-    const int head = is_q ? tile : (is_k ? tile - p.n_q_tiles : tile - p.n_q_tiles - p.n_k_tiles);
-    const int row_base = (p.kv_row_base ? *p.kv_row_base : 0) + p.kv_row_off;
-    for (int i = tid; i < VS_TOK * BM; i += THREADS) {
-      int t = i >> 7, d = i & 127;
-      if (t >= tl.tb_rows) continue;
-      int n = tl.n0 + d;
-      float b = p.bias ? bf2f(p.bias[n]) : 0.f;
-      float x = rbf(tl.ct[t * CT_LD + d] + b);
-      float out = x;
-      if (p.rope && !(!is_q && !is_k)) {
-        int d2 = d < 64 ? d + 64 : d - 64;
-        float b2 = p.bias ? bf2f(p.bias[tl.n0 + d2]) : 0.f;
-        float x2 = rbf(tl.ct[t * CT_LD + d2] + b2);
-        float rot = d < 64 ? -x2 : x2;
-        long pos = p.pos_ids[tl.t0 + t];
-        float c = bf2f(p.cos[pos * 128 + d]), s = bf2f(p.sin[pos * 128 + d]);
-        out = rbf(x * c) + rbf(rot * s);                          // three bf16 roundings (cnets_ours.py:117-118)
-      }
-      bf16 o = f2bf(out);
-      if (is_q) {
-        p.Qout[(long)head * p.q_head_stride + (long)(tl.t0 + t) * 128 + d] = o;
-      } else {
-        bf16* dst = is_k ? p.Kout : p.Vout;
-        dst[(long)head * p.kv_head_stride + (long)(row_base + tl.t0 + t) * 128 + d] = o;
-      }
-    }
-  }
-}
 
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const GemmArgs p) {
@@ -216,32 +149,10 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const GemmArgs 
   }
 
   Tile tl{ct, tile, n0, t0, tb_rows};
-  epilogue<EPI>(p, tl);
+  epilogue<EPI, THREADS>(p, tl, threadIdx.x);
 }
 
 }  // namespace
-
-int gemm_pick_splits(int N, int K, int T) {
-  int n_tiles = (N + BM - 1) / BM;
-  int tok_blocks = (T + VS_TOK - 1) / VS_TOK;
-  int nk = K / BK;
-  long blocks = (long)n_tiles * tok_blocks;
-  int target = 148 * 2;
-  int s = (int)((target + blocks - 1) / blocks);
-  if (s < 1) s = 1;
-  int max_s = nk / 8;               // keep >= 8 k-chunks per block so the pipeline has something to hide
-  if (max_s < 1) max_s = 1;
-  if (s > max_s) s = max_s;
-  if (s > 16) s = 16;
-  return s;
-}
-
-size_t gemm_partials_floats(int N, int T, int splits) {
-  if (splits <= 1) return 0;
-  size_t n_tiles = (N + BM - 1) / BM;
-  size_t tok_blocks = (T + VS_TOK - 1) / VS_TOK;
-  return tok_blocks * splits * n_tiles * VS_TOK * BM;
-}
 
 template <int EPI>
 static cudaError_t launch_t(const GemmArgs& a, cudaStream_t st) {
@@ -259,10 +170,8 @@ static cudaError_t launch_t(const GemmArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st) {
-  if (a.T <= 0) return cudaSuccess;
-  if (a.K % BK != 0 || a.ldw % 8 != 0 || a.ldx % 8 != 0) return cudaErrorInvalidValue;
-  if (a.splits > 1 && (!a.partials || !a.counters)) return cudaErrorInvalidValue;
+// mma.sync bring-up kernel, kept selectable with VS_GEMM_LEGACY=1 for A/B debugging of the tcgen05 path
+cudaError_t launch_gemm_legacy(const GemmArgs& a, cudaStream_t st) {
   switch (a.epi) {
     case EPI_STORE: return launch_t<EPI_STORE>(a, st);
     case EPI_RESID: return launch_t<EPI_RESID>(a, st);
