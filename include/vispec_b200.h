@@ -253,6 +253,73 @@ int vs_spec_cycle(const vs_target* t, const vs_scratch* ts, const vs_draft* dm, 
                   void* logits, int32_t* amax, int32_t* out_rec, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Programs: the persistent decode kernel.  A program is a list of phases that ONE kernel launch (one CTA
+ * per SM, co-resident, phases separated by grid barriers) executes back to back: the weight stream
+ * (TMA -> tcgen05) runs ahead across phase boundaries and is prefetched into L2, so the per-op launches
+ * above collapse into a single launch per draft+verify cycle.  Every vs_program_add_* mirrors the entry
+ * point of the same name above (same arguments, same reference citations, same results up to the fp32
+ * summation order of the k-split); token rows per phase are limited to 32, `splits`, `partials`,
+ * `counters` of vs_linear_args are ignored (the program owns its split and workspace).
+ *
+ *   vs_program_create -> vs_program_add_* ... -> vs_program_workspace_bytes -> (caller allocates) ->
+ *   vs_program_commit -> vs_program_run (any number of times) -> vs_program_destroy
+ *
+ * The handle is host memory owned by the library; all device memory is the caller's workspace.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct vs_program vs_program;
+int vs_program_create(vs_program** out);
+void vs_program_destroy(vs_program* pg);
+const char* vs_program_last_error(void);
+/* options: "pf_ahead" (L2 prefetch distance in 16 KB weight chunks per SM, default 24, 0 = off),
+ * "trace" (1: record a %globaltimer stamp per phase), "grid" (CTAs; default = SM count; before adding phases) */
+int vs_program_set_option(vs_program* pg, const char* name, int value);
+int vs_program_num_phases(const vs_program* pg);
+int vs_program_phase_types(const vs_program* pg, int32_t* out, int cap);
+size_t vs_program_workspace_bytes(vs_program* pg);
+int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* stream);   /* 256-byte aligned workspace */
+int vs_program_run(const vs_program* pg, void* stream);
+int vs_program_read_trace(const vs_program* pg, unsigned long long* out_ns, int cap);
+
+int vs_program_add_linear(vs_program* pg, const vs_linear_args* a);
+int vs_program_add_rmsnorm(vs_program* pg, const void* x, int64_t ldx, const void* weight, void* y, int64_t ldy, int T,
+                           int H, float eps);
+int vs_program_add_gather_rows(vs_program* pg, const void* src, int64_t lds, const int32_t* idx, void* dst, int64_t ldd,
+                               int T, int H);
+int vs_program_add_embed_rows(vs_program* pg, const void* table, int64_t ldt, const int32_t* ids, void* dst, int64_t ldd,
+                              int T, int H, int vocab);
+int vs_program_add_broadcast_row(vs_program* pg, const void* row, void* dst, int64_t ldd, int T, int H);
+int vs_program_add_argmax_rows(vs_program* pg, const void* logits, int64_t ldl, int T, int V, int32_t* out);
+int vs_program_add_logsoftmax_topk(vs_program* pg, const void* logits, int64_t ldl, int T, int V, int k,
+                                   const int32_t* row_sel, float* top_val, int32_t* top_idx);
+int vs_program_add_attention(vs_program* pg, const vs_attn_args* a);
+int vs_program_add_draft_level0(vs_program* pg, const vs_tree_bufs* tb, int32_t* state);
+int vs_program_add_draft_expand(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, int level);
+int vs_program_add_tree_build(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, const int32_t* sample_token_dev,
+                              int sample_token_host);
+int vs_program_add_accept_greedy(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, const int32_t* amax,
+                                 int32_t* out_rec);
+int vs_program_add_kv_splice(vs_program* pg, void* slab, int n_slabs, int n_kv, int64_t max_pos, const int32_t* state,
+                             const int32_t* sel_dev);
+int vs_program_add_decoder_layer(vs_program* pg, const vs_dims* d, const vs_layer* l, const vs_scratch* s,
+                                 const vs_rope* rope, int T, const int32_t* pos_ids, const int32_t* kv_row_base,
+                                 int kv_row_off, const int32_t* n_ctx, int n_ctx_host, int n_new, int causal,
+                                 const uint64_t* bits, int eager);
+int vs_program_add_verify_step(vs_program* pg, const vs_target* t, const vs_scratch* s, const int32_t* token_ids,
+                               const int32_t* pos_ids, const uint64_t* bits, int T, int32_t* state, void* hidden_out,
+                               void* logits, int32_t* amax);
+int vs_program_add_draft_forward(vs_program* pg, const vs_draft* dm, const vs_scratch* s, int T, const int32_t* ids,
+                                 const int32_t* pos_ids, const int32_t* kv_row_base, int kv_row_off, const int32_t* n_ctx,
+                                 int n_new, int causal, const uint64_t* bits);
+int vs_program_add_draft_levels(vs_program* pg, const vs_draft* dm, const vs_scratch* s, const vs_tree_bufs* tb,
+                                int32_t* state, int head_rows, const int32_t* sample_token_dev, int sample_token_host);
+int vs_program_add_draft_tree(vs_program* pg, const vs_draft* dm, const vs_scratch* s, const vs_tree_bufs* tb,
+                              int32_t* state);
+/* the whole draft+verify cycle of vs_spec_cycle as ONE launch */
+int vs_program_add_spec_cycle(vs_program* pg, const vs_target* t, const vs_scratch* ts, const vs_draft* dm,
+                              const vs_scratch* ds, const vs_tree_bufs* tb, int32_t* state, void* kv_slab,
+                              int64_t kv_max_pos, void* hidden_out, void* logits, int32_t* amax, int32_t* out_rec);
+
+/* ------------------------------------------------------------------------------------------------
  * Instrumentation (bench.py): number of kernels launched by this library, and optional CUDA-event timing of
  * every fused-linear (class 0, bytes = weight bytes streamed) and attention (class 1, bytes = K+V bytes per key)
  * launch on the launching stream.  vs_profile_stop synchronises the device and returns the record count.

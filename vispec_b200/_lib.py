@@ -18,6 +18,9 @@ VS_MAX_ACCEPT = 8
  ST_LAST_ROW, ST_CYCLE) = range(12)
 ST_SLOTS = 16
 EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_HEADS = range(4)
+(PH_NOP, PH_GEMM, PH_EPI, PH_NORM, PH_ROWS, PH_ATTN_S, PH_ATTN_PV, PH_ARGMAX, PH_LSM_TOPK, PH_TREE, PH_SPLICE) = range(11)
+PHASE_NAMES = ("nop", "gemm", "epilogue", "rmsnorm", "rows", "attn_scores", "attn_pv", "argmax", "logsoftmax_topk", "tree",
+               "kv_splice")
 
 
 class LinearArgs(C.Structure):
@@ -112,6 +115,42 @@ _SIGS = {
     "vs_draft_tree": (C.c_int, [C.POINTER(Draft), C.POINTER(Scratch), C.POINTER(TreeBufs), c_vp, c_vp]),
     "vs_spec_cycle": (C.c_int, [C.POINTER(Target), C.POINTER(Scratch), C.POINTER(Draft), C.POINTER(Scratch),
                                 C.POINTER(TreeBufs), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    # ---- programs (persistent decode kernel) ----
+    "vs_program_create": (C.c_int, [C.POINTER(c_vp)]),
+    "vs_program_destroy": (None, [c_vp]),
+    "vs_program_last_error": (C.c_char_p, []),
+    "vs_program_set_option": (C.c_int, [c_vp, C.c_char_p, C.c_int]),
+    "vs_program_num_phases": (C.c_int, [c_vp]),
+    "vs_program_phase_types": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "vs_program_workspace_bytes": (C.c_size_t, [c_vp]),
+    "vs_program_commit": (C.c_int, [c_vp, c_vp, C.c_size_t, c_vp]),
+    "vs_program_run": (C.c_int, [c_vp, c_vp]),
+    "vs_program_read_trace": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "vs_program_add_linear": (C.c_int, [c_vp, C.POINTER(LinearArgs)]),
+    "vs_program_add_rmsnorm": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_f32]),
+    "vs_program_add_gather_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, C.c_int]),
+    "vs_program_add_embed_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int]),
+    "vs_program_add_broadcast_row": (C.c_int, [c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int]),
+    "vs_program_add_argmax_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.c_int, c_vp]),
+    "vs_program_add_logsoftmax_topk": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "vs_program_add_attention": (C.c_int, [c_vp, C.POINTER(AttnArgs)]),
+    "vs_program_add_draft_level0": (C.c_int, [c_vp, C.POINTER(TreeBufs), c_vp]),
+    "vs_program_add_draft_expand": (C.c_int, [c_vp, C.POINTER(TreeBufs), c_vp, C.c_int]),
+    "vs_program_add_tree_build": (C.c_int, [c_vp, C.POINTER(TreeBufs), c_vp, c_vp, C.c_int]),
+    "vs_program_add_accept_greedy": (C.c_int, [c_vp, C.POINTER(TreeBufs), c_vp, c_vp, c_vp]),
+    "vs_program_add_kv_splice": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, c_vp, c_vp]),
+    "vs_program_add_decoder_layer": (C.c_int, [c_vp, C.POINTER(Dims), C.POINTER(Layer), C.POINTER(Scratch), C.POINTER(Rope),
+                                               C.c_int, c_vp, c_vp, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int]),
+    "vs_program_add_verify_step": (C.c_int, [c_vp, C.POINTER(Target), C.POINTER(Scratch), c_vp, c_vp, c_vp, C.c_int, c_vp,
+                                             c_vp, c_vp, c_vp]),
+    "vs_program_add_draft_forward": (C.c_int, [c_vp, C.POINTER(Draft), C.POINTER(Scratch), C.c_int, c_vp, c_vp, c_vp,
+                                               C.c_int, c_vp, C.c_int, C.c_int, c_vp]),
+    "vs_program_add_draft_levels": (C.c_int, [c_vp, C.POINTER(Draft), C.POINTER(Scratch), C.POINTER(TreeBufs), c_vp,
+                                              C.c_int, c_vp, C.c_int]),
+    "vs_program_add_draft_tree": (C.c_int, [c_vp, C.POINTER(Draft), C.POINTER(Scratch), C.POINTER(TreeBufs), c_vp]),
+    "vs_program_add_spec_cycle": (C.c_int, [c_vp, C.POINTER(Target), C.POINTER(Scratch), C.POINTER(Draft),
+                                            C.POINTER(Scratch), C.POINTER(TreeBufs), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp,
+                                            c_vp]),
     "vs_launch_count": (C.c_longlong, [C.c_int]),
     "vs_profile_start": (C.c_int, [C.c_int]),
     "vs_profile_stop": (C.c_int, [c_vp, c_vp, c_vp, C.c_int]),
@@ -148,6 +187,13 @@ def load():
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().vs_last_error().decode(errors="replace")
+        raise RuntimeError(f"vispec_b200 {what} failed (code {rc}): {msg}")
+
+
+def pcheck(rc: int, what: str = "") -> None:
+    """Like check() for the vs_program_* entry points (their messages come from vs_program_last_error)."""
+    if rc != 0:
+        msg = load().vs_program_last_error().decode(errors="replace")
         raise RuntimeError(f"vispec_b200 {what} failed (code {rc}): {msg}")
 
 

@@ -13,6 +13,7 @@
 // cast to bf16, PV); otherwise scores stay fp32 and normalisation happens after PV (SDPA-style).
 #include <math.h>
 
+#include "attn_dev.cuh"
 #include "kernels.h"
 #include "profile.h"
 
@@ -20,283 +21,26 @@ namespace vs {
 
 namespace {
 
-constexpr int CHUNK = 64;          // keys per chunk
-constexpr int ATHREADS = 128;      // 4 warps
-constexpr int ROW_B = 256;         // bytes per 128-dim bf16 row
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
 
-__device__ __forceinline__ int swz256(int row, int chunk16) {   // byte offset in a [rows][128] bf16 tile
-  return row * ROW_B + (((chunk16 & 8) | ((chunk16 ^ row) & 7)) << 4);
-}
-
-__device__ __forceinline__ void load_rows_async(uint8_t* dst, const bf16* src, int first_row, int n_rows_valid,
-                                                int n_rows_tile) {
-  // tile rows [0, n_rows_tile) <- src rows first_row + r, zero-filled for r >= n_rows_valid
-  for (int i = threadIdx.x; i < n_rows_tile * 16; i += ATHREADS) {
-    int r = i >> 4, ch = i & 15;
-    bool ok = r < n_rows_valid;
-    const bf16* s = src + (long)(first_row + (ok ? r : 0)) * 128 + ch * 8;
-    cp_async16(dst + swz256(r, ch), s, ok);
-  }
-}
-
-__device__ __forceinline__ bool visible(const AttnArgs& p, int n_ctx, int kv_len, int q_abs, unsigned long long qbits,
-                                        int key) {
-  if (key >= kv_len) return false;
-  if (p.causal) return key < n_ctx + q_abs + 1;
-  if (key < n_ctx) return true;
-  int j = key - n_ctx;
-  return j < 64 && ((qbits >> j) & 1ull);
-}
-
-__global__ void __launch_bounds__(ATHREADS) attn_scores_kernel(const AttnArgs p) {
-  __shared__ __align__(128) uint8_t qs[VS_TOK * ROW_B];
-  __shared__ __align__(128) uint8_t ks[CHUNK * ROW_B];
-  __shared__ float red[4][VS_TOK];
-  __shared__ float rowm[VS_TOK];
-  const int head = blockIdx.x, tqb = blockIdx.z;
-  const int kvh = head / (p.n_heads / p.n_kv_heads);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+// Stand-alone launches: one thread block == one team (attn_dev.cuh); the persistent program kernel (program.cu)
+// runs the same bodies as phases of one launch.
+__global__ void __launch_bounds__(ATT_THREADS) attn_scores_kernel(const AttnArgs p) {
+  __shared__ AttnSmem sm;
   const int n_ctx = p.n_ctx ? *p.n_ctx : p.n_ctx_host;
-  const int kv_len = n_ctx + p.n_new;
-  const int n_chunks = (kv_len + CHUNK - 1) / CHUNK;
-  const int t0 = tqb * VS_TOK;
-  const int tq_rows = min(VS_TOK, p.Tq - t0);
-  const int tq_blocks = gridDim.z;
-  const int g = lane >> 2, t4 = lane & 3;
-
-  load_rows_async(qs, p.Q + (long)head * p.q_head_stride, t0, tq_rows, VS_TOK);
-  cp_async_commit();
-
-  // the four query rows this thread owns in the accumulator layout: mblk*16 + g (+8)
-  unsigned long long qb[4];
-  int qabs[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int q = (i >> 1) * 16 + g + (i & 1) * 8;
-    qabs[i] = t0 + q;
-    qb[i] = (!p.causal && p.bits && q < tq_rows) ? p.bits[t0 + q] : 0ull;
-  }
-
-  const bf16* kbase = p.K + (long)kvh * p.kv_head_stride;
-  float* sbase = p.scores + ((long)head * tq_blocks * VS_TOK + t0) * p.score_ld;
-  float* stat_base = p.stats + (((long)head * tq_blocks + tqb) * p.max_chunks) * VS_TOK * 2;
-  const float inv_div = sqrtf((float)VS_HEAD_DIM);
-
+  const int n_chunks = (n_ctx + p.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
+  bool first = true;
   for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
-    const int key0 = c * CHUNK;
-    __syncthreads();   // previous iteration finished reading ks / red
-    load_rows_async(ks, kbase, key0, min(CHUNK, kv_len - key0), CHUNK);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-
-    float acc[2][2][4];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
-
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      uint32_t bfr[4];
-      {
-        int mat = lane >> 3;
-        int r = warp * 16 + (lane & 7) + (mat >> 1) * 8;
-        int ch = kk * 2 + (mat & 1);
-        ldmatrix_x4(bfr, ks + swz256(r, ch));
-      }
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        uint32_t afr[4];
-        int mat = lane >> 3;
-        int r = mb * 16 + (lane & 7) + (mat & 1) * 8;
-        int ch = kk * 2 + (mat >> 1);
-        ldmatrix_x4(afr, qs + swz256(r, ch));
-        mma_bf16(acc[mb][0], afr, bfr[0], bfr[1]);
-        mma_bf16(acc[mb][1], afr, bfr[2], bfr[3]);
-      }
-    }
-
-    // scale / round / mask; element (mb, ng, e): query = mb*16 + g + (e>>1)*8, key = key0 + warp*16 + ng*8 + 2*t4 + (e&1)
-    float lmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-      for (int ng = 0; ng < 2; ++ng)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          int qi = mb * 2 + (e >> 1);
-          int key = key0 + warp * 16 + ng * 8 + 2 * t4 + (e & 1);
-          float s = acc[mb][ng][e];
-          s = p.eager ? rbf(rbf(s) / inv_div) : s * p.scale;
-          if (!visible(p, n_ctx, kv_len, qabs[qi], qb[qi], key)) s = -INFINITY;
-          acc[mb][ng][e] = s;
-          lmax[qi] = fmaxf(lmax[qi], s);
-        }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      lmax[i] = fmaxf(lmax[i], __shfl_xor_sync(0xffffffffu, lmax[i], 1));
-      lmax[i] = fmaxf(lmax[i], __shfl_xor_sync(0xffffffffu, lmax[i], 2));
-      if (t4 == 0) red[warp][(i >> 1) * 16 + g + (i & 1) * 8] = lmax[i];
-    }
-    __syncthreads();
-    if (tid < VS_TOK) rowm[tid] = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid]));
-    __syncthreads();
-    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-      for (int ng = 0; ng < 2; ++ng)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          int qi = mb * 2 + (e >> 1);
-          int q = mb * 16 + g + (e >> 1) * 8;
-          int key = key0 + warp * 16 + ng * 8 + 2 * t4 + (e & 1);
-          float s = acc[mb][ng][e];
-          if (s != -INFINITY) lsum[qi] += expf(s - rowm[q]);
-          sbase[(long)q * p.score_ld + key] = s;
-        }
-    __syncthreads();   // rowm consumed before red is overwritten below
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      lsum[i] += __shfl_xor_sync(0xffffffffu, lsum[i], 1);
-      lsum[i] += __shfl_xor_sync(0xffffffffu, lsum[i], 2);
-      if (t4 == 0) red[warp][(i >> 1) * 16 + g + (i & 1) * 8] = lsum[i];
-    }
-    __syncthreads();
-    if (tid < VS_TOK) {
-      float l = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-      stat_base[((long)c * VS_TOK + tid) * 2 + 0] = rowm[tid];
-      stat_base[((long)c * VS_TOK + tid) * 2 + 1] = l;
-    }
+    attn_scores_item(p, sm, blockIdx.x, blockIdx.z, gridDim.z, c, first, threadIdx.x, BlockSync());
+    first = false;
   }
 }
 
-__global__ void __launch_bounds__(ATHREADS) attn_pv_kernel(const AttnArgs p) {
-  __shared__ __align__(128) uint8_t vsm[CHUNK * ROW_B];        // V chunk [64][128] bf16
-  __shared__ __align__(128) uint8_t psm[VS_TOK * 128];         // P chunk [32][64] bf16
-  __shared__ float gM[VS_TOK], gL[VS_TOK];
-  __shared__ int s_last;
-  const int head = blockIdx.x, split = blockIdx.y, tqb = blockIdx.z;
-  const int kvh = head / (p.n_heads / p.n_kv_heads);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_ctx = p.n_ctx ? *p.n_ctx : p.n_ctx_host;
-  const int kv_len = n_ctx + p.n_new;
-  const int n_chunks = (kv_len + CHUNK - 1) / CHUNK;
-  const int t0 = tqb * VS_TOK;
-  const int tq_rows = min(VS_TOK, p.Tq - t0);
-  const int tq_blocks = gridDim.z;
-  const int g = lane >> 2, t4 = lane & 3;
-
-  const float* sbase = p.scores + ((long)head * tq_blocks * VS_TOK + t0) * p.score_ld;
-  const float* stat_base = p.stats + (((long)head * tq_blocks + tqb) * p.max_chunks) * VS_TOK * 2;
-
-  // global row max / sum from the chunk statistics (4 lanes per query row, fixed order)
-  {
-    int q = tid >> 2, part = tid & 3;
-    float m = -INFINITY;
-    for (int c = part; c < n_chunks; c += 4) m = fmaxf(m, stat_base[((long)c * VS_TOK + q) * 2]);
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    float l = 0.f;
-    for (int c = part; c < n_chunks; c += 4) {
-      float mc = stat_base[((long)c * VS_TOK + q) * 2], lc = stat_base[((long)c * VS_TOK + q) * 2 + 1];
-      if (mc != -INFINITY) l += lc * expf(mc - m);
-    }
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    if (part == 0) { gM[q] = m; gL[q] = l; }
-  }
-  __syncthreads();
-
-  float acc[2][4][4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
-
-  const bf16* vbase = p.V + (long)kvh * p.kv_head_stride;
-  for (int c = split; c < n_chunks; c += gridDim.y) {
-    const int key0 = c * CHUNK;
-    __syncthreads();
-    load_rows_async(vsm, vbase, key0, min(CHUNK, kv_len - key0), CHUNK);
-    cp_async_commit();
-    // probabilities for this chunk: [32][64] bf16, 128-byte rows, 16-byte chunks swizzled by row
-    for (int i = tid; i < VS_TOK * CHUNK; i += ATHREADS) {
-      int q = i >> 6, k = i & 63;
-      float s = sbase[(long)q * p.score_ld + key0 + k];
-      float pr = 0.f;
-      if (s != -INFINITY && key0 + k < kv_len) {
-        float e = expf(s - gM[q]);
-        pr = p.eager ? e / gL[q] : e;
-      }
-      int ch = k >> 3;
-      reinterpret_cast<bf16*>(psm + q * 128 + ((ch ^ (q & 7)) << 4))[k & 7] = f2bf(pr);
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t afr[2][4];
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        int mat = lane >> 3;
-        int r = mb * 16 + (lane & 7) + (mat & 1) * 8;
-        int ch = kk * 2 + (mat >> 1);
-        ldmatrix_x4(afr[mb], psm + r * 128 + ((ch ^ (r & 7)) << 4));
-      }
-#pragma unroll
-      for (int pr = 0; pr < 2; ++pr) {
-        uint32_t bfr[4];
-        int mat = lane >> 3;
-        int r = kk * 16 + (lane & 7) + (mat & 1) * 8;        // key row
-        int ch = warp * 4 + pr * 2 + (mat >> 1);             // 8-wide d chunk
-        ldmatrix_x4_trans(bfr, vsm + swz256(r, ch));
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          mma_bf16(acc[mb][pr * 2 + 0], afr[mb], bfr[0], bfr[1]);
-          mma_bf16(acc[mb][pr * 2 + 1], afr[mb], bfr[2], bfr[3]);
-        }
-      }
-    }
-  }
-
-  // publish the partial O tile [32][128] fp32; the last split to arrive reduces in split order
-  const int n_splits = gridDim.y;
-  float* obase = p.opart + (((long)head * tq_blocks + tqb) * n_splits) * VS_TOK * 128;
-  float* mine = obase + (long)split * VS_TOK * 128;
-#pragma unroll
-  for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-    for (int ng = 0; ng < 4; ++ng)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        int q = mb * 16 + g + (e >> 1) * 8;
-        int d = warp * 32 + ng * 8 + 2 * t4 + (e & 1);
-        mine[q * 128 + d] = acc[mb][ng][e];
-      }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    int old = atomicAdd(&p.counters[head * tq_blocks + tqb], 1);
-    s_last = (old == n_splits - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = tid; i < VS_TOK * 128; i += ATHREADS) {
-    int q = i >> 7, d = i & 127;
-    if (q >= tq_rows) continue;
-    float v = 0.f;
-    for (int s = 0; s < n_splits; ++s) v += __ldcg(obase + (long)s * VS_TOK * 128 + i);
-    if (!p.eager) v = v / gL[q];
-    p.O[(long)(t0 + q) * p.ldo + head * 128 + d] = f2bf(v);
-  }
-  if (tid == 0) p.counters[head * tq_blocks + tqb] = 0;
+__global__ void __launch_bounds__(ATT_THREADS) attn_pv_kernel(const AttnArgs p) {
+  __shared__ AttnSmem sm;
+  attn_pv_item(p, sm, blockIdx.x, blockIdx.z, gridDim.z, blockIdx.y, gridDim.y, threadIdx.x, BlockSync());
 }
 
 }  // namespace
@@ -310,10 +54,10 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st) {
   // algorithmic bytes: K and V read once = 2 * kv_len * n_kv * 128 * 2 B; kv_len is device-side, so the
   // profiler records the per-key figure and bench.py multiplies by the kv length it knows.
   prof_begin(PROF_ATTN, 2.0 * a.n_kv_heads * 128 * 2, st);
-  attn_scores_kernel<<<dim3(a.n_heads, gy, tq_blocks), ATHREADS, 0, st>>>(a);
+  attn_scores_kernel<<<dim3(a.n_heads, gy, tq_blocks), ATT_THREADS, 0, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  attn_pv_kernel<<<dim3(a.n_heads, a.pv_splits, tq_blocks), ATHREADS, 0, st>>>(a);
+  attn_pv_kernel<<<dim3(a.n_heads, a.pv_splits, tq_blocks), ATT_THREADS, 0, st>>>(a);
   prof_end(st);
   count_launch(2);
   return cudaGetLastError();

@@ -1,0 +1,95 @@
+// The persistent "program" kernel: a list of phases executed by ONE launch of one CTA per SM.
+// Device-side phase descriptors (plain structs in global memory) shared by program.cu (kernel + builder).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "tree.h"
+#include "tree_dev.cuh"
+
+namespace vs {
+
+enum PhaseType : int {
+  PH_NOP = 0,
+  PH_GEMM = 1,      // stream a weight matrix through TMA -> tcgen05; every CTA leaves fp32 partial tiles in L2
+  PH_EPI = 2,       // reduce the partial tiles in k order + fused epilogue (store / residual / SiLU*up / RoPE + KV append)
+  PH_NORM = 3,      // LlamaRMSNorm on T rows (optionally from per-tile sums of squares left by a residual epilogue)
+  PH_ROWS = 4,      // row gather / embedding lookup / broadcast
+  PH_ATTN_S = 5,    // attention pass 1: masked scores + chunk statistics
+  PH_ATTN_PV = 6,   // attention pass 2: softmax in the reference's rounding, P V, split reduction
+  PH_ARGMAX = 7,    // arg-max over the vocabulary per row
+  PH_LSM_TOPK = 8,  // bf16 log-softmax + top-k per row
+  PH_TREE = 9,      // integer tree bookkeeping (level0 / expand / build / accept / commit) on CTA 0
+  PH_SPLICE = 10    // KV-cache splice
+};
+
+enum TreeOp : int { TREE_LEVEL0 = 0, TREE_EXPAND = 1, TREE_BUILD = 2, TREE_ACCEPT = 3, TREE_COMMIT = 4 };
+
+struct Phase {
+  int type;
+  int T;                      // valid token rows (<= 32)
+  // ---- PH_GEMM / PH_EPI
+  int tmW, tmX;               // tensor-map table indices
+  int n_tiles, nk, N;         // ceil(N/128) weight-row tiles, K/64 chunks
+  int maxseg;                 // partial tiles per CTA
+  float* partials;            // [grid][maxseg][32 tokens][128 rows] fp32
+  int epi;
+  const bf16* bias;
+  bf16* Y; long ldy;
+  const bf16* R; long ldr;
+  float* ssq;                 // residual epilogue: [n_tiles][32] sums of squares of the new rows (or null)
+  int n_q_tiles, n_k_tiles, rope;
+  const bf16* cos; const bf16* sin; const int* pos_ids;
+  bf16* Qout; long q_head_stride;
+  bf16* Kout; bf16* Vout; long kv_head_stride;
+  const int* kv_row_base; int kv_row_off;
+  // ---- PH_NORM / PH_ROWS
+  const bf16* src; long lds;
+  const int* idx; int n_src_rows; int broadcast;
+  bf16* dst; long ldd;
+  int H;
+  const bf16* w; float eps;
+  const float* ssq_in; int ssq_tiles;
+  // ---- PH_ATTN_*
+  AttnArgs attn;
+  // ---- PH_ARGMAX / PH_LSM_TOPK
+  const bf16* logits; long ldl; int V; int k;
+  const int* row_sel; float* top_val; int* top_idx; int* amax_out;
+  // ---- PH_TREE
+  int tree_op, level;
+  TreeBufs tb; int* state; const int* amax; int* out_rec; const int* sample_token_dev; int sample_token_host;
+  // ---- PH_SPLICE
+  SpliceArgs splice; int n_items;
+};
+
+struct ProgramHeader {
+  const Phase* phases;
+  int n_phases;
+  const CUtensorMap* maps;
+  unsigned int* counters;          // [0] grid barrier, [1] exit counter
+  unsigned long long* trace;       // [n_phases] globaltimer at the end of each phase (CTA 0) or null
+  int pf_ahead;                    // L2 prefetch distance in 16 KB weight chunks per CTA (0 = off)
+};
+
+// ---- host-side phase constructors (program.cu); the C API and the composite builders live in program_api.cu ----
+}  // namespace vs
+struct vs_program;
+namespace vs {
+// `ssq` / `ssq_in` == PROG_WS_SSQ: the sums-of-squares buffer lives in the program's own workspace (patched at commit)
+#define PROG_WS_SSQ (reinterpret_cast<float*>(uintptr_t(1)))
+int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq);
+int prog_add_norm(vs_program* pg, const bf16* x, long ldx, const bf16* w, bf16* y, long ldy, int T, int H, float eps,
+                  const float* ssq_in, int ssq_tiles);
+int prog_add_rows(vs_program* pg, const bf16* src, long lds, const int* idx, int n_src_rows, int broadcast, bf16* dst,
+                  long ldd, int T, int H);
+int prog_add_attention(vs_program* pg, const AttnArgs& a);
+int prog_add_argmax(vs_program* pg, const bf16* logits, long ldl, int T, int V, int* out);
+int prog_add_lsm_topk(vs_program* pg, const bf16* logits, long ldl, int T, int V, int k, const int* row_sel, float* top_val,
+                      int* top_idx);
+int prog_add_tree(vs_program* pg, int op, const TreeBufs& tb, int* state, int level, const int* amax, int* out_rec,
+                  const int* sample_token_dev, int sample_token_host);
+int prog_add_splice(vs_program* pg, bf16* slab, int n_slabs, int n_kv, long max_pos, const int* state, const int* sel_dev);
+int prog_fail(int code, const char* where, const char* what);
+}  // namespace vs

@@ -1,255 +1,40 @@
-// Integer kernels of the draft-and-verify cycle: draft-tree expansion bookkeeping, tree build,
-// greedy token-accept and the KV-cache splice.  All state stays on the device (int32), so a whole
-// cycle runs without a host sync; the reference does these steps with .tolist()/.item() round trips
-// and Python loops (vispec/model/cnets_ours.py:1109-1238, vispec/model/utils.py:411,438-451,516-546).
-//
-// Tie rule: wherever the reference calls torch.topk / argmax on values that can tie (bf16 log-probs),
-// this library picks (value descending, index ascending).  torch's own order at exact ties is
-// implementation-defined and differs between its CPU and CUDA kernels.
+// Stand-alone launchers of the integer steps of the draft-and-verify cycle (bodies and reference citations in
+// tree_dev.cuh).  The persistent program kernel (program.cu) runs the same bodies as phases of one launch.
 #include "kernels.h"
 #include "profile.h"
 #include "tree.h"
+#include "tree_dev.cuh"
 
 namespace vs {
 
 namespace {
 
-// ---- draft level 0: after the stable forward's log-softmax/top-k on the last valid row ------------
-// cnets_ours.py:1109-1123: scores = top-k log-probs, parents_list=[0], tree_mask = eye(top_k).
-__global__ void draft_level0_kernel(TreeBufs tb, int* st) {
-  const int k = tb.top_k;
-  const int j = threadIdx.x;
-  if (j < k) {
-    float v = tb.top_val[j];
-    int tok = tb.top_idx[j];
-    tb.scores_flat[j] = v;
-    tb.tokens_flat[j] = tok;
-    tb.frontier_scores[j] = v;
-    tb.frontier_ids[j] = tok;
-    tb.cs_index[j] = j;
-    tb.frontier_bits[j] = 1ull << j;
-    tb.gather_idx[j] = st[VS_ST_LAST_ROW];            // input_hidden = last_hidden repeated top_k times
-    tb.draft_pos_ids[j] = st[VS_ST_D_POS];            // all siblings share one position (cnets_ours.py:1128)
-  }
-  if (j == 0) tb.parents[0] = 0;
-}
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
 
-// ---- draft level i (0-based loop index of cnets_ours.py:1126-1165), after that level's forward ------
+__global__ void draft_level0_kernel(TreeBufs tb, int* st) { tree_level0_body(tb, st, threadIdx.x); }
+
 __global__ void draft_expand_kernel(TreeBufs tb, int* st, int level) {
-  const int k = tb.top_k;
-  const int kk = k * k;
-  __shared__ float cu[64];
-  __shared__ unsigned long long keys[64];
-  __shared__ int sel[8];
-  __shared__ unsigned long long old_bits[8];
-  const int tid = threadIdx.x;
-  const int bias = 1 + kk * (level > 1 ? level - 1 : 0) + (level > 0 ? k : 0);
-  if (tid < k) {
-    tb.parents[1 + level * k + tid] = tb.cs_index[tid] + bias;       // uses the PREVIOUS selection
-    old_bits[tid] = tb.frontier_bits[tid];
-  }
-  if (tid < kk) {
-    int r = tid / k;
-    float v = rbf(tb.top_val[tid] + tb.frontier_scores[r]);           // bf16 add (cnets_ours.py:1151)
-    cu[tid] = v;
-    keys[tid] = rank_key(v, (uint32_t)tid);
-    tb.scores_flat[k + level * kk + tid] = v;
-    tb.tokens_flat[k + level * kk + tid] = tb.top_idx[tid];
-  }
-  __syncthreads();
-  if (tid < kk) {
-    int rank = 0;
-    unsigned long long me = keys[tid];
-    for (int i = 0; i < kk; ++i) rank += keys[i] > me;
-    if (rank < k) sel[rank] = tid;
-  }
-  __syncthreads();
-  if (tid < k) {
-    int ci = sel[tid];
-    int out_id = ci / k;
-    tb.cs_index[tid] = ci;
-    tb.frontier_scores[tid] = cu[ci];
-    tb.frontier_ids[tid] = tb.top_idx[ci];
-    tb.gather_idx[tid] = out_id;
-    // tree_mask = cat(tree_mask[:, :, out_ids], eye) (cnets_ours.py:1165): inherit the parent's row, add self
-    tb.frontier_bits[tid] = old_bits[out_id] | (1ull << (k * (level + 1) + tid));
-    tb.draft_pos_ids[tid] = st[VS_ST_D_POS] + level + 1;
-  }
+  __shared__ TreeSmem sm;
+  tree_expand_body(tb, st, level, sm, threadIdx.x, BlockSync());
 }
 
-// ---- tree build (cnets_ours.py:1167-1238) ---------------------------------------------------------
 __global__ void __launch_bounds__(256) tree_build_kernel(TreeBufs tb, int* st, const int* sample_token_ptr,
                                                          int sample_token_host) {
-  const int k = tb.top_k;
-  const int n_sc = k + tb.depth * k * k;
-  const int total = tb.total;                 // drafted nodes; tree has total+1 nodes
-  const int n = total + 1;
-  extern __shared__ unsigned long long sh_keys[];         // [n_sc]
-  __shared__ int sel_sorted[64];                           // flat indices of the selected nodes, ascending
-  __shared__ int parent_slot[64];
-  __shared__ unsigned long long bits[64];
-  __shared__ int is_parent[64];
-  __shared__ int n_leaf_s, max_depth_s;
-  const int tid = threadIdx.x;
-
-  for (int i = tid; i < n_sc; i += blockDim.x) sh_keys[i] = rank_key(tb.scores_flat[i], (uint32_t)i);
-  if (tid < 64) is_parent[tid] = 0;
-  if (tid == 0) { n_leaf_s = 0; max_depth_s = 0; }
-  __syncthreads();
-  // top-`total` by (score desc, index asc), then re-sorted by flat index (torch.sort of the indices)
-  int* selected = reinterpret_cast<int*>(sh_keys + n_sc);          // [n_sc] flags
-  for (int i = tid; i < n_sc; i += blockDim.x) {
-    unsigned long long me = sh_keys[i];
-    int rank = 0;
-    for (int j = 0; j < n_sc; ++j) rank += sh_keys[j] > me;
-    selected[i] = rank < total;
-  }
-  __syncthreads();
-  for (int i = tid; i < n_sc; i += blockDim.x) {
-    if (!selected[i]) continue;
-    int pos = 0;
-    for (int j = 0; j < i; ++j) pos += selected[j];
-    sel_sorted[pos] = i;
-  }
-  __syncthreads();
-  if (tid < total) {
-    int fi = sel_sorted[tid];
-    tb.draft_tokens[tid + 1] = tb.tokens_flat[fi];
-    int dp = tb.parents[fi / k];                 // node id of the parent (0 = root, else flat index + 1)
-    int slot = 0;
-    if (dp != 0) {
-      int cnt = 0;                               // searchsorted(top_idx, dp - 1, left)
-      for (int j = 0; j < total; ++j) cnt += sel_sorted[j] < dp - 1;
-      slot = cnt + 1;
-    }
-    parent_slot[tid + 1] = slot;
-  }
-  if (tid == 0) {
-    tb.draft_tokens[0] = sample_token_ptr ? *sample_token_ptr : sample_token_host;
-    parent_slot[0] = 0;
-  }
-  __syncthreads();
-  if (tid < n) {
-    unsigned long long b = 1ull;                 // column 0 (root) is visible to every node
-    int node = tid;
-    int guard = 0;
-    while (node != 0 && guard++ < 64) {
-      b |= 1ull << node;
-      node = parent_slot[node];
-    }
-    bits[tid] = b;
-    int pos = __popcll(b) - 1;
-    tb.tree_bits[tid] = b;
-    tb.tree_pos[tid] = pos;
-    tb.verify_pos[tid] = pos + st[VS_ST_CUR_LEN];
-    atomicMax(&max_depth_s, pos + 1);
-    if (tid > 0) is_parent[parent_slot[tid]] = 1;
-  }
-  __syncthreads();
-  if (tid < n && !is_parent[tid]) {
-    int rank = 0;
-    for (int j = 0; j < tid; ++j) rank += !is_parent[j];
-    int pos = __popcll(bits[tid]) - 1;
-    int* row = tb.retrieve + rank * VS_RETRIEVE_LD;
-    for (int j = 0; j < VS_RETRIEVE_LD; ++j) row[j] = -1;
-    int node = tid;
-    for (int j = pos; j >= 0; --j) {
-      row[j] = node;
-      node = parent_slot[node];
-    }
-    atomicAdd(&n_leaf_s, 1);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    st[VS_ST_N_LEAVES] = n_leaf_s;
-    st[VS_ST_MAX_DEPTH] = max_depth_s;
-  }
+  __shared__ TreeSmem sm;
+  tree_build_body(tb, st, sample_token_ptr, sample_token_host, sm, threadIdx.x, blockDim.x, BlockSync());
 }
 
-// ---- greedy accept (utils.py:438-451 + the gathers of :411, :516-526, :543-554) -------------------
-__global__ void accept_greedy_kernel(TreeBufs tb, int* st, const int* __restrict__ amax, int* out_rec) {
-  __shared__ int acc[64];
-  const int n_leaves = st[VS_ST_N_LEAVES];
-  const int max_depth = st[VS_ST_MAX_DEPTH];
-  const int tid = threadIdx.x;
-  if (tid < n_leaves) {
-    const int* row = tb.retrieve + tid * VS_RETRIEVE_LD;
-    int a = 0;
-    for (int d = 1; d < max_depth; ++d) {
-      int node = row[d];
-      if (node < 0) break;
-      if (tb.draft_tokens[node] != amax[row[d - 1]]) break;
-      ++a;
-    }
-    acc[tid] = a;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int best = 0, a = 0;
-    for (int l = 0; l < n_leaves; ++l)
-      if (acc[l] > a) { a = acc[l]; best = l; }          // first maximum, 0 when nothing is accepted
-    const int* row = tb.retrieve + best * VS_RETRIEVE_LD;
-    const int prev = st[VS_ST_CUR_LEN];
-    st[VS_ST_PREV_LEN] = prev;
-    st[VS_ST_CUR_LEN] = prev + a + 1;
-    st[VS_ST_ACCEPT] = a;
-    st[VS_ST_BEST] = best;
-    const int next_tok = amax[row[a]];
-    st[VS_ST_NEXT_TOKEN] = next_tok;
-    st[VS_ST_M] = a + 1;
-    st[VS_ST_LAST_ROW] = a;
-    const int dpos = st[VS_ST_D_POS];
-    for (int j = 0; j < VS_MAX_ACCEPT; ++j) {
-      int jj = j <= a ? j : a;
-      int node = row[jj];
-      tb.sel[j] = node;                                   // tree slots of the accepted path (KV splice, hidden gather)
-      // draft stable-forward inputs: feature of token t pairs with token t+1 (cnets_ours.py:1084-1091)
-      tb.stable_ids[j] = j < a ? tb.draft_tokens[row[j + 1]] : next_tok;
-      tb.stable_pos[j] = dpos + j;
-    }
-    if (out_rec) {                                        // host-visible record of this cycle
-      out_rec[0] = a;
-      out_rec[1] = next_tok;
-      for (int j = 0; j < VS_MAX_ACCEPT; ++j) out_rec[2 + j] = j <= a ? tb.draft_tokens[row[j]] : -1;
-    }
-    st[VS_ST_CYCLE] += 1;
-  }
+__global__ void accept_greedy_kernel(TreeBufs tb, int* st, const int* amax, int* out_rec) {
+  __shared__ TreeSmem sm;
+  tree_accept_body(tb, st, amax, out_rec, sm, threadIdx.x, BlockSync());
 }
 
-// after the stable forward: the m = accept+1 new rows become part of the draft's stable KV
-__global__ void draft_commit_kernel(int* st) {
-  if (threadIdx.x == 0) {
-    int m = st[VS_ST_M];
-    st[VS_ST_D_LEN] += m;
-    st[VS_ST_D_POS] += m;
-  }
-}
+__global__ void draft_commit_kernel(int* st) { tree_commit_body(st, threadIdx.x); }
 
-// ---- KV splice (utils.py:529-541) -------------------------------------------------------------------
-struct SpliceArgs {
-  bf16* slab;               // [n_slabs][n_kv][max_pos][128]
-  long head_stride;         // max_pos * 128
-  const int* st;            // device state (prev_len, accept) or null
-  const int* sel_dev;       // device tree slots or null
-  int prev_len_host, n_host;
-  int sel_host[VS_MAX_ACCEPT];
-};
 __global__ void __launch_bounds__(128) kv_splice_kernel(SpliceArgs p) {
-  const int tid = threadIdx.x;
-  const int prev = p.st ? p.st[VS_ST_PREV_LEN] : p.prev_len_host;
-  const int n = p.st ? p.st[VS_ST_ACCEPT] + 1 : p.n_host;
-  bf16* base = p.slab + ((long)blockIdx.x * gridDim.y + blockIdx.y) * p.head_stride;
-  const int r = tid >> 4, ch = tid & 15;          // 8 rows x 16 chunks of 16 bytes
-  uint4 v = make_uint4(0, 0, 0, 0);
-  int src = 0;
-  bool act = r < n;
-  if (act) {
-    src = p.sel_dev ? p.sel_dev[r] : p.sel_host[r];
-    act = src != r;                                // row already in place
-    if (act) v = *reinterpret_cast<const uint4*>(base + (long)(prev + src) * 128 + ch * 8);
-  }
-  __syncthreads();                                 // gather everything before any overwrite (reference gathers into a temp)
-  if (act) *reinterpret_cast<uint4*>(base + (long)(prev + r) * 128 + ch * 8) = v;
+  kv_splice_item(p, (long)blockIdx.x * gridDim.y + blockIdx.y, threadIdx.x, BlockSync());
 }
 
 __global__ void set_state_kernel(int* st, int slot, int value) { st[slot] = value; }
@@ -270,8 +55,8 @@ cudaError_t launch_draft_expand(const TreeBufs& tb, int* st, int level, cudaStre
 cudaError_t launch_tree_build(const TreeBufs& tb, int* st, const int* sample_token_dev, int sample_token_host,
                               cudaStream_t s) {
   int n_sc = tb.top_k + tb.depth * tb.top_k * tb.top_k;
-  if (tb.total + 1 > 64 || tb.total > n_sc) return cudaErrorInvalidValue;
-  tree_build_kernel<<<1, 256, n_sc * (sizeof(unsigned long long) + sizeof(int)), s>>>(tb, st, sample_token_dev, sample_token_host);
+  if (tb.total + 1 > 64 || tb.total > n_sc || n_sc > TREE_MAX_SCORES) return cudaErrorInvalidValue;
+  tree_build_kernel<<<1, 256, 0, s>>>(tb, st, sample_token_dev, sample_token_host);
   count_launch();
   return cudaGetLastError();
 }

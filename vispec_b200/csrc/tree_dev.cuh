@@ -1,0 +1,263 @@
+// Device bodies of the integer steps of the draft-and-verify cycle: draft-tree expansion bookkeeping, tree build,
+// greedy token-accept, draft-KV commit and the KV-cache splice.  All state stays on the device (int32), so a whole
+// cycle runs without a host sync; the reference does these steps with .tolist()/.item() round trips and Python loops
+// (vispec/model/cnets_ours.py:1109-1238, vispec/model/utils.py:411,438-451,516-546).
+//
+// Each body is written for `nthreads` cooperating threads with a caller-supplied barrier, so that it runs both as a
+// stand-alone one-block kernel (tree.cu) and as a phase of the persistent program kernel (program.cu).
+//
+// Tie rule: wherever the reference calls torch.topk / argmax on values that can tie (bf16 log-probs), this library
+// picks (value descending, index ascending).  torch's own order at exact ties is implementation-defined and differs
+// between its CPU and CUDA kernels.
+#pragma once
+#include "kernels.h"
+#include "tree.h"
+
+namespace vs {
+
+constexpr int TREE_MAX_SCORES = 512;     // top_k + depth * top_k^2 <= 8 + 6 * 64
+
+struct TreeSmem {
+  unsigned long long keys[TREE_MAX_SCORES];
+  int selected[TREE_MAX_SCORES];
+  float cu[64];
+  int sel[8];
+  unsigned long long old_bits[8];
+  int sel_sorted[64];
+  int parent_slot[64];
+  unsigned long long bits[64];
+  int is_parent[64];
+  int acc[64];
+  int n_leaf, max_depth;
+};
+
+// ---- draft level 0: after the stable forward's log-softmax/top-k on the last valid row ------------
+// cnets_ours.py:1109-1123: scores = top-k log-probs, parents_list=[0], tree_mask = eye(top_k).
+__device__ __forceinline__ void tree_level0_body(const TreeBufs& tb, int* st, int tid) {
+  const int k = tb.top_k;
+  const int j = tid;
+  if (j < k) {
+    float v = tb.top_val[j];
+    int tok = tb.top_idx[j];
+    tb.scores_flat[j] = v;
+    tb.tokens_flat[j] = tok;
+    tb.frontier_scores[j] = v;
+    tb.frontier_ids[j] = tok;
+    tb.cs_index[j] = j;
+    tb.frontier_bits[j] = 1ull << j;
+    tb.gather_idx[j] = st[VS_ST_LAST_ROW];            // input_hidden = last_hidden repeated top_k times
+    tb.draft_pos_ids[j] = st[VS_ST_D_POS];            // all siblings share one position (cnets_ours.py:1128)
+  }
+  if (j == 0) tb.parents[0] = 0;
+}
+
+// ---- draft level i (0-based loop index of cnets_ours.py:1126-1165), after that level's forward ------
+// needs >= 64 threads
+template <class Sync>
+__device__ __forceinline__ void tree_expand_body(const TreeBufs& tb, int* st, int level, TreeSmem& sm, int tid, Sync sync) {
+  const int k = tb.top_k;
+  const int kk = k * k;
+  const int bias = 1 + kk * (level > 1 ? level - 1 : 0) + (level > 0 ? k : 0);
+  if (tid < k) {
+    tb.parents[1 + level * k + tid] = tb.cs_index[tid] + bias;       // uses the PREVIOUS selection
+    sm.old_bits[tid] = tb.frontier_bits[tid];
+  }
+  if (tid < kk) {
+    int r = tid / k;
+    float v = rbf(tb.top_val[tid] + tb.frontier_scores[r]);           // bf16 add (cnets_ours.py:1151)
+    sm.cu[tid] = v;
+    sm.keys[tid] = rank_key(v, (uint32_t)tid);
+    tb.scores_flat[k + level * kk + tid] = v;
+    tb.tokens_flat[k + level * kk + tid] = tb.top_idx[tid];
+  }
+  sync();
+  if (tid < kk) {
+    int rank = 0;
+    unsigned long long me = sm.keys[tid];
+    for (int i = 0; i < kk; ++i) rank += sm.keys[i] > me;
+    if (rank < k) sm.sel[rank] = tid;
+  }
+  sync();
+  if (tid < k) {
+    int ci = sm.sel[tid];
+    int out_id = ci / k;
+    tb.cs_index[tid] = ci;
+    tb.frontier_scores[tid] = sm.cu[ci];
+    tb.frontier_ids[tid] = tb.top_idx[ci];
+    tb.gather_idx[tid] = out_id;
+    // tree_mask = cat(tree_mask[:, :, out_ids], eye) (cnets_ours.py:1165): inherit the parent's row, add self
+    tb.frontier_bits[tid] = sm.old_bits[out_id] | (1ull << (k * (level + 1) + tid));
+    tb.draft_pos_ids[tid] = st[VS_ST_D_POS] + level + 1;
+  }
+}
+
+// ---- tree build (cnets_ours.py:1167-1238) ---------------------------------------------------------
+template <class Sync>
+__device__ __forceinline__ void tree_build_body(const TreeBufs& tb, int* st, const int* sample_token_ptr,
+                                                int sample_token_host, TreeSmem& sm, int tid, int nthreads, Sync sync) {
+  const int k = tb.top_k;
+  const int n_sc = k + tb.depth * k * k;
+  const int total = tb.total;                 // drafted nodes; tree has total+1 nodes
+  const int n = total + 1;
+
+  for (int i = tid; i < n_sc; i += nthreads) sm.keys[i] = rank_key(tb.scores_flat[i], (uint32_t)i);
+  if (tid < 64) sm.is_parent[tid] = 0;
+  if (tid == 0) { sm.n_leaf = 0; sm.max_depth = 0; }
+  sync();
+  // top-`total` by (score desc, index asc), then re-sorted by flat index (torch.sort of the indices)
+  for (int i = tid; i < n_sc; i += nthreads) {
+    unsigned long long me = sm.keys[i];
+    int rank = 0;
+    for (int j = 0; j < n_sc; ++j) rank += sm.keys[j] > me;
+    sm.selected[i] = rank < total;
+  }
+  sync();
+  for (int i = tid; i < n_sc; i += nthreads) {
+    if (!sm.selected[i]) continue;
+    int pos = 0;
+    for (int j = 0; j < i; ++j) pos += sm.selected[j];
+    sm.sel_sorted[pos] = i;
+  }
+  sync();
+  if (tid < total) {
+    int fi = sm.sel_sorted[tid];
+    tb.draft_tokens[tid + 1] = tb.tokens_flat[fi];
+    int dp = tb.parents[fi / k];                 // node id of the parent (0 = root, else flat index + 1)
+    int slot = 0;
+    if (dp != 0) {
+      int cnt = 0;                               // searchsorted(top_idx, dp - 1, left)
+      for (int j = 0; j < total; ++j) cnt += sm.sel_sorted[j] < dp - 1;
+      slot = cnt + 1;
+    }
+    sm.parent_slot[tid + 1] = slot;
+  }
+  if (tid == 0) {
+    tb.draft_tokens[0] = sample_token_ptr ? *sample_token_ptr : sample_token_host;
+    sm.parent_slot[0] = 0;
+  }
+  sync();
+  if (tid < n) {
+    unsigned long long b = 1ull;                 // column 0 (root) is visible to every node
+    int node = tid;
+    int guard = 0;
+    while (node != 0 && guard++ < 64) {
+      b |= 1ull << node;
+      node = sm.parent_slot[node];
+    }
+    sm.bits[tid] = b;
+    int pos = __popcll(b) - 1;
+    tb.tree_bits[tid] = b;
+    tb.tree_pos[tid] = pos;
+    tb.verify_pos[tid] = pos + st[VS_ST_CUR_LEN];
+    atomicMax(&sm.max_depth, pos + 1);
+    if (tid > 0) sm.is_parent[sm.parent_slot[tid]] = 1;
+  }
+  sync();
+  if (tid < n && !sm.is_parent[tid]) {
+    int rank = 0;
+    for (int j = 0; j < tid; ++j) rank += !sm.is_parent[j];
+    int pos = __popcll(sm.bits[tid]) - 1;
+    int* row = tb.retrieve + rank * VS_RETRIEVE_LD;
+    for (int j = 0; j < VS_RETRIEVE_LD; ++j) row[j] = -1;
+    int node = tid;
+    for (int j = pos; j >= 0; --j) {
+      row[j] = node;
+      node = sm.parent_slot[node];
+    }
+    atomicAdd(&sm.n_leaf, 1);
+  }
+  sync();
+  if (tid == 0) {
+    st[VS_ST_N_LEAVES] = sm.n_leaf;
+    st[VS_ST_MAX_DEPTH] = sm.max_depth;
+  }
+}
+
+// ---- greedy accept (utils.py:438-451 + the gathers of :411, :516-526, :543-554) -------------------
+// needs >= 64 threads
+template <class Sync>
+__device__ __forceinline__ void tree_accept_body(const TreeBufs& tb, int* st, const int* amax, int* out_rec,
+                                                 TreeSmem& sm, int tid, Sync sync) {
+  const int n_leaves = st[VS_ST_N_LEAVES];
+  const int max_depth = st[VS_ST_MAX_DEPTH];
+  if (tid < n_leaves) {
+    const int* row = tb.retrieve + tid * VS_RETRIEVE_LD;
+    int a = 0;
+    for (int d = 1; d < max_depth; ++d) {
+      int node = row[d];
+      if (node < 0) break;
+      if (tb.draft_tokens[node] != amax[row[d - 1]]) break;
+      ++a;
+    }
+    sm.acc[tid] = a;
+  }
+  sync();
+  if (tid == 0) {
+    int best = 0, a = 0;
+    for (int l = 0; l < n_leaves; ++l)
+      if (sm.acc[l] > a) { a = sm.acc[l]; best = l; }          // first maximum, 0 when nothing is accepted
+    const int* row = tb.retrieve + best * VS_RETRIEVE_LD;
+    const int prev = st[VS_ST_CUR_LEN];
+    st[VS_ST_PREV_LEN] = prev;
+    st[VS_ST_CUR_LEN] = prev + a + 1;
+    st[VS_ST_ACCEPT] = a;
+    st[VS_ST_BEST] = best;
+    const int next_tok = amax[row[a]];
+    st[VS_ST_NEXT_TOKEN] = next_tok;
+    st[VS_ST_M] = a + 1;
+    st[VS_ST_LAST_ROW] = a;
+    const int dpos = st[VS_ST_D_POS];
+    for (int j = 0; j < VS_MAX_ACCEPT; ++j) {
+      int jj = j <= a ? j : a;
+      int node = row[jj];
+      tb.sel[j] = node;                                   // tree slots of the accepted path (KV splice, hidden gather)
+      // draft stable-forward inputs: feature of token t pairs with token t+1 (cnets_ours.py:1084-1091)
+      tb.stable_ids[j] = j < a ? tb.draft_tokens[row[j + 1]] : next_tok;
+      tb.stable_pos[j] = dpos + j;
+    }
+    if (out_rec) {                                        // host-visible record of this cycle
+      out_rec[0] = a;
+      out_rec[1] = next_tok;
+      for (int j = 0; j < VS_MAX_ACCEPT; ++j) out_rec[2 + j] = j <= a ? tb.draft_tokens[row[j]] : -1;
+    }
+    st[VS_ST_CYCLE] += 1;
+  }
+}
+
+// after the stable forward: the m = accept+1 new rows become part of the draft's stable KV
+__device__ __forceinline__ void tree_commit_body(int* st, int tid) {
+  if (tid == 0) {
+    int m = st[VS_ST_M];
+    st[VS_ST_D_LEN] += m;
+    st[VS_ST_D_POS] += m;
+  }
+}
+
+// ---- KV splice (utils.py:529-541): one (slab, kv head) item per team of 128 threads ---------------------------
+struct SpliceArgs {
+  bf16* slab;               // [n_slabs][n_kv][max_pos][128]
+  long head_stride;         // max_pos * 128
+  const int* st;            // device state (prev_len, accept) or null
+  const int* sel_dev;       // device tree slots or null
+  int prev_len_host, n_host;
+  int sel_host[VS_MAX_ACCEPT];
+};
+template <class Sync>
+__device__ __forceinline__ void kv_splice_item(const SpliceArgs& p, long item, int tid, Sync sync) {
+  const int prev = p.st ? p.st[VS_ST_PREV_LEN] : p.prev_len_host;
+  const int n = p.st ? p.st[VS_ST_ACCEPT] + 1 : p.n_host;
+  bf16* base = p.slab + item * p.head_stride;
+  const int r = tid >> 4, ch = tid & 15;          // 8 rows x 16 chunks of 16 bytes
+  uint4 v = make_uint4(0, 0, 0, 0);
+  int src = 0;
+  bool act = r < n;
+  if (act) {
+    src = p.sel_dev ? p.sel_dev[r] : p.sel_host[r];
+    act = src != r;                                // row already in place
+    if (act) v = __ldcg(reinterpret_cast<const uint4*>(base + (long)(prev + src) * 128 + ch * 8));
+  }
+  sync();                                          // gather everything before any overwrite (reference gathers into a temp)
+  if (act) *reinterpret_cast<uint4*>(base + (long)(prev + r) * 128 + ch * 8) = v;
+}
+
+}  // namespace vs

@@ -13,12 +13,20 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import torch
 
 from . import _lib as L
+from .program import Program
+
+
+def use_programs() -> bool:
+    """The persistent program kernel (one launch per step) is the product path; VS_MULTI_KERNEL=1 selects the
+    one-launch-per-op path (same kernels' arithmetic, kept for A/B measurements and as a cross-check)."""
+    return os.environ.get("VS_MULTI_KERNEL", "0") != "1"
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -193,6 +201,23 @@ class TargetEngine:
         self.logits = torch.zeros(32, cfg.vocab, dtype=self.dtype, device=dev)
         self.amax = torch.zeros(32, dtype=torch.int32, device=dev)
         self._causal_pos = torch.zeros(32, dtype=torch.int32, device=dev)
+        # fixed staging buffers: programs bake their operand pointers in
+        self._v_ids = torch.zeros(32, dtype=torch.int32, device=dev)
+        self._v_pos = torch.zeros(32, dtype=torch.int32, device=dev)
+        self._v_bits = torch.zeros(32, dtype=torch.int64, device=dev)
+        self._verify_progs: Dict[tuple, Program] = {}
+
+    def _verify_program(self, T: int, has_bits: bool) -> Program:
+        key = (T, has_bits)
+        p = self._verify_progs.get(key)
+        if p is None:
+            p = Program(self.device)
+            p.add("verify_step", C.byref(self.c), C.byref(self.scratch.c), L.ptr(self._v_ids), L.ptr(self._v_pos),
+                  L.ptr(self._v_bits) if has_bits else None, T, L.ptr(self.state), L.ptr(self.hidden_out),
+                  L.ptr(self.logits), L.ptr(self.amax))
+            p.commit()
+            self._verify_progs[key] = p
+        return p
 
     # -- lengths -------------------------------------------------------------------------------------
     def set_len(self, n: int):
@@ -267,6 +292,13 @@ class TargetEngine:
     # -- decode / verify through the C ABI -----------------------------------------------------------------
     def verify(self, token_ids: torch.Tensor, pos_ids: torch.Tensor, bits: Optional[torch.Tensor], T: int):
         """vs_verify_step on T <= 32 tokens appended (uncommitted) at CUR_LEN.  token_ids / pos_ids int32 device."""
+        if use_programs():
+            self._v_ids[:T].copy_(token_ids[:T])
+            self._v_pos[:T].copy_(pos_ids[:T])
+            if bits is not None:
+                self._v_bits[:T].copy_(bits[:T])
+            self._verify_program(T, bits is not None).run()
+            return
         L.check(self.lib.vs_verify_step(C.byref(self.c), C.byref(self.scratch.c), L.ptr(token_ids), L.ptr(pos_ids),
                                         L.ptr(bits), T, L.ptr(self.state), L.ptr(self.hidden_out), L.ptr(self.logits),
                                         L.ptr(self.amax), _stream()), "vs_verify_step")
@@ -336,6 +368,8 @@ class DraftEngine:
         self.last_img_hidden = torch.zeros(1, H, dtype=self.dtype, device=dev)
         self._alloc_tree()
         self.state: Optional[torch.Tensor] = None       # shared with the target engine (bind_state)
+        self._prog_levels: Optional[Program] = None     # LM head + draft levels + tree build after the prefill
+        self._prog_tree: Optional[Program] = None       # stable forward of the accepted rows + the above
 
     def _layer_struct(self) -> L.Layer:
         return L.Layer(None, L.ptr(self.w_qkv), L.ptr(self.b_qkv), L.ptr(self.w_o), L.ptr(self.ln_post),
@@ -474,6 +508,15 @@ class DraftEngine:
         self.state[L.ST_LAST_ROW] = 0
         self.prefill_out = big.h[:n_c]                                      # kept for tests
         self.prefill_pos = pos[:n_c]
+        if use_programs():
+            self.state[L.ST_NEXT_TOKEN] = int(sample_token)
+            if self._prog_levels is None:
+                self._prog_levels = Program(dev)
+                self._prog_levels.add("draft_levels", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb),
+                                      L.ptr(self.state), 1, self.state.data_ptr() + 4 * L.ST_NEXT_TOKEN, 0)
+                self._prog_levels.commit()
+            self._prog_levels.run()
+            return
         L.check(lib.vs_draft_levels(C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state), 1,
                                     None, int(sample_token), st), "vs_draft_levels")
 
@@ -507,6 +550,13 @@ class DraftEngine:
         self.state[L.ST_M] = m
         self.state[L.ST_LAST_ROW] = m - 1
         self.state[L.ST_NEXT_TOKEN] = int(sample_token)
+        if use_programs():
+            if self._prog_tree is None:
+                self._prog_tree = Program(self.device)
+                self._prog_tree.add("draft_tree", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state))
+                self._prog_tree.commit()
+            self._prog_tree.run()
+            return
         L.check(self.lib.vs_draft_tree(C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state),
                                        _stream()), "vs_draft_tree")
 

@@ -19,7 +19,8 @@ from typing import Dict, Optional
 import torch
 
 from .. import _lib as L
-from ..engine import DraftConfig, TargetConfig, TargetEngine, _stream
+from ..engine import DraftConfig, TargetConfig, TargetEngine, _stream, use_programs
+from ..program import Program
 from .cnets_ours import Model
 from .configs import EConfig
 from .kv_cache import initialize_past_key_values
@@ -122,6 +123,16 @@ class SpecModel:
         self._rec_evt = [torch.cuda.Event() for _ in range(2)]
         self._dec_evt = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         self.last_decode_ms = 0.0
+        self._cycle_prog: Optional[Program] = None
+
+    def cycle_program(self, trace: bool = False, pf_ahead: Optional[int] = None) -> Program:
+        """The whole draft+verify cycle (spec_model_ours.py:484-547 loop body) as one persistent-kernel launch."""
+        eng_t, eng_d = self.base_model_engine, self.spec_layer.engine
+        p = Program(eng_t.device, pf_ahead=pf_ahead, trace=trace)
+        p.add("spec_cycle", C.byref(eng_t.c), C.byref(eng_t.scratch.c), C.byref(eng_d.c), C.byref(eng_d.scratch.c),
+              C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.kv), eng_t.kv_max, L.ptr(eng_t.hidden_out),
+              L.ptr(eng_t.logits), L.ptr(eng_t.amax), L.ptr(self._rec_dev[0]))
+        return p.commit()
 
     # -- construction ----------------------------------------------------------------------------------
     @classmethod
@@ -257,7 +268,16 @@ class SpecModel:
         st = _stream()
         lib = eng_t.lib
 
+        programs = use_programs()
+        if programs and self._cycle_prog is None:
+            self._cycle_prog = self.cycle_program()
+
         def launch(slot):
+            if programs:
+                self._cycle_prog.run(st)
+                self._rec_host[slot].copy_(self._rec_dev[0], non_blocking=True)
+                self._rec_evt[slot].record()
+                return
             L.check(lib.vs_spec_cycle(C.byref(eng_t.c), C.byref(eng_t.scratch.c), C.byref(eng_d.c),
                                       C.byref(eng_d.scratch.c), C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.kv),
                                       eng_t.kv_max, L.ptr(eng_t.hidden_out), L.ptr(eng_t.logits), L.ptr(eng_t.amax),
