@@ -279,6 +279,8 @@ size_t vs_program_workspace_bytes(vs_program* pg);
 int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* stream);   /* 256-byte aligned workspace */
 int vs_program_run(const vs_program* pg, void* stream);
 int vs_program_read_trace(const vs_program* pg, unsigned long long* out_ns, int cap);
+/* out[phase * grid + cta] = time at which the CTA finished its work items of the phase; returns the grid size */
+int vs_program_read_trace_cta(const vs_program* pg, unsigned long long* out_ns, int cap);
 
 int vs_program_add_linear(vs_program* pg, const vs_linear_args* a);
 int vs_program_add_rmsnorm(vs_program* pg, const void* x, int64_t ldx, const void* weight, void* y, int64_t ldy, int T,

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Per-phase timing of ONE draft+verify cycle of the persistent program kernel (BASELINE config-2 workload):
+%globaltimer stamps written by CTA 0 at the end of every phase (vs_program option "trace").  Prints the time per
+phase type and the phases of one target layer; `--json` dumps everything."""
+import argparse
+import collections
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import build_llava7b  # noqa: E402
+from vispec_b200 import _lib as L  # noqa: E402
+from vispec_b200.model import utils as vu  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--layers", type=int, default=32)
+ap.add_argument("--pf-ahead", type=int, default=None)
+ap.add_argument("--cycles", type=int, default=4)
+ap.add_argument("--json", default=None)
+args = ap.parse_args()
+
+model, ids, emb, mask = build_llava7b(device="cuda:0", seed=0, layers=args.layers)
+tt = model.spec_layer.total_tokens
+model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, max_new_tokens=8)          # warm-up, allocates the KV views
+model.spec_layer.reset_kv()
+model.current_length_data.zero_()
+vu.reset_tree_mode(model)
+vu.initialize_tree(ids, model, model.past_key_values, None, emb, None, image_mask=mask)
+torch.cuda.synchronize()
+prog = model.cycle_program(trace=True, pf_ahead=args.pf_ahead)
+types = prog.phase_types()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.cycles + 1)]
+ev[0].record()
+for i in range(args.cycles):
+    prog.run()
+    ev[i + 1].record()
+torch.cuda.synchronize()
+ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.cycles)]
+us = prog.read_trace_us()          # last cycle
+tot = collections.defaultdict(lambda: [0, 0.0])
+for t, d in zip(types, us):
+    tot[L.PHASE_NAMES[t]][0] += 1
+    tot[L.PHASE_NAMES[t]][1] += d
+total = sum(us)
+print(f"cycle launches (CUDA events): {['%.3f' % m for m in ms]} ms; traced phases: {len(types)}, sum {total / 1e3:.3f} ms")
+for k, (n, d) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+    print(f"  {k:16s} n={n:4d} total={d:9.1f} us  avg={d / n:7.2f} us  share={100 * d / total:5.1f}%")
+# one target layer in the middle of the verify step
+per_layer = 14
+start = 2 + 5 * per_layer if len(types) > 2 + 6 * per_layer else 0
+print("phases of one target layer:")
+for i in range(start, min(start + per_layer, len(types))):
+    print(f"  [{i}] {L.PHASE_NAMES[types[i]]:16s} {us[i]:8.2f} us")
+end, done = prog.read_trace_detail()
+print("per phase of that layer: work = slowest CTA's items-done minus previous barrier; sync = barrier end minus that")
+for i in range(start, min(start + per_layer, len(types))):
+    t0 = end[i - 1]
+    d = sorted(x - t0 for x in done[i])
+    print(f"  [{i}] {L.PHASE_NAMES[types[i]]:16s} work: min {d[0] / 1e3:6.2f} median {d[len(d) // 2] / 1e3:6.2f} "
+          f"max {d[-1] / 1e3:6.2f} us   sync {(end[i] - t0 - d[-1]) / 1e3:5.2f} us")
+if args.json:
+    json.dump({"types": types, "us": us, "cycle_ms": ms}, open(args.json, "w"))

@@ -18,9 +18,10 @@ VS_MAX_ACCEPT = 8
  ST_LAST_ROW, ST_CYCLE) = range(12)
 ST_SLOTS = 16
 EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_HEADS = range(4)
-(PH_NOP, PH_GEMM, PH_EPI, PH_NORM, PH_ROWS, PH_ATTN_S, PH_ATTN_PV, PH_ARGMAX, PH_LSM_TOPK, PH_TREE, PH_SPLICE) = range(11)
-PHASE_NAMES = ("nop", "gemm", "epilogue", "rmsnorm", "rows", "attn_scores", "attn_pv", "argmax", "logsoftmax_topk", "tree",
-               "kv_splice")
+(PH_NOP, PH_GEMM, PH_EPI, PH_NORM, PH_ROWS, PH_ATTN_S, PH_ATTN_PV, PH_ARGMAX, PH_LSM_STATS, PH_TREE, PH_SPLICE,
+ PH_LSM_CAND) = range(12)
+PHASE_NAMES = ("nop", "gemm", "epilogue", "rmsnorm", "rows", "attn_scores", "attn_pv", "argmax", "lsm_stats", "tree",
+               "kv_splice", "lsm_candidates")
 
 
 class LinearArgs(C.Structure):
@@ -126,6 +127,7 @@ _SIGS = {
     "vs_program_commit": (C.c_int, [c_vp, c_vp, C.c_size_t, c_vp]),
     "vs_program_run": (C.c_int, [c_vp, c_vp]),
     "vs_program_read_trace": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "vs_program_read_trace_cta": (C.c_int, [c_vp, c_vp, C.c_int]),
     "vs_program_add_linear": (C.c_int, [c_vp, C.POINTER(LinearArgs)]),
     "vs_program_add_rmsnorm": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_f32]),
     "vs_program_add_gather_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, C.c_int]),

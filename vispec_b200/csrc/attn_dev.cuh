@@ -77,7 +77,7 @@ __device__ __forceinline__ void attn_scores_item(const AttnArgs& p, AttnSmem& sm
   for (int i = 0; i < 4; ++i) {
     int q = (i >> 1) * 16 + g + (i & 1) * 8;
     qabs[i] = t0 + q;
-    qb[i] = (!p.causal && p.bits && q < tq_rows) ? p.bits[t0 + q] : 0ull;
+    qb[i] = (!p.causal && p.bits && q < tq_rows) ? __ldcg(p.bits + t0 + q) : 0ull;
   }
 
   const bf16* kbase = p.K + (long)kvh * p.kv_head_stride;

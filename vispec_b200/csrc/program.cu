@@ -33,350 +33,78 @@
 #include "../../include/vispec_b200.h"
 #include "attn_dev.cuh"
 #include "profile.h"
+#include "program_dev.cuh"
 #include "sm100.cuh"
 
 namespace vs {
 
 namespace {
 
-constexpr int PG_THREADS = 384;
-constexpr int PG_WORKERS = 256;
-constexpr int PG_TEAM = 128;
-constexpr int BM = 128, BK = 64, NS = 8;
+constexpr int BM = PG_BM, BK = PG_BK, NS = 8;
 constexpr int W_STAGE = BM * BK * 2;             // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;         // 4096
 constexpr int STAGE_BYTES = W_STAGE + X_STAGE;   // 20480 (multiple of 1024)
 constexpr int TEAM_SMEM = 25600;
-constexpr int BAR_OFF = NS * STAGE_BYTES + 2 * TEAM_SMEM;
+constexpr int PHASE_WORDS = (sizeof(Phase) + 3) / 4;
+constexpr int PHASE_SLOT = (sizeof(Phase) + 127) / 128 * 128;
+constexpr int PHBUF_OFF = NS * STAGE_BYTES + 2 * TEAM_SMEM;            // two phase descriptors (double buffer)
+constexpr int BAR_OFF = PHBUF_OFF + 2 * PHASE_SLOT;
 constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
+static_assert(PHASE_WORDS <= 2 * PG_WORKERS, "phase descriptor larger than two words per worker thread");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int TMEM_COLS = 64;
-constexpr int TILE_FLOATS = VS_TOK * BM;         // one partial tile: [32 tokens][128 rows] fp32
 static_assert(sizeof(AttnSmem) <= TEAM_SMEM, "team scratch too small for attention");
 static_assert(sizeof(TreeSmem) <= TEAM_SMEM, "team scratch too small for the tree ops");
-
-struct TeamSync {
-  int id;
-  __device__ __forceinline__ void operator()() const { named_bar_sync(id, PG_TEAM); }
-};
-struct WorkerSync {
-  __device__ __forceinline__ void operator()() const { named_bar_sync(1, PG_WORKERS); }
-};
-
-__device__ __forceinline__ long rng_lo(int b, long C, int G) { return (long)b * C / G; }
-
-__device__ __forceinline__ float ldcg_bf(const bf16* p) {
-  unsigned short u = __ldcg(reinterpret_cast<const unsigned short*>(p));
-  return __uint_as_float(((unsigned int)u) << 16);
-}
-__device__ __forceinline__ float bf_lo(unsigned int u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf_hi(unsigned int u) { return __uint_as_float(u & 0xffff0000u); }
-__device__ __forceinline__ unsigned int pack_bf2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<unsigned int*>(&v);
-}
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
-
-// ---------------------------------------------------------------------------------------------------------------
-// grid barrier (workers only): bar -> one thread: release fence, arrive, acquire-spin, fence -> bar
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target, int wtid) {
-  named_bar_sync(1, PG_WORKERS);
-  if (wtid == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    while (ld_acquire_u32(ctr) < target) {
-    }
-    __threadfence();
-  }
-  named_bar_sync(1, PG_WORKERS);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// PH_EPI: one weight-row tile (128 output features x T tokens) per team item
-// ---------------------------------------------------------------------------------------------------------------
-// Calls f(partial_tile_base) for every CTA that contributed k-chunks to `tile`, in increasing k order.
-template <class F>
-__device__ __forceinline__ void for_each_contributor(const Phase& ph, int tile, int G, F f) {
-  const long C = (long)ph.n_tiles * ph.nk;
-  const long k0 = (long)tile * ph.nk, k1 = k0 + ph.nk;
-  int b = (int)(k0 * G / C);
-  while (b > 0 && rng_lo(b, C, G) > k0) --b;
-  while (b + 1 < G && rng_lo(b + 1, C, G) <= k0) ++b;
-  for (; b < G; ++b) {
-    const long lo = rng_lo(b, C, G), hi = rng_lo(b + 1, C, G);
-    if (lo >= k1) break;
-    if (hi <= lo || hi <= k0) continue;
-    const int seg = tile - (int)(lo / ph.nk);
-    f(ph.partials + ((long)b * ph.maxseg + seg) * TILE_FLOATS);
-  }
-}
-
-__device__ __noinline__ void epi_store_resid(const Phase& ph, int tile, int G, int tt, float* red, TeamSync sync) {
-  const int T = ph.T;
-  float acc[VS_TOK];
-#pragma unroll
-  for (int t = 0; t < VS_TOK; ++t) acc[t] = 0.f;
-  for_each_contributor(ph, tile, G, [&](const float* P) {
-#pragma unroll
-    for (int t = 0; t < VS_TOK; ++t)
-      if (t < T) acc[t] += __ldcg(P + t * BM + tt);
-  });
-  const int n = tile * BM + tt;
-  const bool ok = n < ph.N;
-  const float bias = (ok && ph.bias) ? bf2f(ph.bias[n]) : 0.f;
-  const bool resid = ph.epi == EPI_RESID;
-  const int warp = tt >> 5, lane = tt & 31;
-#pragma unroll
-  for (int t = 0; t < VS_TOK; ++t) {
-    if (t < T) {                                                   // uniform across the team
-      float v = acc[t] + bias;
-      if (resid) {
-        float o = rbf(v);                                          // Linear output rounds to bf16 ...
-        v = (ok ? ldcg_bf(ph.R + (long)t * ph.ldr + n) : 0.f) + o; // ... then the residual add rounds again
-      }
-      bf16 y = f2bf(v);
-      if (ok) ph.Y[(long)t * ph.ldy + n] = y;
-      if (ph.ssq) {
-        float q = ok ? bf2f(y) * bf2f(y) : 0.f;
-        q = warp_sum(q);
-        if (lane == 0) red[warp * VS_TOK + t] = q;
-      }
-    }
-  }
-  if (ph.ssq) {
-    sync();
-    if (tt < T) ph.ssq[tile * VS_TOK + tt] = red[tt] + red[VS_TOK + tt] + red[2 * VS_TOK + tt] + red[3 * VS_TOK + tt];
-    sync();
-  }
-}
-
-__device__ __noinline__ void epi_swiglu(const Phase& ph, int tile, int G, int tt) {
-  // tile rows [0,64) = gate features j0..j0+63, rows [64,128) = the matching up features
-  const int T = ph.T;
-  const int r = tt & 63, t0 = (tt >> 6) * 16;
-  float g[16], u[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { g[i] = 0.f; u[i] = 0.f; }
-  for_each_contributor(ph, tile, G, [&](const float* P) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (t0 + i < T) {
-        g[i] += __ldcg(P + (t0 + i) * BM + r);
-        u[i] += __ldcg(P + (t0 + i) * BM + 64 + r);
-      }
-  });
-  const int j = tile * 64 + r;
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (t0 + i < T) {
-      float a = rbf(silu_f(rbf(g[i])));                            // act_fn(gate) rounds, then * up rounds
-      ph.Y[(long)(t0 + i) * ph.ldy + j] = f2bf(a * rbf(u[i]));
-    }
-}
-
-__device__ __noinline__ void epi_heads(const Phase& ph, int tile, int G, int tt) {
-  // one 128-row tile == one head of q | k | v; optional RoPE; q -> Qout, k/v -> KV rows in place
-  const int T = ph.T;
-  const int d = tt & 63, t0 = (tt >> 6) * 16;
-  float a1[16], a2[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
-  for_each_contributor(ph, tile, G, [&](const float* P) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (t0 + i < T) {
-        a1[i] += __ldcg(P + (t0 + i) * BM + d);
-        a2[i] += __ldcg(P + (t0 + i) * BM + 64 + d);
-      }
-  });
-  const bool is_q = tile < ph.n_q_tiles;
-  const bool is_k = !is_q && tile < ph.n_q_tiles + ph.n_k_tiles;
-  const int head = is_q ? tile : (is_k ? tile - ph.n_q_tiles : tile - ph.n_q_tiles - ph.n_k_tiles);
-  const int row_base = (ph.kv_row_base ? *((volatile const int*)ph.kv_row_base) : 0) + ph.kv_row_off;
-  const float b1 = ph.bias ? bf2f(ph.bias[tile * BM + d]) : 0.f;
-  const float b2 = ph.bias ? bf2f(ph.bias[tile * BM + 64 + d]) : 0.f;
-  const bool rope = ph.rope && (is_q || is_k);
-  bf16* dst = is_q ? ph.Qout + (long)head * ph.q_head_stride
-                   : (is_k ? ph.Kout : ph.Vout) + (long)head * ph.kv_head_stride + (long)row_base * 128;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int t = t0 + i;
-    if (t < T) {
-      float x1 = rbf(a1[i] + b1), x2 = rbf(a2[i] + b2);
-      float o1 = x1, o2 = x2;
-      if (rope) {                                                  // three bf16 roundings (cnets_ours.py:117-118)
-        const long pos = *((volatile const int*)(ph.pos_ids + t));
-        const float c1 = bf2f(ph.cos[pos * 128 + d]), s1 = bf2f(ph.sin[pos * 128 + d]);
-        const float c2 = bf2f(ph.cos[pos * 128 + 64 + d]), s2 = bf2f(ph.sin[pos * 128 + 64 + d]);
-        o1 = rbf(x1 * c1) + rbf(-x2 * s1);
-        o2 = rbf(x2 * c2) + rbf(x1 * s2);
-      }
-      dst[(long)t * 128 + d] = f2bf(o1);
-      dst[(long)t * 128 + 64 + d] = f2bf(o2);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// row phases (one token row per team item)
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void norm_row(const Phase& ph, int t, int tt, float* red, TeamSync sync) {
-  const bf16* x = ph.src + (long)t * ph.lds;
-  bf16* y = ph.dst + (long)t * ph.ldd;
-  const int H = ph.H;
-  float ss = 0.f;
-  if (ph.ssq_in) {
-    for (int i = 0; i < ph.ssq_tiles; ++i) ss += __ldcg(ph.ssq_in + i * VS_TOK + t);   // fixed order, same on every thread
-  } else {
-    for (int i = tt * 8; i < H; i += PG_TEAM * 8) {
-      uint4 v = __ldcg(reinterpret_cast<const uint4*>(x + i));
-      const unsigned int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a = bf_lo(w[j]), b = bf_hi(w[j]);
-        ss += a * a + b * b;
-      }
-    }
-    ss = warp_sum(ss);
-    sync();
-    if ((tt & 31) == 0) red[tt >> 5] = ss;
-    sync();
-    ss = red[0] + red[1] + red[2] + red[3];
-  }
-  const float rstd = 1.0f / sqrtf(ss / (float)H + ph.eps);
-  for (int i = tt * 8; i < H; i += PG_TEAM * 8) {
-    uint4 v = __ldcg(reinterpret_cast<const uint4*>(x + i));
-    uint4 wv = *reinterpret_cast<const uint4*>(ph.w + i);
-    const unsigned int xi[4] = {v.x, v.y, v.z, v.w};
-    const unsigned int wi[4] = {wv.x, wv.y, wv.z, wv.w};
-    unsigned int o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)   // weight * bf16(x * rstd): two bf16 roundings (cnets_ours.py:523-527)
-      o[j] = pack_bf2(bf_lo(wi[j]) * rbf(bf_lo(xi[j]) * rstd), bf_hi(wi[j]) * rbf(bf_hi(xi[j]) * rstd));
-    *reinterpret_cast<uint4*>(y + i) = make_uint4(o[0], o[1], o[2], o[3]);
-  }
-}
-
-__device__ __forceinline__ void copy_row(const Phase& ph, int t, int tt) {
-  int r = ph.broadcast ? 0 : (ph.idx ? *((volatile const int*)(ph.idx + t)) : t);
-  if (ph.n_src_rows > 0) r = min(max(r, 0), ph.n_src_rows - 1);
-  const uint4* s = reinterpret_cast<const uint4*>(ph.src + (long)r * ph.lds);
-  uint4* d = reinterpret_cast<uint4*>(ph.dst + (long)t * ph.ldd);
-  for (int i = tt; i < ph.H / 8; i += PG_TEAM) d[i] = __ldcg(s + i);
-}
-
-__device__ __forceinline__ unsigned long long team_max_u64(unsigned long long v, unsigned long long* red, int tt,
-                                                           TeamSync sync) {
-  v = warp_max_u64(v);
-  sync();
-  if ((tt & 31) == 0) red[tt >> 5] = v;
-  sync();
-  unsigned long long r = red[0];
-#pragma unroll
-  for (int i = 1; i < 4; ++i) r = red[i] > r ? red[i] : r;
-  return r;
-}
-__device__ __forceinline__ float team_max_f(float v, float* red, int tt, TeamSync sync) {
-  v = warp_max(v);
-  sync();
-  if ((tt & 31) == 0) red[tt >> 5] = v;
-  sync();
-  return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-}
-__device__ __forceinline__ float team_sum_f(float v, float* red, int tt, TeamSync sync) {
-  v = warp_sum(v);
-  sync();
-  if ((tt & 31) == 0) red[tt >> 5] = v;
-  sync();
-  return red[0] + red[1] + red[2] + red[3];
-}
-
-// visits the V logits of one row as (value, index); 16-byte loads when the row allows it
-template <class F>
-__device__ __forceinline__ void scan_row(const bf16* xr, int V, int tt, F f) {
-  if ((V & 7) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {
-    for (int i = tt * 8; i < V; i += PG_TEAM * 8) {
-      uint4 v = __ldcg(reinterpret_cast<const uint4*>(xr + i));
-      const unsigned int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f(bf_lo(w[j]), i + 2 * j);
-        f(bf_hi(w[j]), i + 2 * j + 1);
-      }
-    }
-  } else {
-    for (int i = tt; i < V; i += PG_TEAM) f(ldcg_bf(xr + i), i);
-  }
-}
-
-__device__ __noinline__ void argmax_row(const Phase& ph, int t, int tt, void* red, TeamSync sync) {
-  const bf16* xr = ph.logits + (long)t * ph.ldl;
-  unsigned long long best = 0ull;
-  scan_row(xr, ph.V, tt, [&](float v, int i) {
-    unsigned long long k = rank_key(v, (uint32_t)i);
-    best = k > best ? k : best;
-  });
-  best = team_max_u64(best, reinterpret_cast<unsigned long long*>(red), tt, sync);
-  if (tt == 0) ph.amax_out[t] = (int)key_index(best);
-}
-
-// lp = bf16((x - max) - log(sum exp(x - max))) in fp32 math, then the k best by (value desc, index asc), best first
-// (cnets_ours.py:1111-1115,1145-1148).
-__device__ __noinline__ void lsm_topk_row(const Phase& ph, int item, int tt, void* red, TeamSync sync) {
-  constexpr int KMAX = 8;
-  const int row = ph.row_sel ? *((volatile const int*)ph.row_sel) : item;
-  const bf16* xr = ph.logits + (long)row * ph.ldl;
-  const int V = ph.V;
-  float m = -INFINITY;
-  scan_row(xr, V, tt, [&](float v, int) { m = fmaxf(m, v); });
-  m = team_max_f(m, reinterpret_cast<float*>(red), tt, sync);
-  float s = 0.f;
-  scan_row(xr, V, tt, [&](float v, int) { s += expf(v - m); });
-  s = team_sum_f(s, reinterpret_cast<float*>(red), tt, sync);
-  const float lse = logf(s);
-  unsigned long long loc[KMAX];
-#pragma unroll
-  for (int j = 0; j < KMAX; ++j) loc[j] = 0ull;
-  scan_row(xr, V, tt, [&](float v, int i) {
-    float lp = rbf((v - m) - lse);
-    unsigned long long key = rank_key(lp, (uint32_t)i);
-    if (key > loc[KMAX - 1]) {
-      loc[KMAX - 1] = key;
-#pragma unroll
-      for (int j = KMAX - 1; j > 0; --j) {
-        if (loc[j] > loc[j - 1]) {
-          unsigned long long tmp = loc[j];
-          loc[j] = loc[j - 1];
-          loc[j - 1] = tmp;
-        }
-      }
-    }
-  });
-  for (int r = 0; r < ph.k; ++r) {
-    unsigned long long best = team_max_u64(loc[0], reinterpret_cast<unsigned long long*>(red), tt, sync);
-    if (loc[0] == best && best != 0ull) {     // keys are unique (index in the low word): exactly one owner pops
-#pragma unroll
-      for (int j = 0; j < KMAX - 1; ++j) loc[j] = loc[j + 1];
-      loc[KMAX - 1] = 0ull;
-    }
-    if (tt == 0) {
-      ph.top_val[item * ph.k + r] = key_value(best);
-      ph.top_idx[item * ph.k + r] = (int)key_index(best);
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void attn_s_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, TeamSync tsync) {
+  const AttnArgs& a = ph.attn;
+  const int n_ctx = a.n_ctx ? ld_vol(a.n_ctx) : a.n_ctx_host;
+  const int n_chunks = (n_ctx + a.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
+  const int n_items = a.n_heads * n_chunks;
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>(tsm);
+  for (int item = gteam; item < n_items; item += n_teams)
+    attn_scores_item(a, sm, item / n_chunks, 0, 1, item % n_chunks, true, tt, tsync);
+}
+__device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, TeamSync tsync) {
+  const AttnArgs& a = ph.attn;
+  const int n_items = a.n_heads * a.pv_splits;
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>(tsm);
+  for (int item = gteam; item < n_items; item += n_teams)
+    attn_pv_item(a, sm, item / a.pv_splits, 0, 1, item % a.pv_splits, a.pv_splits, tt, tsync);
+}
+__device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team_base) {
+  // the tree bodies read device state with plain loads: drop whatever this SM's L1 still holds from an earlier phase of
+  // this launch (gpu-scope fence = CCTL.IVALL) before anyone reads
+  if (wtid == 0) __threadfence();
+  named_bar_sync(1, PG_WORKERS);
+  TreeSmem& sm = *reinterpret_cast<TreeSmem*>(team_base);
+  if (ph.keys && (ph.tree_op == TREE_ACCEPT || ph.tree_op == TREE_MERGE_ARGMAX)) {
+    merge_argmax(ph, wtid);
+    named_bar_sync(1, PG_WORKERS);
+  }
+  if (ph.keys && (ph.tree_op == TREE_LEVEL0 || ph.tree_op == TREE_EXPAND || ph.tree_op == TREE_MERGE_TOPK))
+    merge_topk(ph, wtid, reinterpret_cast<unsigned long long*>(team_base), 2 * TEAM_SMEM / 8, WorkerSync());
+  if (ph.tree_op == TREE_LEVEL0) tree_level0_body(ph.tb, ph.state, wtid);
+  else if (ph.tree_op == TREE_EXPAND) tree_expand_body(ph.tb, ph.state, ph.level, sm, wtid, WorkerSync());
+  else if (ph.tree_op == TREE_BUILD)
+    tree_build_body(ph.tb, ph.state, ph.sample_token_dev, ph.sample_token_host, sm, wtid, PG_WORKERS, WorkerSync());
+  else if (ph.tree_op == TREE_ACCEPT) tree_accept_body(ph.tb, ph.state, ph.amax, ph.out_rec, sm, wtid, WorkerSync());
+  else if (ph.tree_op == TREE_COMMIT) tree_commit_body(ph.state, wtid);
+}
+
 struct GemmCursor {            // walks the GEMM phases of the program and this CTA's chunk range in each
   const Phase* phases;
+  const int* tables;
   int n_phases;
   int p;                       // current phase index (a PH_GEMM phase) or n_phases
-  long c, hi;                  // next chunk, end of this CTA's range
+  int c, hi;                   // next chunk, end of this CTA's range
   int nk;
   __device__ __forceinline__ void init(const ProgramHeader& h) {
     phases = h.phases;
+    tables = h.tables;
     n_phases = h.n_phases;
     p = -1;
     c = hi = 0;
@@ -386,9 +114,9 @@ struct GemmCursor {            // walks the GEMM phases of the program and this 
   __device__ __forceinline__ bool next_phase(int b, int G) {
     for (++p; p < n_phases; ++p) {
       if (phases[p].type != PH_GEMM) continue;
-      const long C = (long)phases[p].n_tiles * phases[p].nk;
-      c = rng_lo(b, C, G);
-      hi = rng_lo(b + 1, C, G);
+      const int2 r = *reinterpret_cast<const int2*>(tables + phases[p].range_off + 2 * b);
+      c = r.x;
+      hi = r.y;
       nk = phases[p].nk;
       if (c < hi) return true;
     }
@@ -443,7 +171,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       while (cur.next_phase(b, G)) {
         const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmW;
         int tile = (int)(cur.c / cur.nk), kc = (int)(cur.c % cur.nk);
-        for (long c = cur.c; c < cur.hi; ++c) {
+        for (int c = cur.c; c < cur.hi; ++c) {
           mbar_wait(&empty[stage], par ^ 1);
           mbar_expect_tx(&full_w[stage], W_STAGE);
           tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES, kc * BK, tile * BM, HINT_EVICT_FIRST);
@@ -460,10 +188,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       cur.init(hdr);
       int stage = 0, par = 0, acc = 0, acc_par = 0;
       while (cur.next_phase(b, G)) {
-        long c = cur.c;
-        int tile = (int)(c / cur.nk);
+        int c = cur.c;
+        int tile = c / cur.nk;
         while (c < cur.hi) {
-          const long seg_end = min(cur.hi, (long)(tile + 1) * cur.nk);
+          const int seg_end = min(cur.hi, (tile + 1) * cur.nk);
           mbar_wait(&tempty[acc], acc_par ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * 32;
@@ -496,11 +224,13 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       while (cur.next_phase(b, G)) {
         // the token tile is produced by earlier phases of this launch: wait until all of them completed everywhere
         const unsigned int need = (unsigned int)cur.p * (unsigned int)G;
-        while (ld_acquire_u32(hdr.counters) < need) __nanosleep(64);
+        // relaxed polling (no L1 invalidation storm); the tile itself is read by the TMA unit from L2, ordered behind the
+        // observed counter value by the proxy fence
+        while (ld_relaxed_u32(hdr.counters) < need) __nanosleep(64);
         fence_proxy_async();
         const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmX;
         int kc = (int)(cur.c % cur.nk);
-        for (long c = cur.c; c < cur.hi; ++c) {
+        for (int c = cur.c; c < cur.hi; ++c) {
           mbar_wait(&empty[stage], par ^ 1);
           mbar_expect_tx(&full_x[stage], X_STAGE);
           tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kc * BK, 0, HINT_EVICT_LAST);
@@ -518,7 +248,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       while (cur.next_phase(b, G)) {
         const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmW;
         int tile = (int)(cur.c / cur.nk), kc = (int)(cur.c % cur.nk);
-        for (long c = cur.c; c < cur.hi; ++c, ++idx) {
+        for (int c = cur.c; c < cur.hi; ++c, ++idx) {
           while (idx >= *w_issued + hdr.pf_ahead) __nanosleep(100);
           if (idx >= *w_issued + NS) tma_prefetch_2d(tm, kc * BK, tile * BM);   // not about to be loaded anyway
           if (++kc == cur.nk) { kc = 0; ++tile; }
@@ -534,14 +264,30 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     uint8_t* tsm = team_base + team * TEAM_SMEM;
     const int gteam = b * 2 + team, n_teams = 2 * G;
     int acc = 0, acc_par = 0;
+    // Phase descriptors are staged through shared memory: the words of phase p+1 are loaded while phase p runs and
+    // stored just before the barrier, so no phase starts with a chain of L2 round trips for its own arguments.
+    uint8_t* phbuf = smem + PHBUF_OFF;
+    {
+      const unsigned int* src = reinterpret_cast<const unsigned int*>(hdr.phases);
+      unsigned int* dst = reinterpret_cast<unsigned int*>(phbuf);
+      for (int i = wtid; i < PHASE_WORDS; i += PG_WORKERS) dst[i] = src[i];
+      named_bar_sync(1, PG_WORKERS);
+    }
     for (int p = 0; p < hdr.n_phases; ++p) {
-      const Phase& ph = hdr.phases[p];
+      const Phase& ph = *reinterpret_cast<const Phase*>(phbuf + (p & 1) * PHASE_SLOT);
+      unsigned int nxt0 = 0, nxt1 = 0;
+      const bool has_next = p + 1 < hdr.n_phases;
+      if (has_next) {
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(hdr.phases + p + 1);
+        if (wtid < PHASE_WORDS) nxt0 = src[wtid];
+        if (wtid + PG_WORKERS < PHASE_WORDS) nxt1 = src[wtid + PG_WORKERS];
+      }
       switch (ph.type) {
         case PH_GEMM: {
-          const long C = (long)ph.n_tiles * ph.nk;
-          const long lo = rng_lo(b, C, G), hi = rng_lo(b + 1, C, G);
+          const int2 rg = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
+          const int lo = rg.x, hi = rg.y;
           if (lo < hi) {
-            const int tile0 = (int)(lo / ph.nk), tile1 = (int)((hi - 1) / ph.nk);
+            const int tile0 = lo / ph.nk, tile1 = (hi - 1) / ph.nk;
             const int quarter = wwarp & 3, half = wwarp >> 2;
             for (int tile = tile0; tile <= tile1; ++tile) {
               mbar_wait(&tfull[acc], acc_par);
@@ -560,58 +306,28 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
             }
           }
         } break;
-        case PH_EPI: {
-          for (int item = gteam; item < ph.n_tiles; item += n_teams) {
-            if (ph.epi == EPI_SWIGLU) epi_swiglu(ph, item, G, tt);
-            else if (ph.epi == EPI_HEADS) epi_heads(ph, item, G, tt);
-            else epi_store_resid(ph, item, G, tt, reinterpret_cast<float*>(tsm), tsync);
-          }
-        } break;
-        case PH_NORM: {
-          for (int t = gteam; t < ph.T; t += n_teams) norm_row(ph, t, tt, reinterpret_cast<float*>(tsm), tsync);
-        } break;
-        case PH_ROWS: {
-          for (int t = gteam; t < ph.T; t += n_teams) copy_row(ph, t, tt);
-        } break;
-        case PH_ATTN_S: {
-          const AttnArgs& a = ph.attn;
-          const int n_ctx = a.n_ctx ? *((volatile const int*)a.n_ctx) : a.n_ctx_host;
-          const int n_chunks = (n_ctx + a.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
-          const int n_items = a.n_heads * n_chunks;
-          AttnSmem& sm = *reinterpret_cast<AttnSmem*>(tsm);
-          for (int item = gteam; item < n_items; item += n_teams)
-            attn_scores_item(a, sm, item / n_chunks, 0, 1, item % n_chunks, true, tt, tsync);
-        } break;
-        case PH_ATTN_PV: {
-          const AttnArgs& a = ph.attn;
-          const int n_items = a.n_heads * a.pv_splits;
-          AttnSmem& sm = *reinterpret_cast<AttnSmem*>(tsm);
-          for (int item = gteam; item < n_items; item += n_teams)
-            attn_pv_item(a, sm, item / a.pv_splits, 0, 1, item % a.pv_splits, a.pv_splits, tt, tsync);
-        } break;
-        case PH_ARGMAX: {
-          for (int t = gteam; t < ph.T; t += n_teams) argmax_row(ph, t, tt, tsm, tsync);
-        } break;
-        case PH_LSM_TOPK: {
-          for (int t = gteam; t < ph.T; t += n_teams) lsm_topk_row(ph, t, tt, tsm, tsync);
-        } break;
-        case PH_TREE: {
-          if (b == 0) {
-            TreeSmem& sm = *reinterpret_cast<TreeSmem*>(team_base);
-            named_bar_sync(1, PG_WORKERS);
-            if (ph.tree_op == TREE_LEVEL0) tree_level0_body(ph.tb, ph.state, wtid);
-            else if (ph.tree_op == TREE_EXPAND) tree_expand_body(ph.tb, ph.state, ph.level, sm, wtid, WorkerSync());
-            else if (ph.tree_op == TREE_BUILD)
-              tree_build_body(ph.tb, ph.state, ph.sample_token_dev, ph.sample_token_host, sm, wtid, PG_WORKERS, WorkerSync());
-            else if (ph.tree_op == TREE_ACCEPT) tree_accept_body(ph.tb, ph.state, ph.amax, ph.out_rec, sm, wtid, WorkerSync());
-            else if (ph.tree_op == TREE_COMMIT) tree_commit_body(ph.state, wtid);
-          }
-        } break;
+        case PH_EPI: epi_phase(ph, hdr.tables, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
+        case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
+        case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
+        case PH_ATTN_S: attn_s_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
+        case PH_ATTN_PV: attn_pv_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
+        case PH_ARGMAX: argmax_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
+        case PH_LSM_STATS: lsm_stats_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
+        case PH_LSM_CAND: lsm_cand_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
+        case PH_TREE:
+          if (b == 0) tree_phase(ph, wtid, team_base);
+          break;
         case PH_SPLICE: {
           for (long item = gteam; item < ph.n_items; item += n_teams) kv_splice_item(ph.splice, item, tt, tsync);
         } break;
         default: break;
       }
+      if (has_next) {
+        unsigned int* dst = reinterpret_cast<unsigned int*>(phbuf + ((p + 1) & 1) * PHASE_SLOT);
+        if (wtid < PHASE_WORDS) dst[wtid] = nxt0;
+        if (wtid + PG_WORKERS < PHASE_WORDS) dst[wtid + PG_WORKERS] = nxt1;
+      }
+      if (hdr.trace_cta && wtid == 0) hdr.trace_cta[(long)p * G + b] = global_timer();   // this CTA's items are done
       if (p + 1 < hdr.n_phases) grid_barrier(hdr.counters, (unsigned int)(p + 1) * (unsigned int)G, wtid);
       if (hdr.trace && b == 0 && wtid == 0) hdr.trace[p] = global_timer();
     }
@@ -648,15 +364,21 @@ struct vs_program {
   std::vector<vs::Phase> phases;
   struct MapReq { const void* ptr; long ld; int rows, cols, box_rows; };
   std::vector<MapReq> maps;
+  std::vector<int> tables;    // chunk ranges per CTA + contributor info per tile of every GEMM phase
   size_t partial_floats = 0;
   size_t ssq_floats = 0;
+  size_t keys_count = 0;      // u64 entries of the arg-max / top-k candidate buffer
+  size_t lstats_count = 0;    // float2 entries of the log-softmax slice statistics
   int grid = 0;
   int pf_ahead = 24;
+  int tpi_override = 0;       // experiments: force the tokens-per-epilogue-item choice
   bool committed = false;
   bool trace_on = false;
   // device workspace layout (set by commit)
   uint8_t* ws = nullptr;
-  size_t off_maps = 0, off_phases = 0, off_counters = 0, off_trace = 0, off_ssq = 0, off_partials = 0, total = 0;
+  size_t off_trace_cta = 0;
+  size_t off_tables = 0;
+  size_t off_maps = 0, off_phases = 0, off_counters = 0, off_trace = 0, off_ssq = 0, off_keys = 0, off_lstats = 0, off_partials = 0, total = 0;
   std::string err;
 };
 
@@ -705,12 +427,20 @@ void layout(vs_program* pg) {
   off = align_up(off + pg->maps.size() * sizeof(CUtensorMap), 256);
   pg->off_phases = off;
   off = align_up(off + pg->phases.size() * sizeof(Phase), 256);
+  pg->off_tables = off;
+  off = align_up(off + pg->tables.size() * sizeof(int), 256);
   pg->off_counters = off;
   off += 256;
   pg->off_trace = off;
   off = align_up(off + pg->phases.size() * sizeof(unsigned long long), 256);
+  pg->off_trace_cta = off;
+  if (pg->trace_on) off = align_up(off + pg->phases.size() * sizeof(unsigned long long) * (pg->grid > 0 ? pg->grid : device_sms()), 256);
   pg->off_ssq = off;
   off = align_up(off + pg->ssq_floats * sizeof(float), 256);
+  pg->off_keys = off;
+  off = align_up(off + pg->keys_count * sizeof(unsigned long long), 256);
+  pg->off_lstats = off;
+  off = align_up(off + pg->lstats_count * sizeof(float2), 256);
   pg->off_partials = off;
   off += pg->partial_floats * sizeof(float);
   pg->total = align_up(off, 256);
@@ -733,8 +463,30 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
   g.nk = a.K / BK;
   g.N = a.N;
   const long C = (long)g.n_tiles * g.nk;
+  if (C * G >= (1L << 31)) return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_linear", "matrix too large for 32-bit chunk ranges");
   const long per = (C + G - 1) / G;
   g.maxseg = (int)((per + g.nk - 1) / g.nk) + 1;
+  // stream-K partition: CTA b owns per (+1 for the first rem CTAs) consecutive (tile, k-chunk) pairs
+  {
+    const int per_lo = (int)(C / G), rem = (int)(C % G);
+    g.range_off = (int)pg->tables.size();
+    std::vector<int> lo(G + 1);
+    for (int b = 0; b <= G; ++b) lo[b] = b * per_lo + (b < rem ? b : rem);
+    for (int b = 0; b < G; ++b) { pg->tables.push_back(lo[b]); pg->tables.push_back(lo[b + 1]); }
+    while (pg->tables.size() % 4) pg->tables.push_back(0);
+    g.tab_off = (int)pg->tables.size();
+    int b0 = 0;
+    for (int tile = 0; tile < g.n_tiles; ++tile) {
+      const int k0 = tile * g.nk, k1 = k0 + g.nk;
+      while (lo[b0 + 1] <= k0) ++b0;                      // first CTA whose range reaches into the tile
+      int n = 0;
+      while (b0 + n < G && lo[b0 + n] < k1 && lo[b0 + n + 1] > lo[b0 + n]) ++n;
+      pg->tables.push_back(b0);
+      pg->tables.push_back(n);
+      pg->tables.push_back(tile - lo[b0] / g.nk);
+      pg->tables.push_back(0);
+    }
+  }
   g.tmW = add_map(pg, a.W, a.ldw, a.N, a.K, BM);
   g.tmX = add_map(pg, a.X, a.ldx, a.T, a.K, VS_TOK);
   const size_t need = (size_t)G * g.maxseg * TILE_FLOATS;
@@ -742,6 +494,11 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
   pg->phases.push_back(g);
   Phase e = g;
   e.type = PH_EPI;
+  // token rows per epilogue item: as fine as one round over the 2*G teams allows (short load chains per thread)
+  e.tpi = 16;
+  for (int tpi = 4; tpi <= 16; tpi *= 2)
+    if ((long)g.n_tiles * ((a.T + tpi - 1) / tpi) <= 2L * G) { e.tpi = tpi; break; }
+  if (pg->tpi_override) e.tpi = pg->tpi_override;
   e.epi = a.epi;
   e.bias = a.bias;
   e.Y = a.Y; e.ldy = a.ldy; e.R = a.R; e.ldr = a.ldr;
@@ -798,32 +555,68 @@ int prog_add_attention(vs_program* pg, const AttnArgs& a) {
   return VS_OK;
 }
 
-int prog_add_argmax(vs_program* pg, const bf16* logits, long ldl, int T, int V, int* out) {
+static int pick_slices(int V) {
+  int n = 16;
+  while ((long)n * 4096 < V) n *= 2;      // a slice is at most 4096 elements (SCAN_NV vectors per thread)
+  return n;
+}
+
+int prog_add_argmax(vs_program* pg, const bf16* logits, long ldl, int T, int V, int* out, MergeInfo* fuse) {
+  if (T < 1 || T > VS_TOK) return pfail(VS_ERR_INVALID, "vs_program_add_argmax_rows", "programs handle 1..32 rows");
+  if (V % 8 || ldl % 8 || (reinterpret_cast<uintptr_t>(logits) & 15))
+    return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_argmax_rows", "rows must be 16-byte aligned with V % 8 == 0");
+  const int ns = pick_slices(V);
+  if (ns > 64) return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_argmax_rows", "vocabulary too large");
   Phase ph = blank(PH_ARGMAX, T);
-  ph.logits = logits; ph.ldl = ldl; ph.V = V; ph.amax_out = out;
+  ph.logits = logits; ph.ldl = ldl; ph.V = V; ph.amax_out = out; ph.n_slices = ns; ph.keys = PROG_WS_KEYS;
   pg->phases.push_back(ph);
-  return VS_OK;
+  if ((size_t)T * ns > pg->keys_count) pg->keys_count = (size_t)T * ns;
+  MergeInfo mi = {T, ns, 0, nullptr, nullptr, out};
+  if (fuse) { *fuse = mi; return VS_OK; }
+  TreeBufs none;
+  memset(&none, 0, sizeof(none));
+  return prog_add_tree(pg, TREE_MERGE_ARGMAX, none, nullptr, 0, nullptr, nullptr, nullptr, 0, &mi);
 }
 
 int prog_add_lsm_topk(vs_program* pg, const bf16* logits, long ldl, int T, int V, int k, const int* row_sel, float* top_val,
-                      int* top_idx) {
+                      int* top_idx, MergeInfo* fuse) {
   if (k < 1 || k > 8) return pfail(VS_ERR_INVALID, "vs_program_add_logsoftmax_topk", "k must be in 1..8");
+  if (T < 1 || T > VS_TOK) return pfail(VS_ERR_INVALID, "vs_program_add_logsoftmax_topk", "programs handle 1..32 rows");
   if (row_sel && T != 1) return pfail(VS_ERR_INVALID, "vs_program_add_logsoftmax_topk", "row_sel selects exactly one row");
-  Phase ph = blank(PH_LSM_TOPK, T);
+  if (V % 8 || ldl % 8 || (reinterpret_cast<uintptr_t>(logits) & 15))
+    return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_logsoftmax_topk", "rows must be 16-byte aligned with V % 8 == 0");
+  const int ns = pick_slices(V);
+  if (ns > 64) return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_logsoftmax_topk", "vocabulary too large");
+  Phase ph = blank(PH_LSM_STATS, T);
   ph.logits = logits; ph.ldl = ldl; ph.V = V; ph.k = k; ph.row_sel = row_sel; ph.top_val = top_val; ph.top_idx = top_idx;
+  ph.n_slices = ns; ph.keys = PROG_WS_KEYS; ph.lstats = PROG_WS_LSTATS;
   pg->phases.push_back(ph);
-  return VS_OK;
+  ph.type = PH_LSM_CAND;
+  pg->phases.push_back(ph);
+  if ((size_t)T * ns * 8 > pg->keys_count) pg->keys_count = (size_t)T * ns * 8;
+  if ((size_t)T * ns > pg->lstats_count) pg->lstats_count = (size_t)T * ns;
+  MergeInfo mi = {T, ns, k, top_val, top_idx, nullptr};
+  if (fuse) { *fuse = mi; return VS_OK; }
+  TreeBufs none;
+  memset(&none, 0, sizeof(none));
+  return prog_add_tree(pg, TREE_MERGE_TOPK, none, nullptr, 0, nullptr, nullptr, nullptr, 0, &mi);
 }
 
 int prog_add_tree(vs_program* pg, int op, const TreeBufs& tb, int* state, int level, const int* amax, int* out_rec,
-                  const int* sample_token_dev, int sample_token_host) {
-  const int n_sc = tb.top_k + tb.depth * tb.top_k * tb.top_k;
-  if (tb.top_k < 1 || tb.top_k > 8 || tb.depth + 2 > VS_RETRIEVE_LD || tb.total + 1 > 64 || tb.total > n_sc ||
-      n_sc > TREE_MAX_SCORES)
-    return pfail(VS_ERR_INVALID, "vs_program_add_tree_op", "unsupported tree shape");
+                  const int* sample_token_dev, int sample_token_host, const MergeInfo* merge) {
+  if (op != TREE_MERGE_ARGMAX && op != TREE_MERGE_TOPK) {
+    const int n_sc = tb.top_k + tb.depth * tb.top_k * tb.top_k;
+    if (tb.top_k < 1 || tb.top_k > 8 || tb.depth + 2 > VS_RETRIEVE_LD || tb.total + 1 > 64 || tb.total > n_sc ||
+        n_sc > TREE_MAX_SCORES)
+      return pfail(VS_ERR_INVALID, "vs_program_add_tree_op", "unsupported tree shape");
+  }
   Phase ph = blank(PH_TREE, 0);
   ph.tree_op = op; ph.tb = tb; ph.state = state; ph.level = level; ph.amax = amax; ph.out_rec = out_rec;
   ph.sample_token_dev = sample_token_dev; ph.sample_token_host = sample_token_host;
+  if (merge) {
+    ph.T = merge->T; ph.n_slices = merge->n_slices; ph.k = merge->k; ph.keys = PROG_WS_KEYS;
+    ph.top_val = merge->top_val; ph.top_idx = merge->top_idx; ph.amax_out = merge->amax_out;
+  }
   pg->phases.push_back(ph);
   return VS_OK;
 }
@@ -880,6 +673,10 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   if (!pg || !name) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "null argument");
   if (!strcmp(name, "pf_ahead")) pg->pf_ahead = value;
   else if (!strcmp(name, "trace")) pg->trace_on = value != 0;
+  else if (!strcmp(name, "tpi")) {
+    if (value != 0 && value != 4 && value != 8 && value != 16) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "tpi must be 0, 4, 8 or 16");
+    pg->tpi_override = value;
+  }
   else if (!strcmp(name, "grid")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "grid must be set before adding phases");
     pg->grid = value;
@@ -918,12 +715,15 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
     if (r != CUDA_SUCCESS) return pfail(VS_ERR_CUDA, "vs_program_commit", "cuTensorMapEncodeTiled failed");
     memcpy(host.data() + pg->off_maps + i * sizeof(CUtensorMap), &tm, sizeof(tm));
   }
+  memcpy(host.data() + pg->off_tables, pg->tables.data(), pg->tables.size() * sizeof(int));
   float* partials = reinterpret_cast<float*>(pg->ws + pg->off_partials);
   for (size_t i = 0; i < pg->phases.size(); ++i) {
     Phase ph = pg->phases[i];
     if (ph.type == PH_GEMM || ph.type == PH_EPI) ph.partials = partials;
     if (ph.ssq == PROG_WS_SSQ) ph.ssq = reinterpret_cast<float*>(pg->ws + pg->off_ssq);
     if (ph.ssq_in == PROG_WS_SSQ) ph.ssq_in = reinterpret_cast<float*>(pg->ws + pg->off_ssq);
+    if (ph.keys == PROG_WS_KEYS) ph.keys = reinterpret_cast<unsigned long long*>(pg->ws + pg->off_keys);
+    if (ph.lstats == PROG_WS_LSTATS) ph.lstats = reinterpret_cast<float2*>(pg->ws + pg->off_lstats);
     memcpy(host.data() + pg->off_phases + i * sizeof(Phase), &ph, sizeof(Phase));
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -947,8 +747,10 @@ int vs_program_run(const vs_program* pg, void* stream) {
   h.phases = reinterpret_cast<const Phase*>(pg->ws + pg->off_phases);
   h.n_phases = (int)pg->phases.size();
   h.maps = reinterpret_cast<const CUtensorMap*>(pg->ws + pg->off_maps);
+  h.tables = reinterpret_cast<const int*>(pg->ws + pg->off_tables);
   h.counters = reinterpret_cast<unsigned int*>(pg->ws + pg->off_counters);
   h.trace = pg->trace_on ? reinterpret_cast<unsigned long long*>(pg->ws + pg->off_trace) : nullptr;
+  h.trace_cta = pg->trace_on ? reinterpret_cast<unsigned long long*>(pg->ws + pg->off_trace_cta) : nullptr;
   h.pf_ahead = pg->pf_ahead;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pg->grid);
@@ -975,6 +777,16 @@ int vs_program_read_trace(const vs_program* pg, unsigned long long* out, int cap
   if (cudaMemcpy(out, pg->ws + pg->off_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
     return pfail(VS_ERR_CUDA, "vs_program_read_trace", cudaGetErrorString(cudaGetLastError()));
   return n;
+}
+/* per-phase, per-CTA "items done" stamps (ns) of the last run: out[phase * grid + cta]; returns the grid size */
+int vs_program_read_trace_cta(const vs_program* pg, unsigned long long* out, int cap) {
+  using namespace vs;
+  if (!pg || !pg->committed || !pg->trace_on) return pfail(VS_ERR_INVALID, "vs_program_read_trace_cta", "trace not enabled");
+  long n = (long)pg->phases.size() * pg->grid;
+  if (n > cap) return pfail(VS_ERR_INVALID, "vs_program_read_trace_cta", "buffer too small");
+  if (cudaMemcpy(out, pg->ws + pg->off_trace_cta, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return pfail(VS_ERR_CUDA, "vs_program_read_trace_cta", cudaGetErrorString(cudaGetLastError()));
+  return pg->grid;
 }
 int vs_program_phase_types(const vs_program* pg, int32_t* out, int cap) {
   if (!pg) return 0;

@@ -19,13 +19,18 @@ enum PhaseType : int {
   PH_ROWS = 4,      // row gather / embedding lookup / broadcast
   PH_ATTN_S = 5,    // attention pass 1: masked scores + chunk statistics
   PH_ATTN_PV = 6,   // attention pass 2: softmax in the reference's rounding, P V, split reduction
-  PH_ARGMAX = 7,    // arg-max over the vocabulary per row
-  PH_LSM_TOPK = 8,  // bf16 log-softmax + top-k per row
-  PH_TREE = 9,      // integer tree bookkeeping (level0 / expand / build / accept / commit) on CTA 0
-  PH_SPLICE = 10    // KV-cache splice
+  PH_ARGMAX = 7,    // arg-max over the vocabulary: best key per (row, vocabulary slice); merged by the next tree phase
+  PH_LSM_STATS = 8, // bf16 log-softmax + top-k, step 1: (max, sum exp) per (row, slice)
+  PH_TREE = 9,      // integer tree bookkeeping (level0 / expand / build / accept / commit / merges) on CTA 0
+  PH_SPLICE = 10,   // KV-cache splice
+  PH_LSM_CAND = 11  // log-softmax + top-k, step 2: k best log-probs per (row, slice); merged by the next tree phase
 };
 
-enum TreeOp : int { TREE_LEVEL0 = 0, TREE_EXPAND = 1, TREE_BUILD = 2, TREE_ACCEPT = 3, TREE_COMMIT = 4 };
+enum TreeOp : int {
+  TREE_LEVEL0 = 0, TREE_EXPAND = 1, TREE_BUILD = 2, TREE_ACCEPT = 3, TREE_COMMIT = 4,
+  TREE_MERGE_ARGMAX = 5,   // only the merge of PH_ARGMAX keys -> amax_out
+  TREE_MERGE_TOPK = 6      // only the merge of PH_LSM_CAND keys -> top_val / top_idx
+};
 
 struct Phase {
   int type;
@@ -34,8 +39,10 @@ struct Phase {
   int tmW, tmX;               // tensor-map table indices
   int n_tiles, nk, N;         // ceil(N/128) weight-row tiles, K/64 chunks
   int maxseg;                 // partial tiles per CTA
+  int range_off, tab_off;     // offsets into the program's int tables: per-CTA chunk ranges, per-tile contributor info
   float* partials;            // [grid][maxseg][32 tokens][128 rows] fp32
   int epi;
+  int tpi;                    // PH_EPI: tokens per work item (4, 8 or 16)
   const bf16* bias;
   bf16* Y; long ldy;
   const bf16* R; long ldr;
@@ -57,6 +64,9 @@ struct Phase {
   // ---- PH_ARGMAX / PH_LSM_TOPK
   const bf16* logits; long ldl; int V; int k;
   const int* row_sel; float* top_val; int* top_idx; int* amax_out;
+  int n_slices;               // vocabulary slices per row
+  unsigned long long* keys;   // PH_ARGMAX: [T][n_slices]; PH_LSM_CAND: [T][n_slices][8]  (program workspace)
+  float2* lstats;             // PH_LSM_STATS: [T][n_slices] (max, sum exp)                 (program workspace)
   // ---- PH_TREE
   int tree_op, level;
   TreeBufs tb; int* state; const int* amax; int* out_rec; const int* sample_token_dev; int sample_token_host;
@@ -68,8 +78,10 @@ struct ProgramHeader {
   const Phase* phases;
   int n_phases;
   const CUtensorMap* maps;
+  const int* tables;               // host-computed chunk ranges / contributor tables of the GEMM phases
   unsigned int* counters;          // [0] grid barrier, [1] exit counter
   unsigned long long* trace;       // [n_phases] globaltimer at the end of each phase (CTA 0) or null
+  unsigned long long* trace_cta;   // [n_phases][grid] globaltimer when each CTA finished its items of the phase, or null
   int pf_ahead;                    // L2 prefetch distance in 16 KB weight chunks per CTA (0 = off)
 };
 
@@ -85,11 +97,16 @@ int prog_add_norm(vs_program* pg, const bf16* x, long ldx, const bf16* w, bf16* 
 int prog_add_rows(vs_program* pg, const bf16* src, long lds, const int* idx, int n_src_rows, int broadcast, bf16* dst,
                   long ldd, int T, int H);
 int prog_add_attention(vs_program* pg, const AttnArgs& a);
-int prog_add_argmax(vs_program* pg, const bf16* logits, long ldl, int T, int V, int* out);
+#define PROG_WS_KEYS (reinterpret_cast<unsigned long long*>(uintptr_t(1)))
+#define PROG_WS_LSTATS (reinterpret_cast<float2*>(uintptr_t(1)))
+// The vocabulary scans leave per-slice results in the workspace; the merge runs on CTA 0 either as its own tree phase
+// (`fuse` == null) or at the start of the tree phase that consumes the result (pass the MergeInfo to prog_add_tree).
+struct MergeInfo { int T, n_slices, k; float* top_val; int* top_idx; int* amax_out; };
+int prog_add_argmax(vs_program* pg, const bf16* logits, long ldl, int T, int V, int* out, MergeInfo* fuse);
 int prog_add_lsm_topk(vs_program* pg, const bf16* logits, long ldl, int T, int V, int k, const int* row_sel, float* top_val,
-                      int* top_idx);
+                      int* top_idx, MergeInfo* fuse);
 int prog_add_tree(vs_program* pg, int op, const TreeBufs& tb, int* state, int level, const int* amax, int* out_rec,
-                  const int* sample_token_dev, int sample_token_host);
+                  const int* sample_token_dev, int sample_token_host, const MergeInfo* merge);
 int prog_add_splice(vs_program* pg, bf16* slab, int n_slabs, int n_kv, long max_pos, const int* state, const int* sel_dev);
 int prog_fail(int code, const char* where, const char* what);
 }  // namespace vs

@@ -91,7 +91,8 @@ int decoder_layer(vs_program* pg, const vs_dims* d, const vs_layer* l, const vs_
 }
 
 int verify_step(vs_program* pg, const vs_target* t, const vs_scratch* s, const int32_t* token_ids, const int32_t* pos_ids,
-                const uint64_t* bits, int T, int32_t* state, void* hidden_out, void* logits, int32_t* amax) {
+                const uint64_t* bits, int T, int32_t* state, void* hidden_out, void* logits, int32_t* amax,
+                vs::MergeInfo* fuse_argmax) {
   REQUIRE(T >= 1 && T <= VS_TOK_BLOCK, "verify handles 1..32 tree tokens");
   const vs_dims* d = &t->dims;
   const int H = d->hidden, V = d->vocab;
@@ -102,7 +103,7 @@ int verify_step(vs_program* pg, const vs_target* t, const vs_scratch* s, const i
     RET(decoder_layer(pg, d, &t->layers[li], s, &t->rope, T, pos_ids, cur, 0, cur, 0, T, bits ? 0 : 1, bits, 1, &has_ssq));
   RET(vs::prog_add_norm(pg, B(s->h), H, B(t->norm), B(hidden_out), H, T, H, d->eps, has_ssq ? PROG_WS_SSQ : nullptr, H / 128));
   RET(linear(pg, B(hidden_out), H, B(t->lm_head), nullptr, T, V, H, vs::EPI_STORE, B(logits), V, nullptr, 0, nullptr));
-  if (amax) RET(vs::prog_add_argmax(pg, B(logits), V, T, V, amax));
+  if (amax) RET(vs::prog_add_argmax(pg, B(logits), V, T, V, amax, fuse_argmax));
   return VS_OK;
 }
 
@@ -130,25 +131,26 @@ int draft_levels(vs_program* pg, const vs_draft* dm, const vs_scratch* s, const 
   REQUIRE(k * (tb->depth + 1) <= 64, "draft tree mask is one 64-bit word per query");
   REQUIRE(head_rows >= 1 && head_rows <= VS_TOK_BLOCK, "bad head_rows");
   RET(linear(pg, B(s->h), H, B(dm->lm_head), nullptr, head_rows, V, H, vs::EPI_STORE, B(dm->logits), V, nullptr, 0, nullptr));
-  RET(vs::prog_add_lsm_topk(pg, B(dm->logits), V, 1, V, k, state + VS_ST_LAST_ROW, tb->top_val, tb->top_idx));
-  RET(vs::prog_add_tree(pg, vs::TREE_LEVEL0, *tb, state, 0, nullptr, nullptr, nullptr, 0));
+  vs::MergeInfo mi;
+  RET(vs::prog_add_lsm_topk(pg, B(dm->logits), V, 1, V, k, state + VS_ST_LAST_ROW, tb->top_val, tb->top_idx, &mi));
+  RET(vs::prog_add_tree(pg, vs::TREE_LEVEL0, *tb, state, 0, nullptr, nullptr, nullptr, 0, &mi));
   const int32_t* dlen = state + VS_ST_D_LEN;
   for (int i = 0; i < tb->depth; ++i) {
     RET(vs::prog_add_rows(pg, B(s->h), H, tb->gather_idx, VS_TOK_BLOCK, 0, B(dm->x1), 2L * H, k, H));
     RET(draft_forward(pg, dm, s, k, tb->frontier_ids, tb->draft_pos_ids, dlen, k * i, dlen, k * (i + 1), 0,
                       tb->frontier_bits));
     RET(linear(pg, B(s->h), H, B(dm->lm_head), nullptr, k, V, H, vs::EPI_STORE, B(dm->logits), V, nullptr, 0, nullptr));
-    RET(vs::prog_add_lsm_topk(pg, B(dm->logits), V, k, V, k, nullptr, tb->top_val, tb->top_idx));
-    RET(vs::prog_add_tree(pg, vs::TREE_EXPAND, *tb, state, i, nullptr, nullptr, nullptr, 0));
+    RET(vs::prog_add_lsm_topk(pg, B(dm->logits), V, k, V, k, nullptr, tb->top_val, tb->top_idx, &mi));
+    RET(vs::prog_add_tree(pg, vs::TREE_EXPAND, *tb, state, i, nullptr, nullptr, nullptr, 0, &mi));
   }
-  return vs::prog_add_tree(pg, vs::TREE_BUILD, *tb, state, 0, nullptr, nullptr, sample_token_dev, sample_token_host);
+  return vs::prog_add_tree(pg, vs::TREE_BUILD, *tb, state, 0, nullptr, nullptr, sample_token_dev, sample_token_host, nullptr);
 }
 
 int draft_tree(vs_program* pg, const vs_draft* dm, const vs_scratch* s, const vs_tree_bufs* tb, int32_t* state) {
   const int32_t* dlen = state + VS_ST_D_LEN;
   // stable forward on the (padded) accepted rows; rows >= VS_ST_M are scratch and never read back
   RET(draft_forward(pg, dm, s, VS_MAX_ACCEPT, tb->stable_ids, tb->stable_pos, dlen, 0, dlen, VS_MAX_ACCEPT, 1, nullptr));
-  RET(vs::prog_add_tree(pg, vs::TREE_COMMIT, *tb, state, 0, nullptr, nullptr, nullptr, 0));
+  RET(vs::prog_add_tree(pg, vs::TREE_COMMIT, *tb, state, 0, nullptr, nullptr, nullptr, 0, nullptr));
   return draft_levels(pg, dm, s, tb, state, VS_MAX_ACCEPT, state + VS_ST_NEXT_TOKEN, 0);
 }
 
@@ -181,12 +183,12 @@ int vs_program_add_broadcast_row(vs_program* pg, const void* row, void* dst, int
 }
 int vs_program_add_argmax_rows(vs_program* pg, const void* logits, int64_t ldl, int T, int V, int32_t* out) {
   REQUIRE(pg && logits && out, "null operand");
-  return vs::prog_add_argmax(pg, B(logits), ldl, T, V, out);
+  return vs::prog_add_argmax(pg, B(logits), ldl, T, V, out, nullptr);
 }
 int vs_program_add_logsoftmax_topk(vs_program* pg, const void* logits, int64_t ldl, int T, int V, int k,
                                    const int32_t* row_sel, float* top_val, int32_t* top_idx) {
   REQUIRE(pg && logits && top_val && top_idx, "null operand");
-  return vs::prog_add_lsm_topk(pg, B(logits), ldl, T, V, k, row_sel, top_val, top_idx);
+  return vs::prog_add_lsm_topk(pg, B(logits), ldl, T, V, k, row_sel, top_val, top_idx, nullptr);
 }
 int vs_program_add_attention(vs_program* pg, const vs_attn_args* a) {
   REQUIRE(pg && a && a->Q && a->K && a->V && a->O, "null operand");
@@ -202,21 +204,21 @@ int vs_program_add_attention(vs_program* pg, const vs_attn_args* a) {
 }
 int vs_program_add_draft_level0(vs_program* pg, const vs_tree_bufs* tb, int32_t* state) {
   REQUIRE(pg && tb && state, "null operand");
-  return vs::prog_add_tree(pg, vs::TREE_LEVEL0, *tb, state, 0, nullptr, nullptr, nullptr, 0);
+  return vs::prog_add_tree(pg, vs::TREE_LEVEL0, *tb, state, 0, nullptr, nullptr, nullptr, 0, nullptr);
 }
 int vs_program_add_draft_expand(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, int level) {
   REQUIRE(pg && tb && state, "null operand");
-  return vs::prog_add_tree(pg, vs::TREE_EXPAND, *tb, state, level, nullptr, nullptr, nullptr, 0);
+  return vs::prog_add_tree(pg, vs::TREE_EXPAND, *tb, state, level, nullptr, nullptr, nullptr, 0, nullptr);
 }
 int vs_program_add_tree_build(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, const int32_t* sample_token_dev,
                               int sample_token_host) {
   REQUIRE(pg && tb && state, "null operand");
-  return vs::prog_add_tree(pg, vs::TREE_BUILD, *tb, state, 0, nullptr, nullptr, sample_token_dev, sample_token_host);
+  return vs::prog_add_tree(pg, vs::TREE_BUILD, *tb, state, 0, nullptr, nullptr, sample_token_dev, sample_token_host, nullptr);
 }
 int vs_program_add_accept_greedy(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, const int32_t* amax,
                                  int32_t* out_rec) {
   REQUIRE(pg && tb && state && amax, "null operand");
-  return vs::prog_add_tree(pg, vs::TREE_ACCEPT, *tb, state, 0, amax, out_rec, nullptr, 0);
+  return vs::prog_add_tree(pg, vs::TREE_ACCEPT, *tb, state, 0, amax, out_rec, nullptr, 0, nullptr);
 }
 int vs_program_add_kv_splice(vs_program* pg, void* slab, int n_slabs, int n_kv, int64_t max_pos, const int32_t* state,
                              const int32_t* sel_dev) {
@@ -237,7 +239,7 @@ int vs_program_add_verify_step(vs_program* pg, const vs_target* t, const vs_scra
                                const int32_t* pos_ids, const uint64_t* bits, int T, int32_t* state, void* hidden_out,
                                void* logits, int32_t* amax) {
   REQUIRE(pg && t && s && token_ids && pos_ids && state && hidden_out && logits, "null operand");
-  return verify_step(pg, t, s, token_ids, pos_ids, bits, T, state, hidden_out, logits, amax);
+  return verify_step(pg, t, s, token_ids, pos_ids, bits, T, state, hidden_out, logits, amax, nullptr);
 }
 int vs_program_add_draft_forward(vs_program* pg, const vs_draft* dm, const vs_scratch* s, int T, const int32_t* ids,
                                  const int32_t* pos_ids, const int32_t* kv_row_base, int kv_row_off, const int32_t* n_ctx,
@@ -261,8 +263,9 @@ int vs_program_add_spec_cycle(vs_program* pg, const vs_target* t, const vs_scrat
   REQUIRE(pg && t && ts && dm && ds && tb && state && kv_slab && hidden_out && logits && amax, "null operand");
   const int T = tb->total + 1;
   REQUIRE(T <= VS_TOK_BLOCK, "tree larger than 32 nodes");
-  RET(verify_step(pg, t, ts, tb->draft_tokens, tb->verify_pos, tb->tree_bits, T, state, hidden_out, logits, amax));
-  RET(vs::prog_add_tree(pg, vs::TREE_ACCEPT, *tb, state, 0, amax, out_rec, nullptr, 0));
+  vs::MergeInfo mi;
+  RET(verify_step(pg, t, ts, tb->draft_tokens, tb->verify_pos, tb->tree_bits, T, state, hidden_out, logits, amax, &mi));
+  RET(vs::prog_add_tree(pg, vs::TREE_ACCEPT, *tb, state, 0, amax, out_rec, nullptr, 0, &mi));
   RET(vs::prog_add_splice(pg, B(kv_slab), 2 * t->dims.n_layers, t->dims.n_kv_heads, kv_max_pos, state, tb->sel));
   // accepted hidden states -> draft input rows (utils.py:543-546)
   RET(vs::prog_add_rows(pg, B(hidden_out), t->dims.hidden, tb->sel, VS_TOK_BLOCK, 0, B(dm->x1), 2L * dm->dims.hidden,

@@ -244,15 +244,15 @@ struct SpliceArgs {
 };
 template <class Sync>
 __device__ __forceinline__ void kv_splice_item(const SpliceArgs& p, long item, int tid, Sync sync) {
-  const int prev = p.st ? p.st[VS_ST_PREV_LEN] : p.prev_len_host;
-  const int n = p.st ? p.st[VS_ST_ACCEPT] + 1 : p.n_host;
+  const int prev = p.st ? __ldcg(p.st + VS_ST_PREV_LEN) : p.prev_len_host;
+  const int n = p.st ? __ldcg(p.st + VS_ST_ACCEPT) + 1 : p.n_host;
   bf16* base = p.slab + item * p.head_stride;
   const int r = tid >> 4, ch = tid & 15;          // 8 rows x 16 chunks of 16 bytes
   uint4 v = make_uint4(0, 0, 0, 0);
   int src = 0;
   bool act = r < n;
   if (act) {
-    src = p.sel_dev ? p.sel_dev[r] : p.sel_host[r];
+    src = p.sel_dev ? __ldcg(p.sel_dev + r) : p.sel_host[r];
     act = src != r;                                // row already in place
     if (act) v = __ldcg(reinterpret_cast<const uint4*>(base + (long)(prev + src) * 128 + ch * 8));
   }

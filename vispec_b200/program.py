@@ -78,3 +78,17 @@ class Program:
             L.pcheck(got, "vs_program_read_trace")
         st = list(buf)[:got]
         return [0.0] + [(st[i] - st[i - 1]) / 1e3 for i in range(1, len(st))]
+
+    def read_trace_detail(self):
+        """(end[p], done[p][cta]) in ns: `end` = barrier completion of phase p seen by CTA 0, `done` = when each CTA had
+        finished its own work items of phase p (before the barrier)."""
+        n = self.n_phases
+        buf = (C.c_ulonglong * n)()
+        L.pcheck(min(0, self.lib.vs_program_read_trace(self.h, buf, n)), "vs_program_read_trace")
+        cap = n * 4096
+        big = (C.c_ulonglong * cap)()
+        g = self.lib.vs_program_read_trace_cta(self.h, big, cap)
+        if g < 0:
+            L.pcheck(g, "vs_program_read_trace_cta")
+        done = [[big[p * g + b] for b in range(g)] for p in range(n)]
+        return list(buf), done
