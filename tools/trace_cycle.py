@@ -19,6 +19,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--layers", type=int, default=32)
 ap.add_argument("--pf-ahead", type=int, default=None)
 ap.add_argument("--cycles", type=int, default=4)
+ap.add_argument("--inflight", type=int, default=None)
+ap.add_argument("--brief", action="store_true")
 ap.add_argument("--json", default=None)
 args = ap.parse_args()
 
@@ -30,7 +32,7 @@ model.current_length_data.zero_()
 vu.reset_tree_mode(model)
 vu.initialize_tree(ids, model, model.past_key_values, None, emb, None, image_mask=mask)
 torch.cuda.synchronize()
-prog = model.cycle_program(trace=True, pf_ahead=args.pf_ahead)
+prog = model.cycle_program(trace=True, pf_ahead=args.pf_ahead, inflight=args.inflight)
 types = prog.phase_types()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.cycles + 1)]
 ev[0].record()
@@ -48,6 +50,8 @@ total = sum(us)
 print(f"cycle launches (CUDA events): {['%.3f' % m for m in ms]} ms; traced phases: {len(types)}, sum {total / 1e3:.3f} ms")
 for k, (n, d) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:16s} n={n:4d} total={d:9.1f} us  avg={d / n:7.2f} us  share={100 * d / total:5.1f}%")
+if args.brief:
+    sys.exit(0)
 # one target layer in the middle of the verify step
 per_layer = 14
 start = 2 + 5 * per_layer if len(types) > 2 + 6 * per_layer else 0
@@ -62,4 +66,4 @@ for i in range(start, min(start + per_layer, len(types))):
     print(f"  [{i}] {L.PHASE_NAMES[types[i]]:16s} work: min {d[0] / 1e3:6.2f} median {d[len(d) // 2] / 1e3:6.2f} "
           f"max {d[-1] / 1e3:6.2f} us   sync {(end[i] - t0 - d[-1]) / 1e3:5.2f} us")
 if args.json:
-    json.dump({"types": types, "us": us, "cycle_ms": ms}, open(args.json, "w"))
+    json.dump({"types": types, "us": us, "cycle_ms": ms, "end_ns": end, "done_ns": done}, open(args.json, "w"))

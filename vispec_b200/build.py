@@ -32,7 +32,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("VS_NVCC_EXTRA", "").split() + \
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

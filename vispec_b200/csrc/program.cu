@@ -44,22 +44,26 @@ constexpr int BM = PG_BM, BK = PG_BK, NS = 8;
 constexpr int W_STAGE = BM * BK * 2;             // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;         // 4096
 constexpr int STAGE_BYTES = W_STAGE + X_STAGE;   // 20480 (multiple of 1024)
-constexpr int TEAM_SMEM = 25600;
+constexpr int BIG_SMEM = 26112;                  // scratch of one attention team (AttnSmem); both together also stage the
+                                                 // tree ops and the top-k merge on CTA 0
+constexpr int TEAM_SMEM = 1024;                  // reduction scratch of one small team
+constexpr int TEAM_OFF = NS * STAGE_BYTES + PG_BIG_TEAMS * BIG_SMEM;
 constexpr int PHASE_WORDS = (sizeof(Phase) + 3) / 4;
 constexpr int PHASE_SLOT = (sizeof(Phase) + 127) / 128 * 128;
-constexpr int PHBUF_OFF = NS * STAGE_BYTES + 2 * TEAM_SMEM;            // two phase descriptors (double buffer)
+constexpr int PHBUF_OFF = TEAM_OFF + PG_TEAMS * TEAM_SMEM;             // two phase descriptors (double buffer)
 constexpr int BAR_OFF = PHBUF_OFF + 2 * PHASE_SLOT;
 constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
-static_assert(PHASE_WORDS <= 2 * PG_WORKERS, "phase descriptor larger than two words per worker thread");
+static_assert(PHASE_WORDS <= PG_WORKERS, "phase descriptor larger than one word per worker thread");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int TMEM_COLS = 64;
-static_assert(sizeof(AttnSmem) <= TEAM_SMEM, "team scratch too small for attention");
-static_assert(sizeof(TreeSmem) <= TEAM_SMEM, "team scratch too small for the tree ops");
+static_assert(sizeof(AttnSmem) <= BIG_SMEM, "team scratch too small for attention");
+static_assert(sizeof(TreeSmem) <= BIG_SMEM, "team scratch too small for the tree ops");
+static_assert(sizeof(ScanSmem) <= BIG_SMEM, "team scratch too small for the vocabulary scans");
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void attn_s_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, TeamSync tsync) {
+__device__ __noinline__ void attn_s_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, BigTeamSync tsync) {
   const AttnArgs& a = ph.attn;
   const int n_ctx = a.n_ctx ? ld_vol(a.n_ctx) : a.n_ctx_host;
   const int n_chunks = (n_ctx + a.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
@@ -68,7 +72,7 @@ __device__ __noinline__ void attn_s_phase(const Phase& ph, int gteam, int n_team
   for (int item = gteam; item < n_items; item += n_teams)
     attn_scores_item(a, sm, item / n_chunks, 0, 1, item % n_chunks, true, tt, tsync);
 }
-__device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, TeamSync tsync) {
+__device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, BigTeamSync tsync) {
   const AttnArgs& a = ph.attn;
   const int n_items = a.n_heads * a.pv_splits;
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(tsm);
@@ -86,7 +90,7 @@ __device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team
     named_bar_sync(1, PG_WORKERS);
   }
   if (ph.keys && (ph.tree_op == TREE_LEVEL0 || ph.tree_op == TREE_EXPAND || ph.tree_op == TREE_MERGE_TOPK))
-    merge_topk(ph, wtid, reinterpret_cast<unsigned long long*>(team_base), 2 * TEAM_SMEM / 8, WorkerSync());
+    merge_topk(ph, wtid, reinterpret_cast<unsigned long long*>(team_base), PG_BIG_TEAMS * BIG_SMEM / 8, WorkerSync());
   if (ph.tree_op == TREE_LEVEL0) tree_level0_body(ph.tb, ph.state, wtid);
   else if (ph.tree_op == TREE_EXPAND) tree_expand_body(ph.tb, ph.state, ph.level, sm, wtid, WorkerSync());
   else if (ph.tree_op == TREE_BUILD)
@@ -168,11 +172,19 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       GemmCursor cur;
       cur.init(hdr);
       int stage = 0, par = 0, issued = 0;
+      // `inflight`: at most this many stages issued but not yet landed.  The ring (NS stages) is the run-ahead buffer;
+      // the in-flight limit only bounds the depth of the memory-system queues, so that the latency-critical loads of
+      // the non-GEMM phases do not wait behind a whole ring of weight tiles.
+      const int inflight = hdr.inflight > 0 && hdr.inflight < NS ? hdr.inflight : NS;
+      int landed = 0;
       while (cur.next_phase(b, G)) {
         const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmW;
         int tile = (int)(cur.c / cur.nk), kc = (int)(cur.c % cur.nk);
         for (int c = cur.c; c < cur.hi; ++c) {
-          mbar_wait(&empty[stage], par ^ 1);
+          while (issued - landed >= inflight) {
+            if (mbar_try_wait(&full_w[landed % NS], (landed / NS) & 1)) ++landed;
+          }
+          mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
           mbar_expect_tx(&full_w[stage], W_STAGE);
           tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES, kc * BK, tile * BM, HINT_EVICT_FIRST);
           *w_issued = ++issued;
@@ -192,13 +204,13 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         int tile = c / cur.nk;
         while (c < cur.hi) {
           const int seg_end = min(cur.hi, (tile + 1) * cur.nk);
-          mbar_wait(&tempty[acc], acc_par ^ 1);
+          mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * 32;
           bool first = true;
           for (; c < seg_end; ++c) {
-            mbar_wait(&full_w[stage], par);
-            mbar_wait(&full_x[stage], par);
+            mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
+            mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
             tc_fence_after();
             const uint64_t da = make_desc(smem + stage * STAGE_BYTES);
             const uint64_t db = make_desc(smem + stage * STAGE_BYTES + W_STAGE);
@@ -231,7 +243,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmX;
         int kc = (int)(cur.c % cur.nk);
         for (int c = cur.c; c < cur.hi; ++c) {
-          mbar_wait(&empty[stage], par ^ 1);
+          mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
           mbar_expect_tx(&full_x[stage], X_STAGE);
           tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kc * BK, 0, HINT_EVICT_LAST);
           if (++stage == NS) { stage = 0; par ^= 1; }
@@ -257,12 +269,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     }
   } else {
     // ===================== workers (two teams of 128 threads) =====================
-    const int wtid = threadIdx.x - 4 * 32;          // 0..255
-    const int team = wtid >> 7, tt = wtid & 127;
-    const int wwarp = wtid >> 5;                    // 0..7
+    const int wtid = threadIdx.x - 4 * 32;          // 0..511
+    const int team = wtid >> 7, tt = wtid & 127;    // small team
+    const int bteam = wtid >> 8, btt = wtid & 255;  // attention team
+    const int wwarp = wtid >> 5;                    // 0..15
     const TeamSync tsync{2 + team};
-    uint8_t* tsm = team_base + team * TEAM_SMEM;
-    const int gteam = b * 2 + team, n_teams = 2 * G;
+    const BigTeamSync bsync{2 + PG_TEAMS + bteam};
+    uint8_t* tsm = smem + TEAM_OFF + team * TEAM_SMEM;
+    uint8_t* bsm = team_base + bteam * BIG_SMEM;
+    // work items are dealt CTA-first: item i runs on CTA i % G, so a phase with few items spreads over all SMs
+    const int gteam = team * G + b, n_teams = PG_TEAMS * G;
+    const int gbteam = bteam * G + b, n_bteams = PG_BIG_TEAMS * G;
     int acc = 0, acc_par = 0;
     // Phase descriptors are staged through shared memory: the words of phase p+1 are loaded while phase p runs and
     // stored just before the barrier, so no phase starts with a chain of L2 round trips for its own arguments.
@@ -275,45 +292,41 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     }
     for (int p = 0; p < hdr.n_phases; ++p) {
       const Phase& ph = *reinterpret_cast<const Phase*>(phbuf + (p & 1) * PHASE_SLOT);
-      unsigned int nxt0 = 0, nxt1 = 0;
+      unsigned int nxt0 = 0;
       const bool has_next = p + 1 < hdr.n_phases;
-      if (has_next) {
-        const unsigned int* src = reinterpret_cast<const unsigned int*>(hdr.phases + p + 1);
-        if (wtid < PHASE_WORDS) nxt0 = src[wtid];
-        if (wtid + PG_WORKERS < PHASE_WORDS) nxt1 = src[wtid + PG_WORKERS];
-      }
+      if (has_next && wtid < PHASE_WORDS) nxt0 = reinterpret_cast<const unsigned int*>(hdr.phases + p + 1)[wtid];
       switch (ph.type) {
         case PH_GEMM: {
           const int2 rg = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
           const int lo = rg.x, hi = rg.y;
           if (lo < hi) {
             const int tile0 = lo / ph.nk, tile1 = (hi - 1) / ph.nk;
-            const int quarter = wwarp & 3, half = wwarp >> 2;
+            const int quarter = wwarp & 3, cg = wwarp >> 2;       // TMEM lane quarter, group of 8 token columns
             for (int tile = tile0; tile <= tile1; ++tile) {
               mbar_wait(&tfull[acc], acc_par);
               tc_fence_after();
-              float v[16];
-              tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 32 + half * 16, v);
+              float v[8];
+              tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 32 + cg * 8, v);
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[acc]);
               acc ^= 1;
               if (acc == 0) acc_par ^= 1;
-              float* dst = ph.partials + ((long)b * ph.maxseg + (tile - tile0)) * TILE_FLOATS + (half * 16) * BM +
+              float* dst = ph.partials + ((long)b * ph.maxseg + (tile - tile0)) * TILE_FLOATS + (cg * 8) * BM +
                            quarter * 32 + lane;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) dst[i * BM] = v[i];
+              for (int i = 0; i < 8; ++i) dst[i * BM] = v[i];
             }
           }
         } break;
-        case PH_EPI: epi_phase(ph, hdr.tables, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
+        case PH_EPI: epi_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
-        case PH_ATTN_S: attn_s_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
-        case PH_ATTN_PV: attn_pv_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
-        case PH_ARGMAX: argmax_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
-        case PH_LSM_STATS: lsm_stats_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
-        case PH_LSM_CAND: lsm_cand_phase(ph, gteam, n_teams, tt, tsm, tsync); break;
+        case PH_ATTN_S: attn_s_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
+        case PH_ATTN_PV: attn_pv_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
+        case PH_ARGMAX: argmax_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
+        case PH_LSM_STATS: lsm_stats_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
+        case PH_LSM_CAND: lsm_cand_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_TREE:
           if (b == 0) tree_phase(ph, wtid, team_base);
           break;
@@ -322,14 +335,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         } break;
         default: break;
       }
-      if (has_next) {
-        unsigned int* dst = reinterpret_cast<unsigned int*>(phbuf + ((p + 1) & 1) * PHASE_SLOT);
-        if (wtid < PHASE_WORDS) dst[wtid] = nxt0;
-        if (wtid + PG_WORKERS < PHASE_WORDS) dst[wtid + PG_WORKERS] = nxt1;
-      }
+      if (has_next && wtid < PHASE_WORDS)
+        reinterpret_cast<unsigned int*>(phbuf + ((p + 1) & 1) * PHASE_SLOT)[wtid] = nxt0;
       if (hdr.trace_cta && wtid == 0) hdr.trace_cta[(long)p * G + b] = global_timer();   // this CTA's items are done
       if (p + 1 < hdr.n_phases) grid_barrier(hdr.counters, (unsigned int)(p + 1) * (unsigned int)G, wtid);
       if (hdr.trace && b == 0 && wtid == 0) hdr.trace[p] = global_timer();
+#ifdef VS_PROGRAM_CLK
+      if (b == 0 && wtid == 0) g_clk[32 + (p & 15)] = clock64();        // end of the barrier of phase p
+#endif
     }
     // leave the counters at zero for the next launch: the last CTA to get here resets them (every CTA has passed its
     // last barrier wait before it increments the exit counter)
@@ -371,7 +384,8 @@ struct vs_program {
   size_t lstats_count = 0;    // float2 entries of the log-softmax slice statistics
   int grid = 0;
   int pf_ahead = 24;
-  int tpi_override = 0;       // experiments: force the tokens-per-epilogue-item choice
+  int inflight = 0;           // weight stages in flight per SM (0 = the whole ring)
+  int spin_ns = 100;          // back-off of the single-lane role warps between barrier polls
   bool committed = false;
   bool trace_on = false;
   // device workspace layout (set by commit)
@@ -474,18 +488,12 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
     for (int b = 0; b <= G; ++b) lo[b] = b * per_lo + (b < rem ? b : rem);
     for (int b = 0; b < G; ++b) { pg->tables.push_back(lo[b]); pg->tables.push_back(lo[b + 1]); }
     while (pg->tables.size() % 4) pg->tables.push_back(0);
-    g.tab_off = (int)pg->tables.size();
-    int b0 = 0;
-    for (int tile = 0; tile < g.n_tiles; ++tile) {
-      const int k0 = tile * g.nk, k1 = k0 + g.nk;
-      while (lo[b0 + 1] <= k0) ++b0;                      // first CTA whose range reaches into the tile
-      int n = 0;
-      while (b0 + n < G && lo[b0 + n] < k1 && lo[b0 + n + 1] > lo[b0 + n]) ++n;
-      pg->tables.push_back(b0);
-      pg->tables.push_back(n);
-      pg->tables.push_back(tile - lo[b0] / g.nk);
-      pg->tables.push_back(0);
-    }
+    auto magic = [](long d) -> unsigned int { return d <= 1 ? 0u : (unsigned int)((1ull << 32) / (unsigned long long)d + 1ull); };
+    g.per_lo = per_lo;
+    g.rem = rem;
+    g.magic_per_hi = magic(per_lo + 1);
+    g.magic_per_lo = magic(per_lo);
+    g.magic_nk = magic(g.nk);
   }
   g.tmW = add_map(pg, a.W, a.ldw, a.N, a.K, BM);
   g.tmX = add_map(pg, a.X, a.ldx, a.T, a.K, VS_TOK);
@@ -494,11 +502,7 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
   pg->phases.push_back(g);
   Phase e = g;
   e.type = PH_EPI;
-  // token rows per epilogue item: as fine as one round over the 2*G teams allows (short load chains per thread)
-  e.tpi = 16;
-  for (int tpi = 4; tpi <= 16; tpi *= 2)
-    if ((long)g.n_tiles * ((a.T + tpi - 1) / tpi) <= 2L * G) { e.tpi = tpi; break; }
-  if (pg->tpi_override) e.tpi = pg->tpi_override;
+  e.tpi = EPI_TPI;
   e.epi = a.epi;
   e.bias = a.bias;
   e.Y = a.Y; e.ldy = a.ldy; e.R = a.R; e.ldr = a.ldr;
@@ -544,7 +548,7 @@ int prog_add_attention(vs_program* pg, const AttnArgs& a) {
   Phase s = blank(PH_ATTN_S, a.Tq);
   s.attn = a;
   // as many kv splits as give every team one (head, split) item, bounded by the caller's workspace
-  int sp = (2 * G) / (a.n_heads > 0 ? a.n_heads : 1);
+  int sp = (PG_BIG_TEAMS * G) / (a.n_heads > 0 ? a.n_heads : 1);
   if (sp < 1) sp = 1;
   if (sp > a.pv_splits) sp = a.pv_splits;
   s.attn.pv_splits = sp;
@@ -557,7 +561,7 @@ int prog_add_attention(vs_program* pg, const AttnArgs& a) {
 
 static int pick_slices(int V) {
   int n = 16;
-  while ((long)n * 4096 < V) n *= 2;      // a slice is at most 4096 elements (SCAN_NV vectors per thread)
+  while ((long)n * (SCAN_MAX - 8) < V) n *= 2;      // a slice must fit the team's staging buffer
   return n;
 }
 
@@ -660,6 +664,10 @@ int vs_program_create(vs_program** out) {
   *out = new vs_program();
   const char* e = getenv("VS_PF_AHEAD");
   if (e) (*out)->pf_ahead = atoi(e);
+  e = getenv("VS_INFLIGHT");
+  if (e) (*out)->inflight = atoi(e);
+  e = getenv("VS_SPIN_NS");
+  if (e) (*out)->spin_ns = atoi(e);
   return VS_OK;
 }
 
@@ -673,10 +681,9 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   if (!pg || !name) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "null argument");
   if (!strcmp(name, "pf_ahead")) pg->pf_ahead = value;
   else if (!strcmp(name, "trace")) pg->trace_on = value != 0;
-  else if (!strcmp(name, "tpi")) {
-    if (value != 0 && value != 4 && value != 8 && value != 16) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "tpi must be 0, 4, 8 or 16");
-    pg->tpi_override = value;
-  }
+  else if (!strcmp(name, "inflight")) pg->inflight = value;
+  else if (!strcmp(name, "spin_ns")) pg->spin_ns = value;
+
   else if (!strcmp(name, "grid")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "grid must be set before adding phases");
     pg->grid = value;
@@ -752,6 +759,8 @@ int vs_program_run(const vs_program* pg, void* stream) {
   h.trace = pg->trace_on ? reinterpret_cast<unsigned long long*>(pg->ws + pg->off_trace) : nullptr;
   h.trace_cta = pg->trace_on ? reinterpret_cast<unsigned long long*>(pg->ws + pg->off_trace_cta) : nullptr;
   h.pf_ahead = pg->pf_ahead;
+  h.inflight = pg->inflight;
+  h.spin_ns = pg->spin_ns;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pg->grid);
   cfg.blockDim = dim3(PG_THREADS);
@@ -787,6 +796,16 @@ int vs_program_read_trace_cta(const vs_program* pg, unsigned long long* out, int
   if (cudaMemcpy(out, pg->ws + pg->off_trace_cta, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
     return pfail(VS_ERR_CUDA, "vs_program_read_trace_cta", cudaGetErrorString(cudaGetLastError()));
   return pg->grid;
+}
+/* -DVS_PROGRAM_CLK builds only: the checkpoint clocks of program_dev.cuh (64 values); returns 0 when not compiled in */
+int vs_debug_clk(long long* out) {
+#ifdef VS_PROGRAM_CLK
+  cudaMemcpyFromSymbol(out, vs::g_clk, 64 * sizeof(long long));
+  return 64;
+#else
+  (void)out;
+  return 0;
+#endif
 }
 int vs_program_phase_types(const vs_program* pg, int32_t* out, int cap) {
   if (!pg) return 0;

@@ -39,10 +39,12 @@ struct Phase {
   int tmW, tmX;               // tensor-map table indices
   int n_tiles, nk, N;         // ceil(N/128) weight-row tiles, K/64 chunks
   int maxseg;                 // partial tiles per CTA
-  int range_off, tab_off;     // offsets into the program's int tables: per-CTA chunk ranges, per-tile contributor info
+  int range_off;              // offset into the program's int tables: per-CTA chunk ranges [lo, hi)
+  int per_lo, rem;            // balanced partition: CTA b owns per_lo (+1 if b < rem) consecutive chunks
+  unsigned int magic_per_hi, magic_per_lo, magic_nk;   // floor(2^32/d)+1 for d = per_lo+1, per_lo, nk (0 when d == 1)
   float* partials;            // [grid][maxseg][32 tokens][128 rows] fp32
   int epi;
-  int tpi;                    // PH_EPI: tokens per work item (4, 8 or 16)
+  int tpi;                    // PH_EPI: tokens per work item (4 or 8)
   const bf16* bias;
   bf16* Y; long ldy;
   const bf16* R; long ldr;
@@ -83,6 +85,8 @@ struct ProgramHeader {
   unsigned long long* trace;       // [n_phases] globaltimer at the end of each phase (CTA 0) or null
   unsigned long long* trace_cta;   // [n_phases][grid] globaltimer when each CTA finished its items of the phase, or null
   int pf_ahead;                    // L2 prefetch distance in 16 KB weight chunks per CTA (0 = off)
+  int inflight;                    // weight stages issued-but-not-landed per CTA (0 = whole ring)
+  unsigned int spin_ns;            // back-off of the role warps between barrier polls
 };
 
 // ---- host-side phase constructors (program.cu); the C API and the composite builders live in program_api.cu ----

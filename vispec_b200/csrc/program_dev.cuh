@@ -13,15 +13,25 @@
 
 namespace vs {
 
-constexpr int PG_THREADS = 384;
-constexpr int PG_WORKERS = 256;
-constexpr int PG_TEAM = 128;
+// 20 warps per CTA: 4 role warps (weight producer, MMA issuer, activation producer, L2 prefetcher) + 16 worker warps.
+// The non-GEMM phases are chains of dependent instructions on little data; with only 8 worker warps (2 per scheduler)
+// they ran at a fraction of the issue rate, 4 per scheduler hide most of the ALU / shared-memory latency.
+constexpr int PG_THREADS = 640;
+constexpr int PG_WORKERS = 512;
+constexpr int PG_TEAM = 128;          // small team: epilogue / norm / row / scan / splice items   (4 per CTA)
+constexpr int PG_BIG_TEAM = 256;      // attention team (attn_dev.cuh)                            (2 per CTA)
+constexpr int PG_TEAMS = PG_WORKERS / PG_TEAM;
+constexpr int PG_BIG_TEAMS = PG_WORKERS / PG_BIG_TEAM;
 constexpr int PG_BM = 128, PG_BK = 64;
 constexpr int TILE_FLOATS = VS_TOK * PG_BM;      // one partial tile: [32 tokens][128 rows] fp32
 
 struct TeamSync {
   int id;
   __device__ __forceinline__ void operator()() const { named_bar_sync(id, PG_TEAM); }
+};
+struct BigTeamSync {
+  int id;
+  __device__ __forceinline__ void operator()() const { named_bar_sync(id, PG_BIG_TEAM); }
 };
 struct WorkerSync {
   __device__ __forceinline__ void operator()() const { named_bar_sync(1, PG_WORKERS); }
@@ -41,7 +51,8 @@ __device__ __forceinline__ unsigned int pack_bf2(float a, float b) {
   return *reinterpret_cast<unsigned int*>(&v);
 }
 __device__ __forceinline__ float pg_silu(float x) { return x / (1.0f + expf(-x)); }
-__device__ __forceinline__ int ld_vol(const int* p) { return *((volatile const int*)p); }
+// device-state ints written earlier in this launch: L2 load, no volatile (a volatile load is also a scheduling barrier)
+__device__ __forceinline__ int ld_vol(const int* p) { return __ldcg(p); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // grid barrier (workers only): CTA barrier -> one thread: release-add, acquire-spin -> CTA barrier.
@@ -64,189 +75,191 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// PH_EPI: item = (weight-row tile, token group of TPI tokens)
+// PH_EPI: item = (weight-row tile, group of 8 tokens).  ONE code path for all epilogues (the kernel's code must stay
+// small enough to live in the instruction cache: every phase runs for a few microseconds only): thread = (column
+// c < 64 paired with column c + 64, half of the token group), so each thread reduces 2 columns x 4 tokens.
 // ---------------------------------------------------------------------------------------------------------------
-struct Contrib {
-  const float* base[8];     // partial tiles of up to 8 contributors, packed from index 0 (null beyond the count)
-  int next_c, count;
-};
-// contributors c0 .. c0+7 of `tile` (c0 = 0 on the first call; continue with next_c while next_c < count)
-__device__ __forceinline__ void contributors(const Phase& ph, const int* tables, int tile, int c0, Contrib& out) {
-  const int4 e = *reinterpret_cast<const int4*>(tables + ph.tab_off + 4 * tile);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int ci = c0 + c;
-    const long slot = (long)(e.x + ci) * ph.maxseg + (ci == 0 ? e.z : 0);
-    out.base[c] = ci < e.y ? ph.partials + slot * TILE_FLOATS : nullptr;
-  }
-  out.next_c = c0 + 8;
-  out.count = e.y;
-}
+// Optional checkpoint clocks (compile with -DVS_PROGRAM_CLK): thread 0 of team 0 on CTA 0 records clock64() at a few
+// points of its first work item of a phase; tools read them back with vs_debug_clk().
+#ifdef VS_PROGRAM_CLK
+__device__ long long g_clk[64];
+#define CLK_DECL const bool clk_on = blockIdx.x == 0 && tt == 0 && sync.id == 2
+#define CLK(i) do { if (clk_on) g_clk[i] = clock64(); } while (0)
+#else
+#define CLK_DECL
+#define CLK(i)
+#endif
 
-// sum over contributors (k order) of NC columns (col0 + 64 * j), tokens t0 .. t0+TPT-1 (t < T), into acc[j][]:
-// all loads of four contributors are issued before the first add
-template <int TPT, int NC>
-__device__ __forceinline__ void accumulate(const Contrib& cb, int col0, int t0, int T, float (&acc)[NC][TPT]) {
-#pragma unroll
-  for (int c0 = 0; c0 < 8; c0 += 4) {
-    if (!cb.base[c0]) break;                     // contributors are packed from index 0
-    float v[4][NC][TPT];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int j = 0; j < NC; ++j)
-#pragma unroll
-        for (int i = 0; i < TPT; ++i)
-          v[c][j][i] = (cb.base[c0 + c] && t0 + i < T) ? __ldcg(cb.base[c0 + c] + (t0 + i) * PG_BM + col0 + 64 * j) : 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int j = 0; j < NC; ++j)
-#pragma unroll
-        for (int i = 0; i < TPT; ++i) acc[j][i] += v[c][j][i];
-  }
-}
+constexpr int EPI_TPI = 8;     // tokens per item
+constexpr int EPI_TPT = 4;     // tokens per thread
 
-// STORE / RESID: thread = tile row (output feature), TPI tokens
-template <int TPI>
-__device__ __forceinline__ void epi_store_resid(const Phase& ph, const int* tables, int tile, int t0, int tt, float* red,
-                                                TeamSync sync) {
-  const int T = ph.T;
-  const int n = tile * PG_BM + tt;
-  const bool ok = n < ph.N;
-  const bool resid = ph.epi == EPI_RESID;
-  float acc[1][TPI], r[TPI];
-#pragma unroll
-  for (int i = 0; i < TPI; ++i) {
-    acc[0][i] = 0.f;
-    r[i] = (resid && ok && t0 + i < T) ? ldcg_bf(ph.R + (long)(t0 + i) * ph.ldr + n) : 0.f;
-  }
-  const float bias = (ok && ph.bias) ? bf2f(ph.bias[n]) : 0.f;
-  Contrib cb;
-  int c0 = 0;
-  do {
-    contributors(ph, tables, tile, c0, cb);
-    accumulate<TPI, 1>(cb, tt, t0, T, acc);
-    c0 = cb.next_c;
-  } while (c0 < cb.count);
-  const int warp = tt >> 5, lane = tt & 31;
-  if (ph.ssq) sync();                                              // previous item's readers of `red` are done
-#pragma unroll
-  for (int i = 0; i < TPI; ++i) {
-    if (t0 + i < T) {                                              // uniform across the team
-      float v = acc[0][i] + bias;
-      if (resid) v = r[i] + rbf(v);                                // Linear output rounds to bf16, then the add rounds again
-      bf16 y = f2bf(v);
-      if (ok) ph.Y[(long)(t0 + i) * ph.ldy + n] = y;
-      if (ph.ssq) {
-        float q = ok ? bf2f(y) * bf2f(y) : 0.f;
-        q = warp_sum(q);
-        if (lane == 0) red[warp * VS_TOK + i] = q;
-      }
-    }
-  }
-  if (ph.ssq) {
-    sync();
-    if (tt < TPI && t0 + tt < T)
-      ph.ssq[tile * VS_TOK + t0 + tt] = red[tt] + red[VS_TOK + tt] + red[2 * VS_TOK + tt] + red[3 * VS_TOK + tt];
-  }
+// q = k / d for k * d < 2^32, with magic = floor(2^32 / d) + 1 precomputed on the host (d == 1: magic == 0 -> q = k)
+__device__ __forceinline__ int fast_div(int k, unsigned int magic) {
+  return magic ? (int)__umulhi((unsigned int)k, magic) : k;
 }
+__device__ __forceinline__ float bf_bits(unsigned short u) { return __uint_as_float(((unsigned int)u) << 16); }
 
-// SWIGLU: tile rows [0,64) = gate features j0..j0+63, rows [64,128) = the matching up features.
-// thread = (feature r < 64, half of the token group)
-template <int TPI>
-__device__ __forceinline__ void epi_swiglu(const Phase& ph, const int* tables, int tile, int t0, int tt) {
-  constexpr int TPT = TPI / 2;
-  const int T = ph.T;
-  const int r = tt & 63, ts = t0 + (tt >> 6) * TPT;
-  float gu[2][TPT];
-#pragma unroll
-  for (int i = 0; i < TPT; ++i) { gu[0][i] = 0.f; gu[1][i] = 0.f; }
-  Contrib cb;
-  int c0 = 0;
-  do {
-    contributors(ph, tables, tile, c0, cb);
-    accumulate<TPT, 2>(cb, r, ts, T, gu);
-    c0 = cb.next_c;
-  } while (c0 < cb.count);
-  const int j = tile * 64 + r;
-#pragma unroll
-  for (int i = 0; i < TPT; ++i)
-    if (ts + i < T) {
-      float a = rbf(pg_silu(rbf(gu[0][i])));                       // act_fn(gate) rounds, then * up rounds
-      ph.Y[(long)(ts + i) * ph.ldy + j] = f2bf(a * rbf(gu[1][i]));
-    }
-}
-
-// HEADS: one 128-row tile == one head of q | k | v; optional RoPE; q -> Qout, k/v -> KV rows in place.
-// thread = (d < 64 paired with d + 64, half of the token group)
-template <int TPI>
-__device__ __forceinline__ void epi_heads(const Phase& ph, const int* tables, int tile, int t0, int tt) {
-  constexpr int TPT = TPI / 2;
-  const int T = ph.T;
-  const int d = tt & 63, ts = t0 + (tt >> 6) * TPT;
-  const bool is_q = tile < ph.n_q_tiles;
-  const bool is_k = !is_q && tile < ph.n_q_tiles + ph.n_k_tiles;
-  const bool rope = ph.rope && (is_q || is_k);
-  float a[2][TPT], c1[TPT], s1[TPT], c2[TPT], s2[TPT];
-#pragma unroll
-  for (int i = 0; i < TPT; ++i) {
-    a[0][i] = 0.f; a[1][i] = 0.f;
-    c1[i] = 1.f; s1[i] = 0.f; c2[i] = 1.f; s2[i] = 0.f;
-    if (rope && ts + i < T) {
-      const long pos = ld_vol(ph.pos_ids + ts + i);
-      c1[i] = bf2f(ph.cos[pos * 128 + d]); s1[i] = bf2f(ph.sin[pos * 128 + d]);
-      c2[i] = bf2f(ph.cos[pos * 128 + 64 + d]); s2[i] = bf2f(ph.sin[pos * 128 + 64 + d]);
-    }
-  }
-  const int row_base = (ph.kv_row_base ? ld_vol(ph.kv_row_base) : 0) + ph.kv_row_off;
-  const float b1 = ph.bias ? bf2f(ph.bias[tile * PG_BM + d]) : 0.f;
-  const float b2 = ph.bias ? bf2f(ph.bias[tile * PG_BM + 64 + d]) : 0.f;
-  Contrib cb;
-  int c0 = 0;
-  do {
-    contributors(ph, tables, tile, c0, cb);
-    accumulate<TPT, 2>(cb, d, ts, T, a);
-    c0 = cb.next_c;
-  } while (c0 < cb.count);
-  const int head = is_q ? tile : (is_k ? tile - ph.n_q_tiles : tile - ph.n_q_tiles - ph.n_k_tiles);
-  bf16* dst = is_q ? ph.Qout + (long)head * ph.q_head_stride
-                   : (is_k ? ph.Kout : ph.Vout) + (long)head * ph.kv_head_stride + (long)row_base * 128;
-#pragma unroll
-  for (int i = 0; i < TPT; ++i) {
-    const int t = ts + i;
-    if (t < T) {
-      const float x1 = rbf(a[0][i] + b1), x2 = rbf(a[1][i] + b2);
-      float o1 = x1, o2 = x2;
-      if (rope) {                                                  // three bf16 roundings (cnets_ours.py:117-118)
-        o1 = rbf(x1 * c1[i]) + rbf(-x2 * s1[i]);
-        o2 = rbf(x2 * c2[i]) + rbf(x1 * s2[i]);
-      }
-      dst[(long)t * 128 + d] = f2bf(o1);
-      dst[(long)t * 128 + 64 + d] = f2bf(o2);
-    }
-  }
-}
-
-template <int TPI>
-__device__ __forceinline__ void epi_item(const Phase& ph, const int* tables, int tile, int t0, int tt, float* red,
-                                         TeamSync sync) {
-  if (ph.epi == EPI_SWIGLU) epi_swiglu<TPI>(ph, tables, tile, t0, tt);
-  else if (ph.epi == EPI_HEADS) epi_heads<TPI>(ph, tables, tile, t0, tt);
-  else epi_store_resid<TPI>(ph, tables, tile, t0, tt, red, sync);
-}
-
-__device__ __noinline__ void epi_phase(const Phase& ph, const int* tables, int gteam, int n_teams, int tt, float* red,
-                                       TeamSync sync) {
-  const int tpi = ph.tpi;
-  const int groups = (ph.T + tpi - 1) / tpi;
+__device__ __noinline__ void epi_phase(const Phase& ph, int gteam, int n_teams, int tt, float* red, TeamSync sync) {
+  // everything an item needs from the descriptor, once (the descriptor lives in shared memory)
+  const int T = ph.T, N = ph.N, nk = ph.nk, maxseg = ph.maxseg, epi = ph.epi;
+  const int per_lo = ph.per_lo, rem = ph.rem;
+  const unsigned int m_hi = ph.magic_per_hi, m_lo = ph.magic_per_lo, m_nk = ph.magic_nk;
+  const float* partials = ph.partials;
+  const int groups = (T + EPI_TPI - 1) / EPI_TPI;      // 1..4
   const int n_items = ph.n_tiles * groups;
+  const int col = tt & 63, half = tt >> 6;
+  const int warp = tt >> 5, lane = tt & 31;
+  const bool resid = epi == EPI_RESID, heads = epi == EPI_HEADS;
+  const int big = rem * (per_lo + 1);                  // chunks owned by the first `rem` CTAs (one extra chunk each)
+  CLK_DECL;
+  CLK(0);
   for (int item = gteam; item < n_items; item += n_teams) {
-    const int tile = item / groups, t0 = (item % groups) * tpi;
-    if (tpi == 4) epi_item<4>(ph, tables, tile, t0, tt, red, sync);
-    else if (tpi == 8) epi_item<8>(ph, tables, tile, t0, tt, red, sync);
-    else epi_item<16>(ph, tables, tile, t0, tt, red, sync);
+    CLK(1);
+    const int tile = groups == 1 ? item : (groups == 2 ? item >> 1 : (groups == 4 ? item >> 2 : item / 3));
+    const int grp = item - tile * groups;
+    const int ts = grp * EPI_TPI + half * EPI_TPT;     // first token of this thread
+    // contributors of the tile: consecutive CTAs b0 .. b0+n-1; closed form of the balanced partition of program.cu
+    const int k0 = tile * nk, k1 = k0 + nk - 1;
+    const int b0 = k0 < big ? fast_div(k0, m_hi) : rem + fast_div(k0 - big, m_lo);
+    const int b1 = k1 < big ? fast_div(k1, m_hi) : rem + fast_div(k1 - big, m_lo);
+    const int n_c = b1 - b0 + 1;
+    const int seg0 = tile - fast_div(b0 * per_lo + min(b0, rem), m_nk);
+
+    // ---- all operand loads that do not depend on the reduction, issued before anything is consumed.  Indices are
+    // clamped instead of predicated so that the loads are plain back-to-back instructions.
+    unsigned short rraw[2][EPI_TPT];
+    bf16 csraw[4][EPI_TPT];
+    const bool is_q = tile < ph.n_q_tiles;
+    const bool is_k = !is_q && tile < ph.n_q_tiles + ph.n_k_tiles;
+    const bool rope = heads && ph.rope && (is_q || is_k);
+    if (resid) {
+      const bf16* R = ph.R;
+      const long ldr = ph.ldr;
+#pragma unroll
+      for (int i = 0; i < EPI_TPT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          rraw[j][i] = __ldcg(reinterpret_cast<const unsigned short*>(R + (long)min(ts + i, T - 1) * ldr +
+                                                                      min(tile * PG_BM + col + 64 * j, N - 1)));
+    }
+    if (rope) {
+      int pos[EPI_TPT];
+#pragma unroll
+      for (int i = 0; i < EPI_TPT; ++i) pos[i] = __ldcg(ph.pos_ids + min(ts + i, T - 1));
+#pragma unroll
+      for (int i = 0; i < EPI_TPT; ++i) {
+        csraw[0][i] = ph.cos[(long)pos[i] * 128 + col];      csraw[1][i] = ph.sin[(long)pos[i] * 128 + col];
+        csraw[2][i] = ph.cos[(long)pos[i] * 128 + 64 + col]; csraw[3][i] = ph.sin[(long)pos[i] * 128 + 64 + col];
+      }
+    }
+    CLK(2);
+    // ---- reduction over the contributors in k order; the 32 loads of four contributors are in flight together
+    float a[2][EPI_TPT];
+#pragma unroll
+    for (int i = 0; i < EPI_TPT; ++i) { a[0][i] = 0.f; a[1][i] = 0.f; }
+#pragma unroll 1
+    for (int c0 = 0; c0 < n_c; c0 += 4) {
+      float v[4][2][EPI_TPT];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ci = min(c0 + c, n_c - 1);                                   // clamped: always a valid tile
+        const float* base = partials + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS + ts * PG_BM + col;
+#pragma unroll
+        for (int i = 0; i < EPI_TPT; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + i * PG_BM + 64 * j);   // rows >= T hold stale finite data
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float keep = c0 + c < n_c ? 1.f : 0.f;
+#pragma unroll
+        for (int i = 0; i < EPI_TPT; ++i) {
+          a[0][i] += c0 + c < n_c ? v[c][0][i] : 0.f;
+          a[1][i] += c0 + c < n_c ? v[c][1][i] : 0.f;
+        }
+        (void)keep;
+      }
+    }
+
+    CLK(3);
+#ifdef VS_PROGRAM_CLK
+    if (clk_on) g_clk[20] = (long long)(a[0][0] + a[1][3]);       // consume: the loads have landed
+#endif
+    CLK(4);
+    if (epi == EPI_SWIGLU) {
+      // tile rows [0,64) = gate features j0..j0+63, rows [64,128) = the matching up features
+      bf16* Y = ph.Y;
+      const long ldy = ph.ldy;
+#pragma unroll
+      for (int i = 0; i < EPI_TPT; ++i)
+        if (ts + i < T) {
+          const float g = rbf(pg_silu(rbf(a[0][i])));                  // act_fn(gate) rounds, then * up rounds
+          Y[(long)(ts + i) * ldy + tile * 64 + col] = f2bf(g * rbf(a[1][i]));
+        }
+    } else if (heads) {
+      // one 128-row tile == one head of q | k | v; optional RoPE; q -> Qout, k/v -> KV rows in place
+      const int row_base = (ph.kv_row_base ? __ldcg(ph.kv_row_base) : 0) + ph.kv_row_off;
+      const float b1 = ph.bias ? bf2f(ph.bias[tile * PG_BM + col]) : 0.f;
+      const float b2 = ph.bias ? bf2f(ph.bias[tile * PG_BM + 64 + col]) : 0.f;
+      const int head = is_q ? tile : (is_k ? tile - ph.n_q_tiles : tile - ph.n_q_tiles - ph.n_k_tiles);
+      bf16* dst = is_q ? ph.Qout + (long)head * ph.q_head_stride
+                       : (is_k ? ph.Kout : ph.Vout) + (long)head * ph.kv_head_stride + (long)row_base * 128;
+#pragma unroll
+      for (int i = 0; i < EPI_TPT; ++i)
+        if (ts + i < T) {
+          const float x1 = rbf(a[0][i] + b1), x2 = rbf(a[1][i] + b2);
+          float o1 = x1, o2 = x2;
+          if (rope) {   // rotate-half RoPE with three bf16 roundings (cnets_ours.py:117-118)
+            o1 = rbf(x1 * bf2f(csraw[0][i])) + rbf(-x2 * bf2f(csraw[1][i]));
+            o2 = rbf(x2 * bf2f(csraw[2][i])) + rbf(x1 * bf2f(csraw[3][i]));
+          }
+          dst[(long)(ts + i) * 128 + col] = f2bf(o1);
+          dst[(long)(ts + i) * 128 + 64 + col] = f2bf(o2);
+        }
+    } else {
+      // STORE / RESID (+ per-tile sums of squares of the new rows for the RMSNorm that follows)
+      float bias[2];
+      bool ok[2];
+      bf16* Y = ph.Y;
+      const long ldy = ph.ldy;
+      float* ssq = ph.ssq;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = tile * PG_BM + col + 64 * j;
+        ok[j] = n < N;
+        bias[j] = ph.bias ? bf2f(ph.bias[min(n, N - 1)]) : 0.f;
+      }
+      if (ssq) sync();                                                 // previous item's readers of `red` are done
+#pragma unroll
+      for (int i = 0; i < EPI_TPT; ++i) {
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float v = a[j][i] + bias[j];
+          if (resid) v = bf_bits(rraw[j][i]) + rbf(v);                 // Linear output rounds to bf16, then the add rounds again
+          const bf16 y = f2bf(v);
+          if (ok[j] && ts + i < T) {
+            Y[(long)(ts + i) * ldy + tile * PG_BM + col + 64 * j] = y;
+            q += bf2f(y) * bf2f(y);
+          }
+        }
+        if (ssq) {
+          q = warp_sum(q);
+          if (lane == 0) red[warp * EPI_TPT + i] = q;
+        }
+      }
+      if (ssq) {
+        sync();
+        if (tt < EPI_TPI) {                                            // token tt of the group: warps 2*h, 2*h+1 hold its half
+          const int h = tt >> 2, i = tt & 3;
+          const int t = grp * EPI_TPI + tt;
+          if (t < T) ssq[tile * VS_TOK + t] = red[(2 * h) * EPI_TPT + i] + red[(2 * h + 1) * EPI_TPT + i];
+        }
+      }
+    }
+    CLK(5);
   }
+  CLK(6);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -256,36 +269,28 @@ __device__ __noinline__ void norm_phase(const Phase& ph, int gteam, int n_teams,
   const int H = ph.H;
   const int n_items = ph.T * 4;
   const int lane = tt & 31;
+  const int per_part = H / 32;                   // 16-byte vectors per quarter row
   for (int item = gteam; item < n_items; item += n_teams) {
     const int t = item >> 2, part = item & 3;
     const bf16* x = ph.src + (long)t * ph.lds;
     bf16* y = ph.dst + (long)t * ph.ldd;
-    // this thread's slice of the row: 16-byte vectors v = part * H/32 + tt + 128 * j
-    const int per_part = H / 32;                 // vectors per quarter
-    uint4 xv[2], wv[2];
-    int vi[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      vi[j] = tt + PG_TEAM * j;
-      const bool in = vi[j] < per_part;
-      const int e = (part * per_part + (in ? vi[j] : 0)) * 8;
-      xv[j] = in ? __ldcg(reinterpret_cast<const uint4*>(x + e)) : make_uint4(0, 0, 0, 0);
-      wv[j] = in ? *reinterpret_cast<const uint4*>(ph.w + e) : make_uint4(0, 0, 0, 0);
-    }
+    // first vector of this thread: in flight while the row statistics are gathered
+    const bool in0 = tt < per_part;
+    const int e0 = (part * per_part + (in0 ? tt : 0)) * 8;
+    uint4 x0 = in0 ? __ldcg(reinterpret_cast<const uint4*>(x + e0)) : make_uint4(0, 0, 0, 0);
+    uint4 w0 = in0 ? *reinterpret_cast<const uint4*>(ph.w + e0) : make_uint4(0, 0, 0, 0);
     float ss = 0.f;
     if (ph.ssq_in) {
       // per-tile sums of squares left by the residual epilogue: lane i sums tiles i, i+32, ... (fixed order)
       for (int i = lane; i < ph.ssq_tiles; i += 32) ss += __ldcg(ph.ssq_in + i * VS_TOK + t);
       ss = warp_sum(ss);
     } else {
+#pragma unroll 1
       for (int i = tt * 8; i < H; i += PG_TEAM * 8) {
-        uint4 v = __ldcg(reinterpret_cast<const uint4*>(x + i));
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(x + i));
         const unsigned int w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float a = bf_lo(w[j]), b = bf_hi(w[j]);
-          ss += a * a + b * b;
-        }
+        for (int j = 0; j < 4; ++j) ss += bf_lo(w[j]) * bf_lo(w[j]) + bf_hi(w[j]) * bf_hi(w[j]);
       }
       ss = warp_sum(ss);
       sync();
@@ -294,23 +299,21 @@ __device__ __noinline__ void norm_phase(const Phase& ph, int gteam, int n_teams,
       ss = red[0] + red[1] + red[2] + red[3];
     }
     const float rstd = 1.0f / sqrtf(ss / (float)H + ph.eps);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      for (int v = vi[j]; v < per_part; v += 2 * PG_TEAM) {        // first trip uses the preloaded vectors
-        const int e = (part * per_part + v) * 8;
-        uint4 xq = xv[j], wq = wv[j];
-        if (v != vi[j]) {
-          xq = __ldcg(reinterpret_cast<const uint4*>(x + e));
-          wq = *reinterpret_cast<const uint4*>(ph.w + e);
-        }
-        const unsigned int xi[4] = {xq.x, xq.y, xq.z, xq.w};
-        const unsigned int wi[4] = {wq.x, wq.y, wq.z, wq.w};
-        unsigned int o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)   // weight * bf16(x * rstd): two bf16 roundings (cnets_ours.py:523-527)
-          o[q] = pack_bf2(bf_lo(wi[q]) * rbf(bf_lo(xi[q]) * rstd), bf_hi(wi[q]) * rbf(bf_hi(xi[q]) * rstd));
-        *reinterpret_cast<uint4*>(y + e) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll 1
+    for (int v = tt; v < per_part; v += PG_TEAM) {
+      const int e = (part * per_part + v) * 8;
+      uint4 xq = x0, wq = w0;
+      if (v != tt) {
+        xq = __ldcg(reinterpret_cast<const uint4*>(x + e));
+        wq = *reinterpret_cast<const uint4*>(ph.w + e);
       }
+      const unsigned int xi[4] = {xq.x, xq.y, xq.z, xq.w};
+      const unsigned int wi[4] = {wq.x, wq.y, wq.z, wq.w};
+      unsigned int o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)   // weight * bf16(x * rstd): two bf16 roundings (cnets_ours.py:523-527)
+        o[q] = pack_bf2(bf_lo(wi[q]) * rbf(bf_lo(xi[q]) * rstd), bf_hi(wi[q]) * rbf(bf_hi(xi[q]) * rstd));
+      *reinterpret_cast<uint4*>(y + e) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -325,6 +328,7 @@ __device__ __forceinline__ void rows_phase(const Phase& ph, int gteam, int n_tea
     const uint4* s = reinterpret_cast<const uint4*>(ph.src + (long)r * ph.lds);
     uint4* d = reinterpret_cast<uint4*>(ph.dst + (long)t * ph.ldd);
     const int nv = ph.H / 8;
+#pragma unroll 1
     for (int i0 = tt; i0 < nv; i0 += 4 * PG_TEAM) {
       uint4 v[4];
 #pragma unroll
@@ -338,123 +342,120 @@ __device__ __forceinline__ void rows_phase(const Phase& ph, int gteam, int n_tea
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// vocabulary scans: item = (row, slice of the vocabulary); the slices of a row are merged on CTA 0 (tree phase)
+// vocabulary scans: item = (row, slice of the vocabulary) on an attention-sized team of 256 threads; the slice is staged
+// in shared memory once and scanned by rolled loops (small code); the slices of a row are merged on CTA 0 (tree phase)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long team_max_u64(unsigned long long v, unsigned long long* red, int tt,
-                                                           TeamSync sync) {
-  v = warp_max_u64(v);
-  sync();
-  if ((tt & 31) == 0) red[tt >> 5] = v;
-  sync();
-  unsigned long long r = red[0];
-#pragma unroll
-  for (int i = 1; i < 4; ++i) r = red[i] > r ? red[i] : r;
-  return r;
-}
-__device__ __forceinline__ float team_max_f(float v, float* red, int tt, TeamSync sync) {
-  v = warp_max(v);
-  sync();
-  if ((tt & 31) == 0) red[tt >> 5] = v;
-  sync();
-  return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-}
-__device__ __forceinline__ float team_sum_f(float v, float* red, int tt, TeamSync sync) {
-  v = warp_sum(v);
-  sync();
-  if ((tt & 31) == 0) red[tt >> 5] = v;
-  sync();
-  return red[0] + red[1] + red[2] + red[3];
-}
+constexpr int SCAN_MAX = 8192;     // elements per slice (16 KB of the team's scratch)
 
-// slice s of V elements, aligned to 8: [lo, hi)
+struct ScanSmem {
+  bf16 x[SCAN_MAX];
+  unsigned long long red64[8];
+  float redf[8];
+};
+
 __device__ __forceinline__ void slice_bounds(int V, int n_slices, int s, int& lo, int& hi) {
   const int per = ((V + n_slices - 1) / n_slices + 7) & ~7;
   lo = min(V, s * per);
   hi = min(V, lo + per);
 }
-// loads the slice [lo, hi) of a row into registers: up to NV 16-byte vectors per thread (vector v = tt + 128 * j);
-// rows that are not 16-byte aligned or slices longer than NV * 1024 elements are not supported by the builder.
-template <int NV>
-__device__ __forceinline__ void load_slice(const bf16* xr, int lo, int hi, int tt, uint4 (&v)[NV]) {
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int e = lo + (tt + PG_TEAM * j) * 8;
-    v[j] = e < hi ? __ldcg(reinterpret_cast<const uint4*>(xr + e)) : make_uint4(0, 0, 0, 0);
-  }
+// stage logits[row][lo, hi) in shared memory (16-byte loads, all in flight together)
+__device__ __forceinline__ void stage_slice(ScanSmem& sm, const bf16* xr, int lo, int hi, int tid, BigTeamSync sync) {
+  sync();                                           // previous item done with the buffer
+  const int nv = (hi - lo + 7) / 8;
+#pragma unroll 1
+  for (int i = tid; i < nv; i += PG_BIG_TEAM)
+    *reinterpret_cast<uint4*>(&sm.x[i * 8]) = __ldcg(reinterpret_cast<const uint4*>(xr + lo + i * 8));
+  sync();
 }
-template <int NV, class F>
-__device__ __forceinline__ void visit_slice(const uint4 (&v)[NV], int lo, int hi, int tt, F f) {
+__device__ __forceinline__ unsigned long long bteam_max_u64(unsigned long long v, ScanSmem& sm, int tid, BigTeamSync sync) {
+  v = warp_max_u64(v);
+  sync();
+  if ((tid & 31) == 0) sm.red64[tid >> 5] = v;
+  sync();
+  unsigned long long r = sm.red64[0];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int e = lo + (tt + PG_TEAM * j) * 8;
-    if (e < hi) {
-      const unsigned int w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (e + 2 * q < hi) f(bf_lo(w[q]), e + 2 * q);
-        if (e + 2 * q + 1 < hi) f(bf_hi(w[q]), e + 2 * q + 1);
-      }
-    }
-  }
+  for (int i = 1; i < 8; ++i) r = sm.red64[i] > r ? sm.red64[i] : r;
+  return r;
 }
-constexpr int SCAN_NV = 4;     // slices of up to 4096 elements
+__device__ __forceinline__ float bteam_max_f(float v, ScanSmem& sm, int tid, BigTeamSync sync) {
+  v = warp_max(v);
+  sync();
+  if ((tid & 31) == 0) sm.redf[tid >> 5] = v;
+  sync();
+  float r = sm.redf[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = fmaxf(r, sm.redf[i]);
+  return r;
+}
+__device__ __forceinline__ float bteam_sum_f(float v, ScanSmem& sm, int tid, BigTeamSync sync) {
+  v = warp_sum(v);
+  sync();
+  if ((tid & 31) == 0) sm.redf[tid >> 5] = v;
+  sync();
+  float r = sm.redf[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r += sm.redf[i];      // fixed order
+  return r;
+}
 
 // PH_ARGMAX: keys[row][slice] = best (value desc, index asc) key of the slice
-__device__ __noinline__ void argmax_phase(const Phase& ph, int gteam, int n_teams, int tt, void* red, TeamSync sync) {
+__device__ __noinline__ void argmax_phase(const Phase& ph, int gteam, int n_teams, int tid, ScanSmem& sm, BigTeamSync sync) {
   const int n_items = ph.T * ph.n_slices;
   for (int item = gteam; item < n_items; item += n_teams) {
     const int t = item / ph.n_slices, s = item % ph.n_slices;
     int lo, hi;
     slice_bounds(ph.V, ph.n_slices, s, lo, hi);
-    uint4 v[SCAN_NV];
-    load_slice<SCAN_NV>(ph.logits + (long)t * ph.ldl, lo, hi, tt, v);
+    stage_slice(sm, ph.logits + (long)t * ph.ldl, lo, hi, tid, sync);
     unsigned long long best = 0ull;
-    visit_slice<SCAN_NV>(v, lo, hi, tt, [&](float x, int i) {
-      unsigned long long k = rank_key(x, (uint32_t)i);
+#pragma unroll 1
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) {
+      const unsigned long long k = rank_key(bf2f(sm.x[i]), (uint32_t)(lo + i));
       best = k > best ? k : best;
-    });
-    best = team_max_u64(best, reinterpret_cast<unsigned long long*>(red), tt, sync);
-    if (tt == 0) ph.keys[t * ph.n_slices + s] = best;
+    }
+    best = bteam_max_u64(best, sm, tid, sync);
+    if (tid == 0) ph.keys[t * ph.n_slices + s] = best;
   }
 }
 
 // PH_LSM_STATS: lstats[row][slice] = (max, sum exp(x - max)) of the slice
-__device__ __noinline__ void lsm_stats_phase(const Phase& ph, int gteam, int n_teams, int tt, void* red, TeamSync sync) {
+__device__ __noinline__ void lsm_stats_phase(const Phase& ph, int gteam, int n_teams, int tid, ScanSmem& sm,
+                                             BigTeamSync sync) {
   const int n_items = ph.T * ph.n_slices;
   for (int item = gteam; item < n_items; item += n_teams) {
     const int t = item / ph.n_slices, s = item % ph.n_slices;
     const int row = ph.row_sel ? ld_vol(ph.row_sel) : t;
     int lo, hi;
     slice_bounds(ph.V, ph.n_slices, s, lo, hi);
-    uint4 v[SCAN_NV];
-    load_slice<SCAN_NV>(ph.logits + (long)row * ph.ldl, lo, hi, tt, v);
+    stage_slice(sm, ph.logits + (long)row * ph.ldl, lo, hi, tid, sync);
     float m = -INFINITY;
-    visit_slice<SCAN_NV>(v, lo, hi, tt, [&](float x, int) { m = fmaxf(m, x); });
-    m = team_max_f(m, reinterpret_cast<float*>(red), tt, sync);
+#pragma unroll 1
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) m = fmaxf(m, bf2f(sm.x[i]));
+    m = bteam_max_f(m, sm, tid, sync);
     float l = 0.f;
-    visit_slice<SCAN_NV>(v, lo, hi, tt, [&](float x, int) { l += expf(x - m); });
-    l = team_sum_f(l, reinterpret_cast<float*>(red), tt, sync);
-    if (tt == 0) ph.lstats[t * ph.n_slices + s] = make_float2(m, l);
+#pragma unroll 1
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) l += expf(bf2f(sm.x[i]) - m);
+    l = bteam_sum_f(l, sm, tid, sync);
+    if (tid == 0) ph.lstats[t * ph.n_slices + s] = make_float2(m, l);
   }
 }
 
 // PH_LSM_CAND: lp = bf16((x - max) - log(sum exp(x - max))) with the row's global statistics, then the slice's k best
 // by (value desc, index asc) -> keys[row][slice][8]   (cnets_ours.py:1111-1115,1145-1148)
-__device__ __noinline__ void lsm_cand_phase(const Phase& ph, int gteam, int n_teams, int tt, void* red, TeamSync sync) {
+__device__ __noinline__ void lsm_cand_phase(const Phase& ph, int gteam, int n_teams, int tid, ScanSmem& sm,
+                                            BigTeamSync sync) {
   constexpr int KMAX = 8;
   const int n_items = ph.T * ph.n_slices;
+  const int lane = tid & 31;
   for (int item = gteam; item < n_items; item += n_teams) {
     const int t = item / ph.n_slices, s = item % ph.n_slices;
     const int row = ph.row_sel ? ld_vol(ph.row_sel) : t;
     int lo, hi;
     slice_bounds(ph.V, ph.n_slices, s, lo, hi);
-    uint4 v[SCAN_NV];
-    load_slice<SCAN_NV>(ph.logits + (long)row * ph.ldl, lo, hi, tt, v);
-    // global max / log-sum-exp from the slice statistics: lane i holds slices i, i+32 (fixed shuffle order, the same
-    // in every warp)
-    const int lane = tt & 31;
+    // global max / log-sum-exp from the slice statistics: lane i holds slices i, i+32 (fixed shuffle order, the same in
+    // every warp)
     float2 st0 = lane < ph.n_slices ? __ldcg(&ph.lstats[t * ph.n_slices + lane]) : make_float2(-INFINITY, 0.f);
     float2 st1 = lane + 32 < ph.n_slices ? __ldcg(&ph.lstats[t * ph.n_slices + lane + 32]) : make_float2(-INFINITY, 0.f);
+    stage_slice(sm, ph.logits + (long)row * ph.ldl, lo, hi, tid, sync);
     const float m = warp_max(fmaxf(st0.x, st1.x));
     float sum = 0.f;
     if (st0.x != -INFINITY) sum += st0.y * expf(st0.x - m);
@@ -464,32 +465,34 @@ __device__ __noinline__ void lsm_cand_phase(const Phase& ph, int gteam, int n_te
     unsigned long long loc[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) loc[j] = 0ull;
-    visit_slice<SCAN_NV>(v, lo, hi, tt, [&](float x, int i) {
-      float lp = rbf((x - m) - lse);
-      unsigned long long key = rank_key(lp, (uint32_t)i);
+#pragma unroll 1
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) {
+      const float lp = rbf((bf2f(sm.x[i]) - m) - lse);
+      const unsigned long long key = rank_key(lp, (uint32_t)(lo + i));
       if (key > loc[KMAX - 1]) {
         loc[KMAX - 1] = key;
 #pragma unroll
         for (int j = KMAX - 1; j > 0; --j) {
           if (loc[j] > loc[j - 1]) {
-            unsigned long long tmp = loc[j];
+            const unsigned long long tmp = loc[j];
             loc[j] = loc[j - 1];
             loc[j - 1] = tmp;
           }
         }
       }
-    });
+    }
+#pragma unroll 1
     for (int r = 0; r < KMAX; ++r) {
       unsigned long long best = 0ull;
       if (r < ph.k) {
-        best = team_max_u64(loc[0], reinterpret_cast<unsigned long long*>(red), tt, sync);
+        best = bteam_max_u64(loc[0], sm, tid, sync);
         if (loc[0] == best && best != 0ull) {   // keys are unique (index in the low word): exactly one owner pops
 #pragma unroll
           for (int j = 0; j < KMAX - 1; ++j) loc[j] = loc[j + 1];
           loc[KMAX - 1] = 0ull;
         }
       }
-      if (tt == 0) ph.keys[(t * ph.n_slices + s) * KMAX + r] = best;
+      if (tid == 0) ph.keys[(t * ph.n_slices + s) * KMAX + r] = best;
     }
   }
 }

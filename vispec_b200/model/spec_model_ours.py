@@ -125,10 +125,12 @@ class SpecModel:
         self.last_decode_ms = 0.0
         self._cycle_prog: Optional[Program] = None
 
-    def cycle_program(self, trace: bool = False, pf_ahead: Optional[int] = None) -> Program:
+    def cycle_program(self, trace: bool = False, pf_ahead: Optional[int] = None, inflight: Optional[int] = None) -> Program:
         """The whole draft+verify cycle (spec_model_ours.py:484-547 loop body) as one persistent-kernel launch."""
         eng_t, eng_d = self.base_model_engine, self.spec_layer.engine
         p = Program(eng_t.device, pf_ahead=pf_ahead, trace=trace)
+        if inflight is not None:
+            p.set_option("inflight", inflight)
         p.add("spec_cycle", C.byref(eng_t.c), C.byref(eng_t.scratch.c), C.byref(eng_d.c), C.byref(eng_d.scratch.c),
               C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.kv), eng_t.kv_max, L.ptr(eng_t.hidden_out),
               L.ptr(eng_t.logits), L.ptr(eng_t.amax), L.ptr(self._rec_dev[0]))
