@@ -10,7 +10,12 @@ checkpoints offline).  One "step" = one generation of 256 tokens.
           `return_decode_time` region, spec_model_ours.py:480-482,575-578), CUDA events, max over ranks.
   e2e   : the same metric through the public API `SpecModel.specgenerate` with HOST (pinned) inputs: H2D copy of
           ids/embeddings/mask, prefill, decode and the D2H read of the output ids are all inside the timed region.
-  roofline     : the dominant kernel (the weight-streaming fused linear), algorithmic weight bytes / CUDA-event time.
+  roofline     : the dominant kernel = the persistent program kernel (ONE launch per draft+verify cycle): algorithmic
+                 bytes per launch (every weight matrix of the 32-layer verify step and of the 4 draft forwards read once
+                 + the KV rows read once) / the kernel's average launch duration over the timed region
+                 (CUDA events on the launching stream), against the measured HBM copy bandwidth.
+  roofline_attention : the north star's KV-read figure: K+V bytes of one layer / the duration of that layer's two
+                 attention phases inside the kernel (per-phase %globaltimer trace of the same kernel).
   cpu_baseline : the oracle (CPU restatement of the reference) timed on this box's host cores on a bounded sample.
 
 `--impl reference` times the reference algorithm's CPU implementation (oracle port) on the host cores.
@@ -36,6 +41,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one program_kernel launch from the committed `ncu --set full` capture
+# (profiles/README.md); None until a capture of the current kernel exists
+NCU_TRAFFIC_BYTES = 20.85e9
+NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_full_program_kernel.csv"
 N_PRE, N_IMG, N_POST = 5, 576, 123          # 576 image + 128 text tokens = 704
 GEN_TOKENS = 256
 WORKLOAD = "LLaVA-1.6-Vicuna-7B shapes + ViSpec head, T=0, 576 img + 128 text tokens, 256-token gen, 1xB200"
@@ -266,6 +275,46 @@ def cpu_reference_sample(n_cycles: int, warm: int, threads: int, layers: int = 3
     return tokens, dt, acc
 
 
+
+# ------------------------------------------------------------------------------------------------------------
+# algorithmic bytes of one draft+verify cycle (DESIGN.md "Roofline")
+# ------------------------------------------------------------------------------------------------------------
+def cycle_algorithmic_bytes(tcfg, dcfg, kv_len_target: float, kv_len_draft: float):
+    H, I, V, nh, nkv, Lyr = tcfg.hidden, tcfg.inter, tcfg.vocab, tcfg.heads, tcfg.kv_heads, tcfg.layers
+    w_target = Lyr * ((nh + 2 * nkv) * 128 * H + H * nh * 128 + 3 * H * I) * 2 + V * H * 2
+    Hd, Id = dcfg.hidden, dcfg.inter
+    w_draft_fwd = (2 * Hd * 2 * Hd + 4 * Hd * Hd + 3 * Hd * Id + V * Hd) * 2
+    kv_target = Lyr * 2 * kv_len_target * nkv * 128 * 2
+    kv_draft_fwd = 2 * kv_len_draft * Hd * 2
+    n_fwd = dcfg.depth + 1
+    return {"weights_target": w_target, "weights_draft": n_fwd * w_draft_fwd, "kv_target": kv_target,
+            "kv_draft": n_fwd * kv_draft_fwd,
+            "total": w_target + n_fwd * w_draft_fwd + kv_target + n_fwd * kv_draft_fwd}
+
+
+def phase_trace(model, ids, emb, mask, cycles=4):
+    """Per-phase durations of one cycle of the persistent kernel (us, CTA 0's %globaltimer stamps)."""
+    from vispec_b200 import _lib as L
+    from vispec_b200.model import utils as vu
+
+    model.spec_layer.reset_kv()
+    model.current_length_data.zero_()
+    vu.reset_tree_mode(model)
+    vu.initialize_tree(ids, model, model.past_key_values, None, emb, None, image_mask=mask)
+    torch.cuda.synchronize()
+    prog = model.cycle_program(trace=True)
+    for _ in range(cycles):
+        prog.run()
+    torch.cuda.synchronize()
+    us = prog.read_trace_us()
+    types = prog.phase_types()
+    by = {}
+    for t, d in zip(types, us):
+        k = L.PHASE_NAMES[t]
+        n, tot = by.get(k, (0, 0.0))
+        by[k] = (n + 1, tot + d)
+    return types, us, by
+
 # ------------------------------------------------------------------------------------------------------------
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
@@ -368,32 +417,44 @@ def run_ours(args):
     dec_ms_max, e2e_s_max = t.tolist()
     tokens_all, e2e_tokens_all, launches_all = cnt.tolist()
 
-    # roofline leg (rank 0): per-launch CUDA events around every fused-linear / attention launch of a few cycles
-    roof, roof_attn = None, None
+    # roofline leg (rank 0): the dominant kernel is the persistent program kernel, one launch per cycle
+    roof, roof_attn, phases = None, None, None
     if rank == 0:
+        from vispec_b200.engine import use_programs
         peak, peak_src = hbm_peak()
-        lib.vs_profile_start(200000)
-        model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, temperature=0.0, max_new_tokens=12)
-        cap = 200000
-        ms = (C.c_float * cap)(); by = (C.c_double * cap)(); cl = (C.c_int32 * cap)()
-        n = lib.vs_profile_stop(ms, by, cl, cap)
-        g_ms = g_by = 0.0; g_n = 0; a_ms = a_by = 0.0; a_n = 0
-        kv_len = ids.shape[1] + 30
-        for i in range(n):
-            if cl[i] == 0 and by[i] >= 30e6:          # decode-path weight streams (skip the tiny prefill-side calls)
-                g_ms += ms[i]; g_by += by[i]; g_n += 1
-            elif cl[i] == 1 and by[i] == 2.0 * 32 * 128 * 2:
-                a_ms += ms[i]; a_by += by[i] * kv_len; a_n += 1
-        if g_n:
-            ach = g_by / (g_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "gemm_skinny_kernel (fused linear, weight stream)", "achieved": ach,
-                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                    "launches_timed": g_n, "avg_launch_us": g_ms / g_n * 1e3, "avg_bytes_per_launch": g_by / g_n}
-        if a_n:
-            ach = a_by / (a_ms * 1e-3) / 1e9
-            roof_attn = {"bound": "hbm", "kernel": "attn_scores_kernel + attn_pv_kernel (per layer)", "achieved": ach,
-                         "peak": peak, "unit": "GB/s", "frac": ach / peak, "kv_len": kv_len, "launch_pairs_timed": a_n,
-                         "avg_pair_us": a_ms / a_n * 1e3}
+        tcfg, dcfg = eng.cfg, model.spec_layer.config
+        n_cycles = len(accs)
+        prompt_len = ids.shape[1]
+        mean_accept = sum(accs) / max(1, len(accs))
+        kv_t = prompt_len + (GEN_TOKENS / 2.0) + dcfg.total_tokens            # mean target KV length seen by verify
+        kv_d = (prompt_len - N_IMG + dcfg.num_q - 1) + (GEN_TOKENS / 2.0) + 8 * (dcfg.depth + 1) / 2.0
+        ab = cycle_algorithmic_bytes(tcfg, dcfg, kv_t, kv_d)
+        if use_programs() and n_cycles:
+            avg_ms = dec_ms / n_cycles                                          # CUDA events around the timed region
+            ach = ab["total"] / (avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "program_kernel (persistent draft+verify cycle, one launch per cycle)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
+                    "launches_timed": n_cycles, "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes_per_launch": ab["total"],
+                    "algorithmic_bytes": ab, "mean_accept_len": mean_accept}
+            types, us, by = phase_trace(model, ids, emb, mask)
+            tot = sum(us)
+            phases = {k: {"n": n, "us": round(t, 1), "share": round(t / tot, 4)} for k, (n, t) in sorted(by.items(), key=lambda kv: -kv[1][1])}
+            n_attn = by.get("attn_scores", (0, 0.0))[0]
+            if n_attn:
+                # target layers only: the first `layers` attention phase pairs of the cycle
+                t_attn = 0.0
+                seen = 0
+                for t, d in zip(types, us):
+                    if t in (L.PH_ATTN_S, L.PH_ATTN_PV) and seen < 2 * tcfg.layers:
+                        t_attn += d
+                        seen += 1
+                kv_len = prompt_len + dcfg.total_tokens
+                per_layer = 2 * kv_len * tcfg.kv_heads * 128 * 2
+                ach_a = per_layer * tcfg.layers / (t_attn * 1e-6) / 1e9
+                roof_attn = {"bound": "hbm", "kernel": "attention phases of program_kernel (scores + PV, incl. 2 grid barriers)",
+                             "achieved": ach_a, "peak": peak, "unit": "GB/s", "frac": ach_a / peak, "kv_len": kv_len,
+                             "kv_bytes_per_layer": per_layer, "avg_layer_us": t_attn / tcfg.layers}
     if rank != 0:
         return
     value = tokens_all / (dec_ms_max * 1e-3)
@@ -409,12 +470,13 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dec_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tree": "total_token=30 depth=3 top_k=8 num_q=2", "weights": "random-init",
-                       "layers": args.layers, "l2": "inputs larger than L2 (13.2 GB of weights streamed per cycle)",
+                       "layers": args.layers, "l2": "inputs larger than L2 (16.4 GB of weights streamed per cycle)",
+                       "path": "persistent program kernel" if os.environ.get("VS_MULTI_KERNEL", "0") != "1" else "one launch per op",
                        "parallelism": f"replicas x{world}"},
             "accept_len_mean": sum(accs) / max(1, len(accs)), "cycles_per_step": len(accs) / args.steps,
             "e2e": {"value": e2e_v, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "roofline_attention": roof_attn,
-            "cpu_baseline": cpu}
+            "phases_us_per_cycle": phases, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
 

@@ -270,7 +270,7 @@ typedef struct vs_program vs_program;
 int vs_program_create(vs_program** out);
 void vs_program_destroy(vs_program* pg);
 const char* vs_program_last_error(void);
-/* options: "pf_ahead" (L2 prefetch distance in 16 KB weight chunks per SM, default 24, 0 = off),
+/* options: "pf_ahead" (L2 prefetch distance in 16 KB weight chunks per SM, default 0 = off),
  * "trace" (1: record a %globaltimer stamp per phase), "grid" (CTAs; default = SM count; before adding phases) */
 int vs_program_set_option(vs_program* pg, const char* name, int value);
 int vs_program_num_phases(const vs_program* pg);
@@ -282,6 +282,13 @@ int vs_program_read_trace(const vs_program* pg, unsigned long long* out_ns, int 
 /* out[phase * grid + cta] = time at which the CTA finished its work items of the phase; returns the grid size */
 int vs_program_read_trace_cta(const vs_program* pg, unsigned long long* out_ns, int cap);
 
+/* Weight layout for HBM streaming.  A row-major weight matrix W[N][K] can additionally be given in the TILED layout:
+ * ceil(N/128) x (K/64) blocks of 16 KB, block (tile, kc) = rows [128*tile, +128) x columns [64*kc, +64) stored
+ * contiguously in the shared-memory image the tensor cores read (row r of the block at byte 128*r, its eight 16-byte
+ * chunks j stored at chunk position j ^ (r & 7); rows >= N are zero).  vispec_b200.engine.pack_weight_tiles builds
+ * it.  Every linear added AFTER the registration whose W pointer matches (and ldw == K) streams the tiled copy with
+ * contiguous 16 KB bulk copies and is prefetched into L2 ahead of use ("pf_ahead"); results are bit-identical. */
+int vs_program_register_tiled(vs_program* pg, const void* w_row_major, const void* w_tiled);
 int vs_program_add_linear(vs_program* pg, const vs_linear_args* a);
 int vs_program_add_rmsnorm(vs_program* pg, const void* x, int64_t ldx, const void* weight, void* y, int64_t ldy, int T,
                            int H, float eps);

@@ -260,3 +260,23 @@ def test_program_rejects_more_than_32_rows():
         p.add("linear", C.byref(a))
     with pytest.raises(RuntimeError, match="empty"):
         p.commit()
+
+
+@pytest.mark.parametrize("T,N,K", [(30, 4096, 4096), (8, 32064, 4096), (5, 1000, 256), (32, 4096, 11008)])
+@pytest.mark.parametrize("pf_ahead", [0, 16])
+def test_program_linear_tiled_weights_bit_identical(T, N, K, pf_ahead):
+    """The tiled HBM layout (contiguous, pre-swizzled 16 KB blocks + L2 prefetch) must give the same bits as the
+    row-major tensor-map path: it only changes how the bytes travel."""
+    from vispec_b200.engine import pack_weight_tiles
+    x, w = randn(T, K, seed=41), randn(N, K, std=K ** -0.5, seed=42)
+    b = randn(N, std=0.1, seed=43)
+    y0 = torch.zeros(T, N, dtype=BF, device=DEV)
+    y1 = torch.zeros(T, N, dtype=BF, device=DEV)
+    a0 = linear_args(x, w, b, T, N, K, y=y0)
+    run_program(lambda p: p.add("linear", C.byref(a0)), pf_ahead=0)
+    wt = pack_weight_tiles(w)
+    assert wt.data_ptr() % 1024 == 0 and wt.numel() == ((N + 127) // 128) * 128 * K
+    a1 = linear_args(x, w, b, T, N, K, y=y1)
+    run_program(lambda p: p.register_tiled([(w, wt)]).add("linear", C.byref(a1)), pf_ahead=pf_ahead)
+    assert torch.equal(y0, y1)
+    assert_bf16_close(y1, (x.float() @ w.float().T + b.float()).to(BF))

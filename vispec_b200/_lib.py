@@ -128,6 +128,7 @@ _SIGS = {
     "vs_program_run": (C.c_int, [c_vp, c_vp]),
     "vs_program_read_trace": (C.c_int, [c_vp, c_vp, C.c_int]),
     "vs_program_read_trace_cta": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "vs_program_register_tiled": (C.c_int, [c_vp, c_vp, c_vp]),
     "vs_program_add_linear": (C.c_int, [c_vp, C.POINTER(LinearArgs)]),
     "vs_program_add_rmsnorm": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_f32]),
     "vs_program_add_gather_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, C.c_int]),

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       int landed = 0;
       while (cur.next_phase(b, G)) {
         const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmW;
+        const bf16* wt = hdr.phases[cur.p].Wt;            // tiled layout: chunk c is the 16 KB block c of the matrix
         int tile = (int)(cur.c / cur.nk), kc = (int)(cur.c % cur.nk);
         for (int c = cur.c; c < cur.hi; ++c) {
           while (issued - landed >= inflight) {
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
           }
           mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
           mbar_expect_tx(&full_w[stage], W_STAGE);
-          tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES, kc * BK, tile * BM, HINT_EVICT_FIRST);
+          if (wt) bulk_load(smem + stage * STAGE_BYTES, wt + (long)c * (BM * BK), W_STAGE, &full_w[stage], HINT_EVICT_FIRST);
+          else tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES, kc * BK, tile * BM, HINT_EVICT_FIRST);
           *w_issued = ++issued;
           if (++stage == NS) { stage = 0; par ^= 1; }
           if (++kc == cur.nk) { kc = 0; ++tile; }
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       int stage = 0, par = 0;
       while (cur.next_phase(b, G)) {
         // the token tile is produced by earlier phases of this launch: wait until all of them completed everywhere
-        const unsigned int need = (unsigned int)cur.p * (unsigned int)G;
+        const unsigned int need = (unsigned int)hdr.phases[cur.p].bars_before * (unsigned int)G;
         // relaxed polling (no L1 invalidation storm); the tile itself is read by the TMA unit from L2, ordered behind the
         // observed counter value by the proxy fence
         while (ld_relaxed_u32(hdr.counters) < need) __nanosleep(64);
@@ -253,17 +255,23 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     }
   } else if (warp == 3) {
     // ===================== L2 prefetcher =====================
+    // Tiled weights only: this CTA's chunk range of a GEMM phase is ONE contiguous byte range, prefetched into L2 in
+    // 64 KB pieces up to `pf_ahead` chunks ahead of the weight producer -- across phase boundaries, so HBM keeps
+    // streaming while the CTA sits in an epilogue / attention phase or a grid barrier with a full shared-memory ring.
     if (lane == 0 && hdr.pf_ahead > 0) {
       GemmCursor cur;
       cur.init(hdr);
-      int idx = 0;
+      int idx = 0;                                       // chunks prefetched so far (program order)
+      constexpr int PIECE = 4;                           // chunks per prefetch instruction
       while (cur.next_phase(b, G)) {
-        const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmW;
-        int tile = (int)(cur.c / cur.nk), kc = (int)(cur.c % cur.nk);
-        for (int c = cur.c; c < cur.hi; ++c, ++idx) {
-          while (idx >= *w_issued + hdr.pf_ahead) __nanosleep(100);
-          if (idx >= *w_issued + NS) tma_prefetch_2d(tm, kc * BK, tile * BM);   // not about to be loaded anyway
-          if (++kc == cur.nk) { kc = 0; ++tile; }
+        const bf16* wt = hdr.phases[cur.p].Wt;
+        const int n = cur.hi - cur.c;
+        if (!wt) { idx += n; continue; }
+        for (int c = cur.c; c < cur.hi; c += PIECE) {
+          const int m = min(PIECE, cur.hi - c);
+          while (idx >= *w_issued + hdr.pf_ahead) __nanosleep(200);
+          if (idx >= *w_issued + NS) bulk_prefetch_l2(wt + (long)c * (BM * BK), (uint32_t)m * W_STAGE);
+          idx += m;
         }
       }
     }
@@ -281,6 +289,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     const int gteam = team * G + b, n_teams = PG_TEAMS * G;
     const int gbteam = bteam * G + b, n_bteams = PG_BIG_TEAMS * G;
     int acc = 0, acc_par = 0;
+    const unsigned int epoch = ld_relaxed_u32(hdr.counters + 2);     // launches completed before this one
     // Phase descriptors are staged through shared memory: the words of phase p+1 are loaded while phase p runs and
     // stored just before the barrier, so no phase starts with a chain of L2 round trips for its own arguments.
     uint8_t* phbuf = smem + PHBUF_OFF;
@@ -316,10 +325,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
                            quarter * 32 + lane;
 #pragma unroll
               for (int i = 0; i < 8; ++i) dst[i * BM] = v[i];
+              if (ph.no_barrier) {       // publish this contribution: the tile's epilogue items poll the counter
+                named_bar_sync(1, PG_WORKERS);
+                if (wtid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ph.tile_cnt + tile) : "memory");
+              }
             }
           }
         } break;
-        case PH_EPI: epi_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
+        case PH_EPI: epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
         case PH_ATTN_S: attn_s_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
@@ -338,7 +351,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       if (has_next && wtid < PHASE_WORDS)
         reinterpret_cast<unsigned int*>(phbuf + ((p + 1) & 1) * PHASE_SLOT)[wtid] = nxt0;
       if (hdr.trace_cta && wtid == 0) hdr.trace_cta[(long)p * G + b] = global_timer();   // this CTA's items are done
-      if (p + 1 < hdr.n_phases) grid_barrier(hdr.counters, (unsigned int)(p + 1) * (unsigned int)G, wtid);
+      if (p + 1 < hdr.n_phases) {
+        if (ph.type == PH_GEMM && ph.no_barrier) named_bar_sync(1, PG_WORKERS);   // only the staged descriptor needs it
+        else grid_barrier(hdr.counters, (unsigned int)(ph.bars_before + 1) * (unsigned int)G, wtid);
+      }
       if (hdr.trace && b == 0 && wtid == 0) hdr.trace[p] = global_timer();
 #ifdef VS_PROGRAM_CLK
       if (b == 0 && wtid == 0) g_clk[32 + (p & 15)] = clock64();        // end of the barrier of phase p
@@ -353,6 +369,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       if (old == (unsigned int)G - 1) {
         hdr.counters[0] = 0;
         hdr.counters[1] = 0;
+        hdr.counters[2] = epoch + 1;
         __threadfence();
       }
     }
@@ -378,12 +395,15 @@ struct vs_program {
   struct MapReq { const void* ptr; long ld; int rows, cols, box_rows; };
   std::vector<MapReq> maps;
   std::vector<int> tables;    // chunk ranges per CTA + contributor info per tile of every GEMM phase
+  std::vector<std::pair<const void*, const void*>> tiled;   // row-major weight pointer -> tiled copy
   size_t partial_floats = 0;
   size_t ssq_floats = 0;
+  size_t tile_cnt_count = 0;  // per-tile arrival counters of all fused GEMM+epilogue pairs
+  bool fuse_epilogue = true;  // epilogue phases wait on per-tile counters instead of a grid barrier
   size_t keys_count = 0;      // u64 entries of the arg-max / top-k candidate buffer
   size_t lstats_count = 0;    // float2 entries of the log-softmax slice statistics
   int grid = 0;
-  int pf_ahead = 24;
+  int pf_ahead = 0;            // L2 prefetch distance (tensor-map prefetch costs as much TMA issue as the load itself: off)
   int inflight = 0;           // weight stages in flight per SM (0 = the whole ring)
   int spin_ns = 100;          // back-off of the single-lane role warps between barrier polls
   bool committed = false;
@@ -392,7 +412,7 @@ struct vs_program {
   uint8_t* ws = nullptr;
   size_t off_trace_cta = 0;
   size_t off_tables = 0;
-  size_t off_maps = 0, off_phases = 0, off_counters = 0, off_trace = 0, off_ssq = 0, off_keys = 0, off_lstats = 0, off_partials = 0, total = 0;
+  size_t off_maps = 0, off_phases = 0, off_counters = 0, off_trace = 0, off_ssq = 0, off_tilecnt = 0, off_keys = 0, off_lstats = 0, off_partials = 0, total = 0;
   std::string err;
 };
 
@@ -451,6 +471,8 @@ void layout(vs_program* pg) {
   if (pg->trace_on) off = align_up(off + pg->phases.size() * sizeof(unsigned long long) * (pg->grid > 0 ? pg->grid : device_sms()), 256);
   pg->off_ssq = off;
   off = align_up(off + pg->ssq_floats * sizeof(float), 256);
+  pg->off_tilecnt = off;
+  off = align_up(off + pg->tile_cnt_count * sizeof(unsigned int), 256);
   pg->off_keys = off;
   off = align_up(off + pg->keys_count * sizeof(unsigned long long), 256);
   pg->off_lstats = off;
@@ -496,9 +518,17 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
     g.magic_nk = magic(g.nk);
   }
   g.tmW = add_map(pg, a.W, a.ldw, a.N, a.K, BM);
+  g.Wt = nullptr;
+  if (a.ldw == a.K)
+    for (const auto& pr : pg->tiled)
+      if (pr.first == a.W) g.Wt = static_cast<const bf16*>(pr.second);
   g.tmX = add_map(pg, a.X, a.ldx, a.T, a.K, VS_TOK);
   const size_t need = (size_t)G * g.maxseg * TILE_FLOATS;
   if (need > pg->partial_floats) pg->partial_floats = need;
+  g.no_barrier = pg->fuse_epilogue ? 1 : 0;
+  // offset (in counters) into the workspace region, +1 so that 0 stays "none"; patched to a pointer at commit
+  g.tile_cnt = pg->fuse_epilogue ? reinterpret_cast<unsigned int*>(uintptr_t(pg->tile_cnt_count + 1)) : nullptr;
+  if (pg->fuse_epilogue) pg->tile_cnt_count += g.n_tiles;
   pg->phases.push_back(g);
   Phase e = g;
   e.type = PH_EPI;
@@ -666,6 +696,8 @@ int vs_program_create(vs_program** out) {
   if (e) (*out)->pf_ahead = atoi(e);
   e = getenv("VS_INFLIGHT");
   if (e) (*out)->inflight = atoi(e);
+  e = getenv("VS_FUSE_EPILOGUE");
+  if (e) (*out)->fuse_epilogue = atoi(e) != 0;
   e = getenv("VS_SPIN_NS");
   if (e) (*out)->spin_ns = atoi(e);
   return VS_OK;
@@ -682,12 +714,23 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   if (!strcmp(name, "pf_ahead")) pg->pf_ahead = value;
   else if (!strcmp(name, "trace")) pg->trace_on = value != 0;
   else if (!strcmp(name, "inflight")) pg->inflight = value;
+  else if (!strcmp(name, "fuse_epilogue")) {
+    if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "fuse_epilogue must be set before adding phases");
+    pg->fuse_epilogue = value != 0;
+  }
   else if (!strcmp(name, "spin_ns")) pg->spin_ns = value;
 
   else if (!strcmp(name, "grid")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "grid must be set before adding phases");
     pg->grid = value;
   } else return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "unknown option");
+  return VS_OK;
+}
+
+int vs_program_register_tiled(vs_program* pg, const void* w_row_major, const void* w_tiled) {
+  if (!pg || !w_row_major || !w_tiled) return vs::pfail(VS_ERR_INVALID, "vs_program_register_tiled", "null argument");
+  if (reinterpret_cast<uintptr_t>(w_tiled) % 1024) return vs::pfail(VS_ERR_INVALID, "vs_program_register_tiled", "tiled weights must be 1024-byte aligned");
+  pg->tiled.emplace_back(w_row_major, w_tiled);
   return VS_OK;
 }
 
@@ -724,8 +767,13 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
   }
   memcpy(host.data() + pg->off_tables, pg->tables.data(), pg->tables.size() * sizeof(int));
   float* partials = reinterpret_cast<float*>(pg->ws + pg->off_partials);
+  int bars = 0;
   for (size_t i = 0; i < pg->phases.size(); ++i) {
     Phase ph = pg->phases[i];
+    ph.bars_before = bars;
+    if (!(ph.type == PH_GEMM && ph.no_barrier)) ++bars;
+    if (ph.tile_cnt)
+      ph.tile_cnt = reinterpret_cast<unsigned int*>(pg->ws + pg->off_tilecnt) + (reinterpret_cast<uintptr_t>(ph.tile_cnt) - 1);
     if (ph.type == PH_GEMM || ph.type == PH_EPI) ph.partials = partials;
     if (ph.ssq == PROG_WS_SSQ) ph.ssq = reinterpret_cast<float*>(pg->ws + pg->off_ssq);
     if (ph.ssq_in == PROG_WS_SSQ) ph.ssq_in = reinterpret_cast<float*>(pg->ws + pg->off_ssq);

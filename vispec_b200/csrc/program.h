@@ -37,8 +37,12 @@ struct Phase {
   int T;                      // valid token rows (<= 32)
   // ---- PH_GEMM / PH_EPI
   int tmW, tmX;               // tensor-map table indices
+  const bf16* Wt;             // weights in the tiled layout (see vs_program_register_tiled) or null -> tensor map tmW
   int n_tiles, nk, N;         // ceil(N/128) weight-row tiles, K/64 chunks
   int maxseg;                 // partial tiles per CTA
+  int bars_before;            // grid barriers executed before this phase (every phase; set at commit)
+  int no_barrier;             // PH_GEMM: the epilogue phase that follows waits on per-tile counters instead of a grid barrier
+  unsigned int* tile_cnt;     // PH_GEMM / PH_EPI: [n_tiles] arrivals of contributors, monotonic across launches (workspace)
   int range_off;              // offset into the program's int tables: per-CTA chunk ranges [lo, hi)
   int per_lo, rem;            // balanced partition: CTA b owns per_lo (+1 if b < rem) consecutive chunks
   unsigned int magic_per_hi, magic_per_lo, magic_nk;   // floor(2^32/d)+1 for d = per_lo+1, per_lo, nk (0 when d == 1)
@@ -81,7 +85,7 @@ struct ProgramHeader {
   int n_phases;
   const CUtensorMap* maps;
   const int* tables;               // host-computed chunk ranges / contributor tables of the GEMM phases
-  unsigned int* counters;          // [0] grid barrier, [1] exit counter
+  unsigned int* counters;          // [0] grid barrier, [1] exit counter, [2] launch epoch (launches completed)
   unsigned long long* trace;       // [n_phases] globaltimer at the end of each phase (CTA 0) or null
   unsigned long long* trace_cta;   // [n_phases][grid] globaltimer when each CTA finished its items of the phase, or null
   int pf_ahead;                    // L2 prefetch distance in 16 KB weight chunks per CTA (0 = off)

@@ -92,6 +92,7 @@ __device__ long long g_clk[64];
 
 constexpr int EPI_TPI = 8;     // tokens per item
 constexpr int EPI_TPT = 4;     // tokens per thread
+constexpr int EPI_BATCH = 4;   // contributors whose partial tiles are loaded together (32 loads in flight per thread)
 
 // q = k / d for k * d < 2^32, with magic = floor(2^32 / d) + 1 precomputed on the host (d == 1: magic == 0 -> q = k)
 __device__ __forceinline__ int fast_div(int k, unsigned int magic) {
@@ -99,12 +100,14 @@ __device__ __forceinline__ int fast_div(int k, unsigned int magic) {
 }
 __device__ __forceinline__ float bf_bits(unsigned short u) { return __uint_as_float(((unsigned int)u) << 16); }
 
-__device__ __noinline__ void epi_phase(const Phase& ph, int gteam, int n_teams, int tt, float* red, TeamSync sync) {
+__device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
+                                       TeamSync sync) {
   // everything an item needs from the descriptor, once (the descriptor lives in shared memory)
   const int T = ph.T, N = ph.N, nk = ph.nk, maxseg = ph.maxseg, epi = ph.epi;
   const int per_lo = ph.per_lo, rem = ph.rem;
   const unsigned int m_hi = ph.magic_per_hi, m_lo = ph.magic_per_lo, m_nk = ph.magic_nk;
   const float* partials = ph.partials;
+  const unsigned int* tile_cnt = ph.tile_cnt;
   const int groups = (T + EPI_TPI - 1) / EPI_TPI;      // 1..4
   const int n_items = ph.n_tiles * groups;
   const int col = tt & 63, half = tt >> 6;
@@ -153,15 +156,25 @@ __device__ __noinline__ void epi_phase(const Phase& ph, int gteam, int n_teams, 
       }
     }
     CLK(2);
-    // ---- reduction over the contributors in k order; the 32 loads of four contributors are in flight together
+    // ---- fused GEMM+epilogue: no grid barrier separated us from the GEMM phase; wait until every contributor of this
+    // tile has published its partial tile (monotonic counter: n_c arrivals per launch)
+    if (tile_cnt) {
+      if (tt == 0) {
+        const unsigned int want = (epoch + 1u) * (unsigned int)n_c;
+        while (ld_relaxed_u32(tile_cnt + tile) < want) {
+        }
+      }
+      sync();
+    }
+    // ---- reduction over the contributors in k order; the loads of EPI_BATCH contributors are in flight together
     float a[2][EPI_TPT];
 #pragma unroll
     for (int i = 0; i < EPI_TPT; ++i) { a[0][i] = 0.f; a[1][i] = 0.f; }
 #pragma unroll 1
-    for (int c0 = 0; c0 < n_c; c0 += 4) {
-      float v[4][2][EPI_TPT];
+    for (int c0 = 0; c0 < n_c; c0 += EPI_BATCH) {
+      float v[EPI_BATCH][2][EPI_TPT];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < EPI_BATCH; ++c) {
         const int ci = min(c0 + c, n_c - 1);                                   // clamped: always a valid tile
         const float* base = partials + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS + ts * PG_BM + col;
 #pragma unroll
@@ -170,14 +183,12 @@ __device__ __noinline__ void epi_phase(const Phase& ph, int gteam, int n_teams, 
           for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + i * PG_BM + 64 * j);   // rows >= T hold stale finite data
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float keep = c0 + c < n_c ? 1.f : 0.f;
+      for (int c = 0; c < EPI_BATCH; ++c) {
 #pragma unroll
         for (int i = 0; i < EPI_TPT; ++i) {
           a[0][i] += c0 + c < n_c ? v[c][0][i] : 0.f;
           a[1][i] += c0 + c < n_c ? v[c][1][i] : 0.f;
         }
-        (void)keep;
       }
     }
 

@@ -23,6 +23,12 @@ from . import _lib as L
 from .program import Program
 
 
+def use_tiled() -> bool:
+    """Keep a second, tiled copy of every decode weight for the program kernel (VS_TILED=0: stream the row-major copy
+    through tensor maps instead)."""
+    return os.environ.get("VS_TILED", "1") != "0"
+
+
 def use_programs() -> bool:
     """The persistent program kernel (one launch per step) is the product path; VS_MULTI_KERNEL=1 selects the
     one-launch-per-op path (same kernels' arithmetic, kept for A/B measurements and as a cross-check)."""
@@ -90,6 +96,29 @@ def pack_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     assert inter % 64 == 0, "intermediate size must be a multiple of 64"
     return torch.stack((gate.view(inter // 64, 64, hidden), up.view(inter // 64, 64, hidden)), dim=1) \
         .reshape(2 * inter, hidden).contiguous()
+
+
+def pack_weight_tiles(w: torch.Tensor) -> torch.Tensor:
+    """Row-major [N,K] bf16 -> the tiled HBM layout of include/vispec_b200.h (vs_program_register_tiled):
+    [ceil(N/128), K/64, 128, 64] blocks of 16 KB, each block already in the 128-byte-swizzled shared-memory image
+    (16-byte chunk j of row r stored at chunk j ^ (r & 7)); rows beyond N are zero.  1024-byte aligned."""
+    n, k = w.shape
+    assert k % 64 == 0, "K must be a multiple of 64"
+    n_tiles = (n + 127) // 128
+    if n_tiles * 128 != n:
+        w = torch.cat([w, torch.zeros(n_tiles * 128 - n, k, dtype=w.dtype, device=w.device)], dim=0)
+    t = w.view(n_tiles, 128, k // 64, 8, 8).permute(0, 2, 1, 3, 4)                 # [tile, kc, r, j, e]
+    r = torch.arange(128, device=w.device)
+    j = torch.arange(8, device=w.device)
+    idx = (j[None, :] ^ (r[:, None] & 7))                                          # out[r, j'] = in[r, j' ^ (r & 7)]
+    idx = idx[None, None, :, :, None].expand(n_tiles, k // 64, 128, 8, 8)
+    out = torch.gather(t, 3, idx).contiguous()
+    buf = torch.empty(out.numel() + 512, dtype=w.dtype, device=w.device)           # room to align to 1024 bytes
+    off = ((-buf.data_ptr()) % 1024) // 2
+    packed = buf[off:off + out.numel()]
+    packed.copy_(out.view(-1))
+    packed._vs_storage = buf
+    return packed
 
 
 def _stream() -> int:
@@ -191,6 +220,13 @@ class TargetEngine:
                               L.ptr(t["w_gateup"]), L.ptr(t["w_down"]), L.ptr(self.kv[2 * li]), L.ptr(self.kv[2 * li + 1]),
                               self.kv_max * 128)
         self._layer_arr = arr
+        # tiled copies for the persistent program kernel (the row-major copies stay for the prefill / per-op path)
+        self.tiled = []
+        if use_programs() and use_tiled():
+            for t in self.layers_t:
+                for k in ("w_qkv", "w_o", "w_gateup", "w_down"):
+                    self.tiled.append((t[k], pack_weight_tiles(t[k])))
+            self.tiled.append((self.lm_head, pack_weight_tiles(self.lm_head)))
         self.dims = _dims(cfg.hidden, cfg.inter, cfg.heads, cfg.kv_heads, cfg.vocab, cfg.layers, cfg.eps)
         self.c = L.Target(self.dims, arr, L.ptr(self.embed), L.ptr(self.norm), L.ptr(self.lm_head),
                           L.Rope(L.ptr(self.cos), L.ptr(self.sin)))
@@ -211,7 +247,7 @@ class TargetEngine:
         key = (T, has_bits)
         p = self._verify_progs.get(key)
         if p is None:
-            p = Program(self.device)
+            p = Program(self.device).register_tiled(self.tiled)
             p.add("verify_step", C.byref(self.c), C.byref(self.scratch.c), L.ptr(self._v_ids), L.ptr(self._v_pos),
                   L.ptr(self._v_bits) if has_bits else None, T, L.ptr(self.state), L.ptr(self.hidden_out),
                   L.ptr(self.logits), L.ptr(self.amax))
@@ -355,6 +391,10 @@ class DraftEngine:
         self.adpt_q = torch.zeros(nh, 32, 128, dtype=self.dtype, device=dev)
         self.adpt_q[:, :cfg.num_q] = g("imadpt.q").view(cfg.num_q, nh, 128).transpose(0, 1)
         self.lm_head = lm_head
+        self.tiled = []                                   # the target engine's lm_head pair is added by bind_tiled
+        if use_programs() and use_tiled():
+            for w in (self.w_qkv, self.w_o, self.w_gateup, self.w_down, self.w_fc, self.w_img_fc):
+                self.tiled.append((w, pack_weight_tiles(w)))
         self.cos, self.sin = rope_tables(128, cfg.max_pos, cfg.rope_theta, self.dtype, dev)
         self.cache_rows = cache_rows
         self.k_cache = torch.zeros(nh, cache_rows, 128, dtype=self.dtype, device=dev)
@@ -399,6 +439,10 @@ class DraftEngine:
 
     def bind_state(self, state: torch.Tensor):
         self.state = state
+
+    def bind_tiled(self, pairs):
+        """Tiled copies owned by the target engine that the draft also streams (the shared LM head)."""
+        self.tiled = self.tiled + [p for p in pairs if p[0].data_ptr() == self.lm_head.data_ptr()]
 
     def reset_kv(self):
         """cnets_ours.py:1040-1041."""
@@ -511,7 +555,7 @@ class DraftEngine:
         if use_programs():
             self.state[L.ST_NEXT_TOKEN] = int(sample_token)
             if self._prog_levels is None:
-                self._prog_levels = Program(dev)
+                self._prog_levels = Program(dev).register_tiled(self.tiled)
                 self._prog_levels.add("draft_levels", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb),
                                       L.ptr(self.state), 1, self.state.data_ptr() + 4 * L.ST_NEXT_TOKEN, 0)
                 self._prog_levels.commit()
@@ -552,7 +596,7 @@ class DraftEngine:
         self.state[L.ST_NEXT_TOKEN] = int(sample_token)
         if use_programs():
             if self._prog_tree is None:
-                self._prog_tree = Program(self.device)
+                self._prog_tree = Program(self.device).register_tiled(self.tiled)
                 self._prog_tree.add("draft_tree", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state))
                 self._prog_tree.commit()
             self._prog_tree.run()

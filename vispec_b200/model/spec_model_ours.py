@@ -111,6 +111,7 @@ class SpecModel:
         self.config = base_model.config
         self.spec_layer = spec_layer
         self.spec_layer.engine.bind_state(self.base_model_engine.state)
+        self.spec_layer.engine.bind_tiled(self.base_model_engine.tiled)
         self.hidden_size = base_model.engine.cfg.hidden
         self.vocab_size = base_model.engine.cfg.vocab
         self.tokenizer = tokenizer if tokenizer is not None else SimpleNamespace(eos_token_id=eos_token_id)
@@ -129,6 +130,7 @@ class SpecModel:
         """The whole draft+verify cycle (spec_model_ours.py:484-547 loop body) as one persistent-kernel launch."""
         eng_t, eng_d = self.base_model_engine, self.spec_layer.engine
         p = Program(eng_t.device, pf_ahead=pf_ahead, trace=trace)
+        p.register_tiled(eng_t.tiled + eng_d.tiled)
         if inflight is not None:
             p.set_option("inflight", inflight)
         p.add("spec_cycle", C.byref(eng_t.c), C.byref(eng_t.scratch.c), C.byref(eng_d.c), C.byref(eng_d.scratch.c),

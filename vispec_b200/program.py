@@ -37,6 +37,14 @@ class Program:
     def set_option(self, name: str, value: int):
         L.pcheck(self.lib.vs_program_set_option(self.h, name.encode(), int(value)), "vs_program_set_option")
 
+    def register_tiled(self, pairs):
+        """pairs of (row-major weight tensor, tiled copy from engine.pack_weight_tiles): linears added afterwards that
+        use one of these weights stream the tiled copy (contiguous 16 KB blocks, L2 prefetch)."""
+        self._tiled_refs = getattr(self, "_tiled_refs", []) + list(pairs)
+        for w, wt in pairs:
+            L.pcheck(self.lib.vs_program_register_tiled(self.h, w.data_ptr(), wt.data_ptr()), "vs_program_register_tiled")
+        return self
+
     def add(self, fn_name: str, *args):
         """Call `vs_program_add_<fn_name>(program, *args)`."""
         fn = getattr(self.lib, "vs_program_add_" + fn_name)
