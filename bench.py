@@ -47,7 +47,7 @@ NCU_TRAFFIC_BYTES = 16.86e9
 NCU_TRAFFIC_SOURCE = "profiles/r1d_ncu_full_program_kernel.csv"
 N_PRE, N_IMG, N_POST = 5, 576, 123          # 576 image + 128 text tokens = 704
 GEN_TOKENS = 256
-WORKLOAD = "LLaVA-1.6-Vicuna-7B shapes + ViSpec head, T=0, 576 img + 128 text tokens, 256-token gen, 1xB200"
+WORKLOAD = "LLaVA-1.6-Vicuna-7B shapes + ViSpec head, T=0, 576 img + 128 text tokens, 256-token gen, one stream per B200"
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -112,8 +112,29 @@ def synth_prompt(cfg, embed, seed, device):
     return ids.to(device), emb, mask.to(device)
 
 
-def build_llava7b(device="cuda", seed=0, layers=32):
-    """(model, input_ids, inputs_embeds, image_mask) for the BASELINE config-2 workload."""
+def make_bigram(tw, dw, tcfg, dcfg):
+    """The tau > 0 fixture of SURVEY.md 7.2 at full size (oracle/synth.py:make_bigram_fixture is the CPU original):
+    every target layer's o_proj / down_proj is zero, so next = argmax(lm_head(norm(embed[tok]))), and the draft
+    (same embedding, fc = [I | 0], zero o_proj / down_proj) predicts it: accept length = depth + 1."""
+    for li in range(tcfg.layers):
+        tw[f"model.layers.{li}.self_attn.o_proj.weight"].zero_()
+        tw[f"model.layers.{li}.mlp.down_proj.weight"].zero_()
+    tw["model.norm.weight"].fill_(1.0)
+    dw["embed_tokens.weight"] = tw["model.embed_tokens.weight"]
+    H = dcfg.hidden
+    fc = torch.zeros(H, 2 * H, dtype=torch.bfloat16, device=dw["fc.weight"].device)
+    fc[:, :H] = torch.eye(H, dtype=torch.bfloat16, device=fc.device)
+    dw["fc.weight"] = fc
+    if "fc.bias" in dw:
+        dw["fc.bias"].zero_()
+    dw["layers.0.self_attn.o_proj.weight"].zero_()
+    dw["layers.0.mlp.down_proj.weight"].zero_()
+
+
+def build_llava7b(device="cuda", seed=0, layers=32, fixture="random"):
+    """(model, input_ids, inputs_embeds, image_mask) for the BASELINE config-2 workload.  fixture="bigram": the same
+    shapes with weights under which the draft is always right (accept length 4), to exercise accept / splice / the
+    accepted-rows draft forward at full size."""
     from vispec_b200.engine import DraftConfig, TargetConfig
     from vispec_b200.model.spec_model_ours import SpecModel
 
@@ -121,6 +142,8 @@ def build_llava7b(device="cuda", seed=0, layers=32):
     dcfg = DraftConfig()
     tw = synth_target_weights(tcfg, seed, device)
     dw = synth_draft_weights(dcfg, seed + 1, device)
+    if fixture == "bigram":
+        make_bigram(tw, dw, tcfg, dcfg)
     model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=device, eos_token_id=None)
     ids, emb, mask = synth_prompt(tcfg, model.base_model_engine.embed, seed + 7, device)
     del tw, dw
@@ -455,7 +478,27 @@ def run_ours(args):
                 roof_attn = {"bound": "hbm", "kernel": "attention phases of program_kernel (scores + PV, incl. 2 grid barriers)",
                              "achieved": ach_a, "peak": peak, "unit": "GB/s", "frac": ach_a / peak, "kv_len": kv_len,
                              "kv_bytes_per_layer": per_layer, "avg_layer_us": t_attn / tcfg.layers}
+    # accept-length leg (rank 0, N=1): the same kernel on the bigram fixture of SURVEY.md 7.2 at the same shapes, where
+    # the draft is (mostly) right -- tokens/s scales with accept length + 1 at an unchanged cycle time
+    fixture = None
+    if rank == 0 and world == 1 and not args.no_fixture:
+        del model
+        torch.cuda.empty_cache()
+        m2, ids2, emb2, mask2 = build_llava7b(device=device, seed=rank + 3, layers=args.layers, fixture="bigram")
+        for _ in range(2):
+            m2.specgenerate(ids2, inputs_embeds=emb2, image_mask=mask2, **gen_kw)
+        tok2, ms2, acc2 = 0, 0.0, []
+        for _ in range(max(1, args.steps // 2)):
+            _, n2, _, a2 = m2.specgenerate(ids2, inputs_embeds=emb2, image_mask=mask2, **gen_kw)
+            tok2 += n2; ms2 += m2.last_decode_ms; acc2 += a2
+        fixture = {"weights": "bigram fixture (target o_proj/down_proj = 0, draft = target embedding + identity fc)",
+                   "value": tok2 / (ms2 * 1e-3), "unit": "tokens/s", "accept_len_mean": sum(acc2) / max(1, len(acc2)),
+                   "ms_per_cycle": ms2 / max(1, len(acc2))}
+        del m2
+        torch.cuda.empty_cache()
     if rank != 0:
+        if use_dist:
+            dist.destroy_process_group()
         return
     value = tokens_all / (dec_ms_max * 1e-3)
     e2e_v = e2e_tokens_all / e2e_s_max
@@ -476,8 +519,10 @@ def run_ours(args):
             "accept_len_mean": sum(accs) / max(1, len(accs)), "cycles_per_step": len(accs) / args.steps,
             "e2e": {"value": e2e_v, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "roofline_attention": roof_attn,
-            "phases_us_per_cycle": phases, "cpu_baseline": cpu}
+            "phases_us_per_cycle": phases, "accept_fixture": fixture, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
 
 
 def main():
@@ -489,6 +534,7 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--ref-cycles", type=int, default=3, help="CPU cycles per bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fixture", action="store_true", help="skip the accept-length (bigram fixture) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -225,3 +225,28 @@ def test_llava7b_spec_equals_greedy(llava7b):
     assert out[0, ids.shape[1]:].tolist() == seq
     st = model.base_model_engine.state.tolist()
     assert st[L.ST_D_LEN] >= 129      # 128 text rows + 1 compressed image token + accepted tokens
+
+
+def test_llava7b_bigram_fixture_accepts_and_equals_greedy():
+    """Full LLaVA-7B shapes with the bigram fixture: the draft follows the target's bigram table, so
+    cycles accept 2-4 drafted tokens (the target's RMSNorm rounds the embedding, the draft has no final norm, so a few
+    near-ties differ) -- accept, KV splice and the multi-row accepted-hidden draft forward run at full size inside the
+    persistent kernel -- and the output must still equal plain greedy decoding of the target."""
+    from bench import build_llava7b
+    model, ids, emb, mask = build_llava7b(device=DEV, seed=3, fixture="bigram")
+    n_tok = 40
+    out, new_token, idx, acc = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, log=True,
+                                                  return_acceptance_len=True, max_new_tokens=n_tok)
+    assert acc and sum(acc) / len(acc) >= 2.0 and max(acc) == 4, acc
+    assert new_token == sum(acc) + len(acc)
+    pkv, _, _ = initialize_past_key_values(model.base_model)
+    lm = model.base_model
+    o = lm(inputs_embeds=emb, past_key_values=pkv)
+    seq = []
+    for _ in range(new_token):
+        tok = torch.argmax(o.logits[:, -1])[None, None]
+        seq.append(int(tok))
+        o = lm(input_ids=tok, past_key_values=pkv)
+    assert out[0, ids.shape[1]:].tolist() == seq
+    del model
+    torch.cuda.empty_cache()

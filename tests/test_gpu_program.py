@@ -41,7 +41,9 @@ def run_program(build, **opts):
 
 
 @pytest.mark.parametrize("T,N,K", [(1, 256, 256), (5, 1000, 256), (30, 4096, 4096), (32, 4096, 11008), (8, 32064, 4096),
-                                   (30, 4096, 8192), (3, 128, 64)])
+                                   (30, 4096, 8192), (3, 128, 64),
+                                   (30, 5120, 13824), (30, 15360, 5120),      # LLaVA-1.6-13B: down_proj, q|k|v
+                                   (30, 4608, 3584), (8, 152064, 3584)])      # Qwen2.5-VL-7B: q|k|v (28q + 2x4kv heads), LM head
 @pytest.mark.parametrize("bias", [False, True])
 def test_program_linear_store(T, N, K, bias):
     x, w = randn(T, K, seed=1), randn(N, K, std=K ** -0.5, seed=2)
