@@ -463,19 +463,20 @@ def run_ours(args):
             types, us, by = phase_trace(model, ids, emb, mask)
             tot = sum(us)
             phases = {k: {"n": n, "us": round(t, 1), "share": round(t / tot, 4)} for k, (n, t) in sorted(by.items(), key=lambda kv: -kv[1][1])}
-            n_attn = by.get("attn_scores", (0, 0.0))[0]
+            n_attn = by.get("attn_scores", (0, 0.0))[0] + by.get("attn_fused", (0, 0.0))[0]
             if n_attn:
                 # target layers only: the first `layers` attention phase pairs of the cycle
                 t_attn = 0.0
                 seen = 0
+                n_target = tcfg.layers * (1 if by.get("attn_fused") else 2)
                 for t, d in zip(types, us):
-                    if t in (L.PH_ATTN_S, L.PH_ATTN_PV) and seen < 2 * tcfg.layers:
+                    if t in (L.PH_ATTN_S, L.PH_ATTN_PV, L.PH_ATTN_FUSED) and seen < n_target:
                         t_attn += d
                         seen += 1
                 kv_len = prompt_len + dcfg.total_tokens
                 per_layer = 2 * kv_len * tcfg.kv_heads * 128 * 2
                 ach_a = per_layer * tcfg.layers / (t_attn * 1e-6) / 1e9
-                roof_attn = {"bound": "hbm", "kernel": "attention phases of program_kernel (scores + PV, incl. 2 grid barriers)",
+                roof_attn = {"bound": "hbm", "kernel": "attention phase(s) of program_kernel (scores + softmax + PV, incl. the closing grid barrier)",
                              "achieved": ach_a, "peak": peak, "unit": "GB/s", "frac": ach_a / peak, "kv_len": kv_len,
                              "kv_bytes_per_layer": per_layer, "avg_layer_us": t_attn / tcfg.layers}
     # accept-length leg (rank 0, N=1): the same kernel on the bigram fixture of SURVEY.md 7.2 at the same shapes, where

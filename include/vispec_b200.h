@@ -270,8 +270,16 @@ typedef struct vs_program vs_program;
 int vs_program_create(vs_program** out);
 void vs_program_destroy(vs_program* pg);
 const char* vs_program_last_error(void);
+/* Attention inside a program runs either as two phases (scores | softmax + PV; any kv length) or, with option
+ * "attn_fused" = 1, as ONE phase in which every (head, kv split) item is resident and the two passes meet at a per-head
+ * arrival counter (K and V read once, scores never leave the SM).  The fused phase holds at most
+ * vs_attention_fused_capacity(n_heads, scratch pv_splits, scratch max_chunks) keys (n_ctx + n_new; 1152 for 32 heads on
+ * 148 SMs); the kernel traps beyond it -- the caller selects the program by the kv length it is about to run. */
+int vs_attention_fused_capacity(int n_heads, int pv_splits_cap, int max_chunks);
 /* options: "pf_ahead" (L2 prefetch distance in 16 KB weight chunks per SM, default 0 = off),
- * "trace" (1: record a %globaltimer stamp per phase), "grid" (CTAs; default = SM count; before adding phases) */
+ * "trace" (1: record a %globaltimer stamp per phase), "grid" (CTAs; default = SM count; before adding phases),
+ * "attn_fused" (see above; before adding phases), "fuse_epilogue" (default 1: an epilogue waits on per-tile arrival
+ * counters instead of a grid barrier), "inflight" / "spin_ns" (tuning of the producer warps) */
 int vs_program_set_option(vs_program* pg, const char* name, int value);
 int vs_program_num_phases(const vs_program* pg);
 int vs_program_phase_types(const vs_program* pg, int32_t* out, int cap);

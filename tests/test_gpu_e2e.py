@@ -165,6 +165,23 @@ def test_specgenerate_fused_matches_reference_and_greedy(name):
     assert torch.equal(out2, out) and acc2 == acc
 
 
+def test_specgenerate_switches_attention_program_at_capacity():
+    """The single-phase attention holds a bounded number of keys; specgenerate must switch to the two-phase program
+    when the KV length is about to exceed it -- mid-generation, without changing a token."""
+    g, tcfg, dcfg, tw, dw, ids, emb, mask = load_case("bigram_noisy_img")
+    model = build(tcfg, dcfg, tw, dw)
+    kw = dict(temperature=0.0, log=True, return_acceptance_len=True, max_new_tokens=60)
+    if emb is not None:
+        kw.update(inputs_embeds=emb.to(DEV), image_mask=mask.to(DEV))
+    ref_out, _, _, ref_acc = model.specgenerate(ids.to(DEV), **kw)
+    assert set(model._cycle_progs) == {True}                       # everything fit the fused phase
+    # shrink the capacity so that the target crosses it after a few cycles
+    model.base_model_engine.scratch.fused_kv_capacity = ids.shape[1] + 2 * L.VS_MAX_ACCEPT + 30 + 12
+    out, _, _, acc = model.specgenerate(ids.to(DEV), **kw)
+    assert set(model._cycle_progs) == {True, False}                # both programs were used
+    assert torch.equal(out, ref_out) and acc == ref_acc
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_causal_decode_equals_reference_greedy(name):
     """The autoregressive baseline loop (gen_baseline_answer_coco_caption.py:34-133) through the same kernels."""

@@ -199,7 +199,7 @@ def test_program_rows_argmax_topk():
     assert torch.equal(tv1, tv.view(8, k)[5]) and torch.equal(ti1, ti.view(8, k)[5])
 
 
-def program_attention(Q, K, V, nh, nkv, Tq, n_ctx, n_new, causal, bits, eager, n_ctx_dev=True):
+def program_attention(Q, K, V, nh, nkv, Tq, n_ctx, n_new, causal, bits, eager, n_ctx_dev=True, fused=False):
     sc = ScratchBuffers(nh * 128, 256, nh, 1000, 32, K.shape[1], DEV)
     O = torch.zeros(Tq, nh * 128, dtype=BF, device=DEV)
     a = L.AttnArgs()
@@ -210,31 +210,42 @@ def program_attention(Q, K, V, nh, nkv, Tq, n_ctx, n_new, causal, bits, eager, n
     a.n_new, a.causal, a.bits, a.eager, a.scale = n_new, int(causal), L.ptr(bits), int(eager), 1 / math.sqrt(128)
     a.scores, a.score_ld, a.stats, a.max_chunks = sc.scores.data_ptr(), sc.score_ld, sc.stats.data_ptr(), sc.max_chunks
     a.opart, a.pv_splits, a.counters, a.O, a.ldo = sc.opart.data_ptr(), sc.pv_splits, sc.attn_counters.data_ptr(), O.data_ptr(), nh * 128
-    p = run_program(lambda p: p.add("attention", C.byref(a)))
-    assert p.phase_types() == [L.PH_ATTN_S, L.PH_ATTN_PV]
+    if fused:
+        assert n_ctx + n_new <= sc.fused_kv_capacity
+    p = run_program(lambda p: p.add("attention", C.byref(a)), attn_fused=fused)
+    assert p.phase_types() == ([L.PH_ATTN_FUSED] if fused else [L.PH_ATTN_S, L.PH_ATTN_PV])
     assert int(sc.attn_counters.abs().sum()) == 0
+    if fused:                                 # relaunch: the per-head arrival counters are monotonic across launches
+        O1 = O.clone()
+        O.zero_()
+        p.run()
+        torch.cuda.synchronize()
+        assert torch.equal(O, O1)
     return O
 
 
 @pytest.mark.parametrize("eager", [True, False])
-@pytest.mark.parametrize("nh,nkv,n_ctx", [(32, 32, 704), (4, 2, 61), (2, 2, 0), (8, 8, 3000)])
-def test_program_attention_tree(eager, nh, nkv, n_ctx):
+@pytest.mark.parametrize("nh,nkv,n_ctx,fused", [(32, 32, 704, False), (4, 2, 61, False), (2, 2, 0, False), (8, 8, 3000, False),
+                                                (32, 32, 704, True), (32, 32, 1100, True), (4, 2, 61, True), (2, 2, 0, True),
+                                                (8, 8, 1900, True)])
+def test_program_attention_tree(eager, nh, nkv, n_ctx, fused):
     T, rows = 30, 4096
     Q = randn(nh, 32, 128, seed=20)
     K, V = randn(nkv, rows, 128, seed=21), randn(nkv, rows, 128, seed=22)
     bits = tk.tree_bits(T, 5)
-    O = program_attention(Q, K, V, nh, nkv, T, n_ctx, T, False, bits, eager)
+    O = program_attention(Q, K, V, nh, nkv, T, n_ctx, T, False, bits, eager, fused=fused)
     ref = tk.attention_ref(Q[:, :T], K, V, n_ctx, T, False, bits.tolist(), eager, nh, nkv)
     torch.testing.assert_close(O.float(), ref.float(), rtol=2 ** -6, atol=2e-2)
     assert (O.float() == ref.float()).float().mean() > 0.9
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("Tq,n_ctx", [(1, 100), (5, 129), (8, 40), (32, 0)])
-def test_program_attention_causal(Tq, n_ctx):
+def test_program_attention_causal(Tq, n_ctx, fused):
     nh = nkv = 4
     Q = randn(nh, 32, 128, seed=23)
     K, V = randn(nkv, 1024, 128, seed=24), randn(nkv, 1024, 128, seed=25)
-    O = program_attention(Q, K, V, nh, nkv, Tq, n_ctx, Tq, True, None, False, n_ctx_dev=(n_ctx > 0))
+    O = program_attention(Q, K, V, nh, nkv, Tq, n_ctx, Tq, True, None, False, n_ctx_dev=(n_ctx > 0), fused=fused)
     ref = tk.attention_ref(Q[:, :Tq], K, V, n_ctx, Tq, True, None, False, nh, nkv)
     torch.testing.assert_close(O.float(), ref.float(), rtol=2 ** -6, atol=2e-2)
 

@@ -21,6 +21,7 @@ ap.add_argument("--pf-ahead", type=int, default=None)
 ap.add_argument("--cycles", type=int, default=4)
 ap.add_argument("--inflight", type=int, default=None)
 ap.add_argument("--brief", action="store_true")
+ap.add_argument("--two-phase-attention", action="store_true")
 ap.add_argument("--json", default=None)
 args = ap.parse_args()
 
@@ -32,7 +33,8 @@ model.current_length_data.zero_()
 vu.reset_tree_mode(model)
 vu.initialize_tree(ids, model, model.past_key_values, None, emb, None, image_mask=mask)
 torch.cuda.synchronize()
-prog = model.cycle_program(trace=True, pf_ahead=args.pf_ahead, inflight=args.inflight)
+prog = model.cycle_program(trace=True, pf_ahead=args.pf_ahead, inflight=args.inflight,
+                           attn_fused=not args.two_phase_attention)
 types = prog.phase_types()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.cycles + 1)]
 ev[0].record()
@@ -53,7 +55,7 @@ for k, (n, d) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
 if args.brief:
     sys.exit(0)
 # one target layer in the middle of the verify step
-per_layer = 14
+per_layer = 14 if args.two_phase_attention else 13
 start = 2 + 5 * per_layer if len(types) > 2 + 6 * per_layer else 0
 print("phases of one target layer:")
 for i in range(start, min(start + per_layer, len(types))):

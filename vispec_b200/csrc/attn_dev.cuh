@@ -12,6 +12,14 @@
 
 namespace vs {
 
+// Optional checkpoint clocks (compile with -DVS_PROGRAM_CLK): see program_dev.cuh
+#ifdef VS_PROGRAM_CLK
+__device__ long long g_clk[64];
+#define ACLK(i) do { if (aclk_on) g_clk[i] = clock64(); } while (0)
+#else
+#define ACLK(i)
+#endif
+
 constexpr int ATT_CHUNK = 64;      // keys per chunk
 constexpr int ATT_THREADS = 256;   // one team
 constexpr int ATT_WARPS = ATT_THREADS / 32;
@@ -364,6 +372,334 @@ __device__ __forceinline__ void attn_pv_item(const AttnArgs& p, AttnSmem& sm, in
     *reinterpret_cast<uint2*>(p.O + (long)(t0 + q) * p.ldo + head * 128 + d4) = *reinterpret_cast<const uint2*>(o4);
   }
   if (tid == 0) p.counters[head * tq_blocks + tqb] = 0;
+}
+
+
+// =================================================================================================================
+// Fused single-phase attention for the persistent program kernel (short and medium contexts).
+//
+// One item = (head, kv split) and EVERY item of the phase is resident at the same time (one per 256-thread team), so
+// the two passes of the algorithm above can meet in the middle of the phase instead of at a grid barrier:
+//   load Q + this split's K chunks (<= 2)  ->  S = Q K^T in registers, split max / sum-exp  ->  publish the statistics,
+//   start loading the V chunks into the K buffers  ->  wait for the head's other splits (per-head arrival counter)  ->
+//   exact global softmax denominators  ->  P in the reference's rounding (from the registers)  ->  P V  ->  partial O,
+//   last split of the head reduces in split order.
+// K and V are read once, scores never leave the SM, one HBM latency is exposed instead of two plus a barrier.
+// Capacity: n_splits * 2 * 64 keys (1152 at 32 heads on 148 SMs); the caller picks the two-phase path beyond it.
+// =================================================================================================================
+struct __align__(128) AttnFusedSmem {
+  uint8_t qp[VS_TOK * ATT_ROW_B];            // Q tile [32][128] bf16 (pass 1), then P [32][<=128 keys] bf16 (pass 2)
+  uint8_t kv[2][ATT_CHUNK * ATT_ROW_B];      // K chunks, then V chunks
+  float red[ATT_WARPS][VS_TOK];
+  float rowm[VS_TOK];
+  float gM[VS_TOK], gL[VS_TOK];
+  int last;
+};
+constexpr int ATT_FUSED_CPS = 2;             // chunks per split the fused item can hold
+
+__device__ __forceinline__ unsigned int att_ld_relaxed(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// head_cnt: per-head arrival counter, monotonic across launches (epoch = launches completed before this one).
+// stats layout (p.stats): [head][split][32 rows] float2 (max, sum exp).
+template <class Sync>
+__device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem& sm, int head, int split, int n_splits,
+                                                unsigned int* head_cnt, unsigned int epoch, int tid, Sync sync) {
+  const int kvh = head / (p.n_heads / p.n_kv_heads);
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n_ctx = p.n_ctx ? __ldcg(p.n_ctx) : p.n_ctx_host;
+  const int kv_len = n_ctx + p.n_new;
+  const int n_chunks = (kv_len + ATT_CHUNK - 1) / ATT_CHUNK;
+  const int cps = (n_chunks + n_splits - 1) / n_splits;           // chunks per split (contiguous)
+  if (cps > ATT_FUSED_CPS) __trap();                              // the host selects the two-phase program beyond this
+  const int c_lo = min(split * cps, n_chunks), c_hi = min(c_lo + cps, n_chunks);
+  const int nck = c_hi - c_lo;                                    // 0, 1 or 2 chunks
+  const int tq_rows = min(VS_TOK, p.Tq);
+  const int g = lane >> 2, t4 = lane & 3;
+  const int key_lo = c_lo * ATT_CHUNK;
+  const bf16* kbase = p.K + (long)kvh * p.kv_head_stride;
+  const bf16* vbase = p.V + (long)kvh * p.kv_head_stride;
+#ifdef VS_PROGRAM_CLK
+  const bool aclk_on = blockIdx.x == 0 && tid == 0 && head == 0;
+#endif
+  ACLK(0);
+
+  // ---- loads of pass 1
+  att_load_rows_async(sm.qp, p.Q + (long)head * p.q_head_stride, 0, tq_rows, VS_TOK, tid);
+#pragma unroll
+  for (int j = 0; j < ATT_FUSED_CPS; ++j)
+    if (j < nck)
+      att_load_rows_async(sm.kv[j], kbase, key_lo + j * ATT_CHUNK, min(ATT_CHUNK, kv_len - key_lo - j * ATT_CHUNK),
+                          ATT_CHUNK, tid);
+  cp_async_commit();
+  ACLK(12);
+  unsigned long long vis[ATT_FUSED_CPS][4];
+  {
+    unsigned long long qb[4] = {0ull, 0ull, 0ull, 0ull};
+    if (!p.causal && p.bits) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qb[i] = __ldcg(p.bits + min((i >> 1) * 16 + g + (i & 1) * 8, tq_rows - 1));
+    }
+#ifdef VS_PROGRAM_CLK
+    if (aclk_on) g_clk[14] = (long long)(qb[0] + qb[1] + qb[2] + qb[3]);
+#endif
+    ACLK(13);
+#pragma unroll
+    for (int j = 0; j < ATT_FUSED_CPS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        vis[j][i] = att_visible_mask(p, n_ctx, kv_len, (i >> 1) * 16 + g + (i & 1) * 8, qb[i], key_lo + j * ATT_CHUNK);
+  }
+  const float inv_div = sqrtf((float)VS_HEAD_DIM);
+  ACLK(1);
+  cp_async_wait<0>();
+  sync();
+  ACLK(2);
+
+  // ---- S = Q K^T: acc[j][mb][e]: query = mb*16 + g + (e>>1)*8, key = key_lo + 64*j + 8*warp + 2*t4 + (e&1)
+  float acc[ATT_FUSED_CPS][2][4];
+  const int kofs = warp * 8 + 2 * t4;
+  float lmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int j = 0; j < ATT_FUSED_CPS; ++j) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][a][e] = -INFINITY;
+    if (j < nck) {
+      float c[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[a][e] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        uint32_t bfr[2];
+        ldmatrix_x2(bfr, sm.kv[j] + att_swz256(warp * 8 + (lane & 7), kk * 2 + ((lane >> 3) & 1)));
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          uint32_t afr[4];
+          const int mat = lane >> 3;
+          ldmatrix_x4(afr, sm.qp + att_swz256(mb * 16 + (lane & 7) + (mat & 1) * 8, kk * 2 + (mat >> 1)));
+          mma_bf16(c[mb], afr, bfr[0], bfr[1]);
+        }
+      }
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int eh = 0; eh < 2; ++eh) {
+          const int qi = mb * 2 + eh;
+          float s0 = c[mb][eh * 2], s1 = c[mb][eh * 2 + 1];
+          s0 = p.eager ? rbf(rbf(s0) / inv_div) : s0 * p.scale;
+          s1 = p.eager ? rbf(rbf(s1) / inv_div) : s1 * p.scale;
+          if (!((vis[j][qi] >> kofs) & 1ull)) s0 = -INFINITY;
+          if (!((vis[j][qi] >> (kofs + 1)) & 1ull)) s1 = -INFINITY;
+          acc[j][mb][eh * 2] = s0;
+          acc[j][mb][eh * 2 + 1] = s1;
+          lmax[qi] = fmaxf(lmax[qi], fmaxf(s0, s1));
+        }
+    }
+  }
+  ACLK(3);
+  // ---- split statistics: row max, then sum exp
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    lmax[i] = fmaxf(lmax[i], __shfl_xor_sync(0xffffffffu, lmax[i], 1));
+    lmax[i] = fmaxf(lmax[i], __shfl_xor_sync(0xffffffffu, lmax[i], 2));
+    if (t4 == 0) sm.red[warp][(i >> 1) * 16 + g + (i & 1) * 8] = lmax[i];
+  }
+  sync();                                                          // also: every warp is done with Q and K in shared memory
+  // the V chunks take the place of the K chunks; in flight during the statistics exchange
+#pragma unroll
+  for (int j = 0; j < ATT_FUSED_CPS; ++j)
+    if (j < nck)
+      att_load_rows_async(sm.kv[j], vbase, key_lo + j * ATT_CHUNK, min(ATT_CHUNK, kv_len - key_lo - j * ATT_CHUNK),
+                          ATT_CHUNK, tid);
+  cp_async_commit();
+  if (tid < VS_TOK) {
+    float m = sm.red[0][tid];
+#pragma unroll
+    for (int w = 1; w < ATT_WARPS; ++w) m = fmaxf(m, sm.red[w][tid]);
+    sm.rowm[tid] = m;
+  }
+  sync();
+  float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < ATT_FUSED_CPS; ++j)
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int eh = 0; eh < 2; ++eh) {
+        const int qi = mb * 2 + eh;
+        const float rm = sm.rowm[mb * 16 + g + eh * 8];
+        const float s0 = acc[j][mb][eh * 2], s1 = acc[j][mb][eh * 2 + 1];
+        if (s0 != -INFINITY) lsum[qi] += expf(s0 - rm);
+        if (s1 != -INFINITY) lsum[qi] += expf(s1 - rm);
+      }
+  sync();                                                          // rowm consumed before red is overwritten
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    lsum[i] += __shfl_xor_sync(0xffffffffu, lsum[i], 1);
+    lsum[i] += __shfl_xor_sync(0xffffffffu, lsum[i], 2);
+    if (t4 == 0) sm.red[warp][(i >> 1) * 16 + g + (i & 1) * 8] = lsum[i];
+  }
+  sync();
+  float* stat_head = p.stats + (long)head * p.max_chunks * VS_TOK * 2;
+  if (tid < VS_TOK) {
+    float l = sm.red[0][tid];
+#pragma unroll
+    for (int w = 1; w < ATT_WARPS; ++w) l += sm.red[w][tid];        // fixed order
+    *reinterpret_cast<float2*>(stat_head + ((long)split * VS_TOK + tid) * 2) = make_float2(sm.rowm[tid], l);
+  }
+  sync();
+  ACLK(4);
+  // ---- publish, then wait for the other splits of this head
+  if (tid == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(head_cnt + head) : "memory");
+    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
+    while (att_ld_relaxed(head_cnt + head) < want) {
+    }
+  }
+  sync();
+  ACLK(5);
+  // ---- exact global denominators from the split statistics: 8 lanes per row, splits part, part+8 (fixed order)
+  {
+    const int q = tid >> 3, part = tid & 7;
+    float2 st[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      st[j] = __ldcg(reinterpret_cast<const float2*>(stat_head + ((long)min(part + 8 * j, n_splits - 1) * VS_TOK + q) * 2));
+    float m = -INFINITY, l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (part + 8 * j < n_splits && st[j].x != -INFINITY) {
+        const float mn = fmaxf(m, st[j].x);
+        l = l * expf(m - mn) + st[j].y * expf(st[j].x - mn);
+        m = mn;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
+      const float mn = fmaxf(m, mo);
+      const float a = m == -INFINITY ? 0.f : l * expf(m - mn);
+      const float b = mo == -INFINITY ? 0.f : lo * expf(mo - mn);
+      l = a + b;
+      m = mn;
+    }
+    if (part == 0) { sm.gM[q] = m; sm.gL[q] = l; }
+  }
+  sync();
+  ACLK(6);
+  // ---- P in the reference's rounding, written over the Q tile: row q, key column 64*j + 8*warp + 2*t4 (+1)
+#pragma unroll
+  for (int j = 0; j < ATT_FUSED_CPS; ++j)
+    if (j < nck) {
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int eh = 0; eh < 2; ++eh) {
+          const int q = mb * 16 + g + eh * 8;
+          const float gm = sm.gM[q], gl = sm.gL[q];
+          float pr[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float s = acc[j][mb][eh * 2 + e];
+            float v = 0.f;
+            if (s != -INFINITY) {
+              const float ex = expf(s - gm);
+              v = p.eager ? ex / gl : ex;
+            }
+            pr[e] = v;
+          }
+          const int kx = j * ATT_CHUNK + kofs;                      // even
+          *reinterpret_cast<__nv_bfloat162*>(sm.qp + att_swz256(q, kx >> 3) + (kx & 7) * 2) = __floats2bfloat162_rn(pr[0], pr[1]);
+        }
+    }
+  ACLK(7);
+  cp_async_wait<0>();
+  sync();
+  ACLK(8);
+  // ---- O += P V: warp w owns output columns 16w .. 16w+15
+  float oacc[2][2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[a][b][e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < ATT_FUSED_CPS; ++j)
+    if (j < nck) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t afr[2][4];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const int mat = lane >> 3;
+          ldmatrix_x4(afr[mb], sm.qp + att_swz256(mb * 16 + (lane & 7) + (mat & 1) * 8, j * 8 + kk * 2 + (mat >> 1)));
+        }
+        uint32_t bfr[4];
+        {
+          const int mat = lane >> 3;
+          ldmatrix_x4_trans(bfr, sm.kv[j] + att_swz256(kk * 16 + (lane & 7) + (mat & 1) * 8, warp * 2 + (mat >> 1)));
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          mma_bf16(oacc[mb][0], afr[mb], bfr[0], bfr[1]);
+          mma_bf16(oacc[mb][1], afr[mb], bfr[2], bfr[3]);
+        }
+      }
+    }
+  ACLK(9);
+  // ---- publish the partial O tile; the last split of the head reduces in split order
+  float* obase = p.opart + ((long)head * n_splits) * VS_TOK * 128;
+  float* mine = obase + (long)split * VS_TOK * 128;
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int eh = 0; eh < 2; ++eh) {
+        const int q = mb * 16 + g + eh * 8;
+        const int d = warp * 16 + nb * 8 + 2 * t4;
+        *reinterpret_cast<float2*>(mine + q * 128 + d) = make_float2(oacc[mb][nb][eh * 2], oacc[mb][nb][eh * 2 + 1]);
+      }
+  __threadfence();
+  sync();
+  if (tid == 0) {
+    int old = atomicAdd(&p.counters[head], 1);
+    sm.last = (old == n_splits - 1);
+  }
+  sync();
+  ACLK(10);
+  if (!sm.last) return;
+  __threadfence();
+  for (int i = tid; i < VS_TOK * 32; i += ATT_THREADS) {
+    const int q = i >> 5, d4 = (i & 31) * 4;
+    if (q >= tq_rows) continue;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < n_splits; s0 += 4) {
+      float4 t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        t[j] = __ldcg(reinterpret_cast<const float4*>(obase + (long)min(s0 + j, n_splits - 1) * VS_TOK * 128 + q * 128 + d4));
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (s0 + j < n_splits) { v.x += t[j].x; v.y += t[j].y; v.z += t[j].z; v.w += t[j].w; }
+    }
+    if (!p.eager) {
+      const float l = sm.gL[q];
+      v.x /= l; v.y /= l; v.z /= l; v.w /= l;
+    }
+    bf16 o4[4] = {f2bf(v.x), f2bf(v.y), f2bf(v.z), f2bf(v.w)};
+    *reinterpret_cast<uint2*>(p.O + (long)q * p.ldo + head * 128 + d4) = *reinterpret_cast<const uint2*>(o4);
+  }
+  if (tid == 0) p.counters[head] = 0;
+  ACLK(11);
 }
 
 }  // namespace vs

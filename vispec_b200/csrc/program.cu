@@ -40,11 +40,11 @@ namespace vs {
 
 namespace {
 
-constexpr int BM = PG_BM, BK = PG_BK, NS = 8;
+constexpr int BM = PG_BM, BK = PG_BK, NS = 6;
 constexpr int W_STAGE = BM * BK * 2;             // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;         // 4096
 constexpr int STAGE_BYTES = W_STAGE + X_STAGE;   // 20480 (multiple of 1024)
-constexpr int BIG_SMEM = 26112;                  // scratch of one attention team (AttnSmem); both together also stage the
+constexpr int BIG_SMEM = 43008;                  // scratch of one attention team (AttnSmem); both together also stage the
                                                  // tree ops and the top-k merge on CTA 0
 constexpr int TEAM_SMEM = 1024;                  // reduction scratch of one small team
 constexpr int TEAM_OFF = NS * STAGE_BYTES + PG_BIG_TEAMS * BIG_SMEM;
@@ -57,14 +57,18 @@ static_assert(PHASE_WORDS <= PG_WORKERS, "phase descriptor larger than one word 
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int TMEM_COLS = 64;
 static_assert(sizeof(AttnSmem) <= BIG_SMEM, "team scratch too small for attention");
+static_assert(sizeof(AttnFusedSmem) <= BIG_SMEM, "team scratch too small for fused attention");
 static_assert(sizeof(TreeSmem) <= BIG_SMEM, "team scratch too small for the tree ops");
 static_assert(sizeof(ScanSmem) <= BIG_SMEM, "team scratch too small for the vocabulary scans");
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
+// NOTE: the phase descriptor lives in shared memory; the bodies below read its fields many times between barriers and
+// inline asm with memory clobbers, which would turn every use into a fresh generic load.  Each phase therefore works on
+// a private (register) copy of the arguments it needs.
 __device__ __noinline__ void attn_s_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, BigTeamSync tsync) {
-  const AttnArgs& a = ph.attn;
+  const AttnArgs a = ph.attn;
   const int n_ctx = a.n_ctx ? ld_vol(a.n_ctx) : a.n_ctx_host;
   const int n_chunks = (n_ctx + a.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
   const int n_items = a.n_heads * n_chunks;
@@ -73,11 +77,18 @@ __device__ __noinline__ void attn_s_phase(const Phase& ph, int gteam, int n_team
     attn_scores_item(a, sm, item / n_chunks, 0, 1, item % n_chunks, true, tt, tsync);
 }
 __device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, BigTeamSync tsync) {
-  const AttnArgs& a = ph.attn;
+  const AttnArgs a = ph.attn;
   const int n_items = a.n_heads * a.pv_splits;
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(tsm);
   for (int item = gteam; item < n_items; item += n_teams)
     attn_pv_item(a, sm, item / a.pv_splits, 0, 1, item % a.pv_splits, a.pv_splits, tt, tsync);
+}
+__device__ __noinline__ void attn_fused_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
+                                              BigTeamSync tsync) {
+  const AttnArgs a = ph.attn;
+  if (gteam < a.n_heads * a.pv_splits)       // one resident item per team: the items of a head wait for each other
+    attn_fused_item(a, *reinterpret_cast<AttnFusedSmem*>(tsm), gteam / a.pv_splits, gteam % a.pv_splits, a.pv_splits,
+                    ph.tile_cnt, epoch, tt, tsync);
 }
 __device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team_base) {
   // the tree bodies read device state with plain loads: drop whatever this SM's L1 still holds from an earlier phase of
@@ -337,6 +348,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
         case PH_ATTN_S: attn_s_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
         case PH_ATTN_PV: attn_pv_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
+        case PH_ATTN_FUSED: attn_fused_phase(ph, epoch, gbteam, btt, bsm, bsync); break;
         case PH_ARGMAX: argmax_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_LSM_STATS: lsm_stats_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_LSM_CAND: lsm_cand_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
@@ -400,6 +412,7 @@ struct vs_program {
   size_t ssq_floats = 0;
   size_t tile_cnt_count = 0;  // per-tile arrival counters of all fused GEMM+epilogue pairs
   bool fuse_epilogue = true;  // epilogue phases wait on per-tile counters instead of a grid barrier
+  bool attn_fused = false;    // attention as ONE phase (kv length limited to vs_attention_fused_capacity)
   size_t keys_count = 0;      // u64 entries of the arg-max / top-k candidate buffer
   size_t lstats_count = 0;    // float2 entries of the log-softmax slice statistics
   int grid = 0;
@@ -569,12 +582,34 @@ int prog_add_rows(vs_program* pg, const bf16* src, long lds, const int* idx, int
   return VS_OK;
 }
 
+// kv splits of the fused single-phase attention: every (head, split) item needs its own resident 256-thread team
+static int fused_splits(int G, int n_heads, int pv_splits_cap, int max_chunks) {
+  int sp = (PG_BIG_TEAMS * G) / (n_heads > 0 ? n_heads : 1);
+  if (sp > 16) sp = 16;
+  if (sp > pv_splits_cap) sp = pv_splits_cap;
+  if (sp > max_chunks) sp = max_chunks;
+  return sp;
+}
+
 int prog_add_attention(vs_program* pg, const AttnArgs& a) {
   if (a.Tq < 1 || a.Tq > VS_TOK) return pfail(VS_ERR_INVALID, "vs_program_add_attention", "programs handle 1..32 query rows");
   if (!a.scores || !a.stats || !a.opart || !a.counters || a.pv_splits < 1 || a.max_chunks < 1)
     return pfail(VS_ERR_INVALID, "vs_program_add_attention", "missing workspace");
   const int G = pg->grid ? pg->grid : device_sms();
   pg->grid = G;
+  if (pg->attn_fused) {
+    const int sp = fused_splits(G, a.n_heads, a.pv_splits, a.max_chunks);
+    if (sp < 1 || a.n_heads * sp > PG_BIG_TEAMS * G)
+      return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_attention", "too many heads for the fused attention phase");
+    Phase f = blank(PH_ATTN_FUSED, a.Tq);
+    f.attn = a;
+    f.attn.pv_splits = sp;
+    // per-head arrival counters live with the per-tile counters of the fused epilogues (+1: 0 stays "none")
+    f.tile_cnt = reinterpret_cast<unsigned int*>(uintptr_t(pg->tile_cnt_count + 1));
+    pg->tile_cnt_count += a.n_heads;
+    pg->phases.push_back(f);
+    return VS_OK;
+  }
   Phase s = blank(PH_ATTN_S, a.Tq);
   s.attn = a;
   // as many kv splits as give every team one (head, split) item, bounded by the caller's workspace
@@ -714,7 +749,10 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   if (!strcmp(name, "pf_ahead")) pg->pf_ahead = value;
   else if (!strcmp(name, "trace")) pg->trace_on = value != 0;
   else if (!strcmp(name, "inflight")) pg->inflight = value;
-  else if (!strcmp(name, "fuse_epilogue")) {
+  else if (!strcmp(name, "attn_fused")) {
+    if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "attn_fused must be set before adding phases");
+    pg->attn_fused = value != 0;
+  } else if (!strcmp(name, "fuse_epilogue")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "fuse_epilogue must be set before adding phases");
     pg->fuse_epilogue = value != 0;
   }
@@ -725,6 +763,10 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
     pg->grid = value;
   } else return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "unknown option");
   return VS_OK;
+}
+
+int vs_attention_fused_capacity(int n_heads, int pv_splits_cap, int max_chunks) {
+  return vs::fused_splits(vs::device_sms(), n_heads, pv_splits_cap, max_chunks) * vs::ATT_FUSED_CPS * vs::ATT_CHUNK;
 }
 
 int vs_program_register_tiled(vs_program* pg, const void* w_row_major, const void* w_tiled) {

@@ -23,7 +23,8 @@ enum PhaseType : int {
   PH_LSM_STATS = 8, // bf16 log-softmax + top-k, step 1: (max, sum exp) per (row, slice)
   PH_TREE = 9,      // integer tree bookkeeping (level0 / expand / build / accept / commit / merges) on CTA 0
   PH_SPLICE = 10,   // KV-cache splice
-  PH_LSM_CAND = 11  // log-softmax + top-k, step 2: k best log-probs per (row, slice); merged by the next tree phase
+  PH_LSM_CAND = 11, // log-softmax + top-k, step 2: k best log-probs per (row, slice); merged by the next tree phase
+  PH_ATTN_FUSED = 12 // both attention passes in one phase (every (head, split) item resident; per-head arrival counters)
 };
 
 enum TreeOp : int {

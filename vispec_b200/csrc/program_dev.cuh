@@ -82,9 +82,8 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
 // Optional checkpoint clocks (compile with -DVS_PROGRAM_CLK): thread 0 of team 0 on CTA 0 records clock64() at a few
 // points of its first work item of a phase; tools read them back with vs_debug_clk().
 #ifdef VS_PROGRAM_CLK
-__device__ long long g_clk[64];
 #define CLK_DECL const bool clk_on = blockIdx.x == 0 && tt == 0 && sync.id == 2
-#define CLK(i) do { if (clk_on) g_clk[i] = clock64(); } while (0)
+#define CLK(i) do { if (clk_on) g_clk[16 + i] = clock64(); } while (0)
 #else
 #define CLK_DECL
 #define CLK(i)

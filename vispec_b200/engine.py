@@ -166,6 +166,8 @@ class ScratchBuffers:
         self.stats = z(heads * tok_blocks * self.max_chunks * 32 * 2, dtype=f32)
         self.opart = z(heads * tok_blocks * self.pv_splits * 32 * 128, dtype=f32)
         self.attn_counters = z(heads * tok_blocks + 64, dtype=i32)
+        # keys the single-phase ("fused") attention of a program can hold with these buffers
+        self.fused_kv_capacity = lib.vs_attention_fused_capacity(heads, self.pv_splits, self.max_chunks)
         self.c = L.Scratch(self.max_rows, L.ptr(self.h), L.ptr(self.x), L.ptr(self.q), L.ptr(self.attn),
                            L.ptr(self.act), L.ptr(self.partials), self.partials.numel(), L.ptr(self.counters),
                            L.ptr(self.scores), self.score_ld, L.ptr(self.stats), self.max_chunks,
@@ -243,11 +245,11 @@ class TargetEngine:
         self._v_bits = torch.zeros(32, dtype=torch.int64, device=dev)
         self._verify_progs: Dict[tuple, Program] = {}
 
-    def _verify_program(self, T: int, has_bits: bool) -> Program:
-        key = (T, has_bits)
+    def _verify_program(self, T: int, has_bits: bool, fused: bool) -> Program:
+        key = (T, has_bits, fused)
         p = self._verify_progs.get(key)
         if p is None:
-            p = Program(self.device).register_tiled(self.tiled)
+            p = Program(self.device, attn_fused=fused).register_tiled(self.tiled)
             p.add("verify_step", C.byref(self.c), C.byref(self.scratch.c), L.ptr(self._v_ids), L.ptr(self._v_pos),
                   L.ptr(self._v_bits) if has_bits else None, T, L.ptr(self.state), L.ptr(self.hidden_out),
                   L.ptr(self.logits), L.ptr(self.amax))
@@ -326,14 +328,17 @@ class TargetEngine:
         return logits_last, hidden
 
     # -- decode / verify through the C ABI -----------------------------------------------------------------
-    def verify(self, token_ids: torch.Tensor, pos_ids: torch.Tensor, bits: Optional[torch.Tensor], T: int):
-        """vs_verify_step on T <= 32 tokens appended (uncommitted) at CUR_LEN.  token_ids / pos_ids int32 device."""
+    def verify(self, token_ids: torch.Tensor, pos_ids: torch.Tensor, bits: Optional[torch.Tensor], T: int,
+               cur_len: Optional[int] = None):
+        """vs_verify_step on T <= 32 tokens appended (uncommitted) at CUR_LEN.  token_ids / pos_ids int32 device.
+        `cur_len` (host copy of CUR_LEN, if the caller has it) lets the short-context single-phase attention be used."""
         if use_programs():
             self._v_ids[:T].copy_(token_ids[:T])
             self._v_pos[:T].copy_(pos_ids[:T])
             if bits is not None:
                 self._v_bits[:T].copy_(bits[:T])
-            self._verify_program(T, bits is not None).run()
+            fused = cur_len is not None and cur_len + T <= self.scratch.fused_kv_capacity
+            self._verify_program(T, bits is not None, fused).run()
             return
         L.check(self.lib.vs_verify_step(C.byref(self.c), C.byref(self.scratch.c), L.ptr(token_ids), L.ptr(pos_ids),
                                         L.ptr(bits), T, L.ptr(self.state), L.ptr(self.hidden_out), L.ptr(self.logits),
@@ -345,7 +350,7 @@ class TargetEngine:
         T = ids.numel()
         cur = self.get_len()
         self._causal_pos[:T] = torch.arange(cur, cur + T, dtype=torch.int32, device=self.device)
-        self.verify(ids.to(device=self.device, dtype=torch.int32).contiguous(), self._causal_pos, None, T)
+        self.verify(ids.to(device=self.device, dtype=torch.int32).contiguous(), self._causal_pos, None, T, cur_len=cur)
         self.set_len(cur + T)
         return self.logits[:T]
 
@@ -408,8 +413,9 @@ class DraftEngine:
         self.last_img_hidden = torch.zeros(1, H, dtype=self.dtype, device=dev)
         self._alloc_tree()
         self.state: Optional[torch.Tensor] = None       # shared with the target engine (bind_state)
-        self._prog_levels: Optional[Program] = None     # LM head + draft levels + tree build after the prefill
-        self._prog_tree: Optional[Program] = None       # stable forward of the accepted rows + the above
+        self._prog_levels: Dict[bool, Program] = {}     # LM head + draft levels + tree build after the prefill
+        self._prog_tree: Dict[bool, Program] = {}       # stable forward of the accepted rows + the above
+        # (keyed by: single-phase attention usable for the current draft KV length)
 
     def _layer_struct(self) -> L.Layer:
         return L.Layer(None, L.ptr(self.w_qkv), L.ptr(self.b_qkv), L.ptr(self.w_o), L.ptr(self.ln_post),
@@ -554,12 +560,13 @@ class DraftEngine:
         self.prefill_pos = pos[:n_c]
         if use_programs():
             self.state[L.ST_NEXT_TOKEN] = int(sample_token)
-            if self._prog_levels is None:
-                self._prog_levels = Program(dev).register_tiled(self.tiled)
-                self._prog_levels.add("draft_levels", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb),
-                                      L.ptr(self.state), 1, self.state.data_ptr() + 4 * L.ST_NEXT_TOKEN, 0)
-                self._prog_levels.commit()
-            self._prog_levels.run()
+            fused = n_c + 8 * (cfg.depth + 1) <= self.scratch.fused_kv_capacity
+            if self._prog_levels.get(fused) is None:
+                pr = Program(dev, attn_fused=fused).register_tiled(self.tiled)
+                pr.add("draft_levels", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb),
+                       L.ptr(self.state), 1, self.state.data_ptr() + 4 * L.ST_NEXT_TOKEN, 0)
+                self._prog_levels[fused] = pr.commit()
+            self._prog_levels[fused].run()
             return
         L.check(lib.vs_draft_levels(C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state), 1,
                                     None, int(sample_token), st), "vs_draft_levels")
@@ -595,11 +602,13 @@ class DraftEngine:
         self.state[L.ST_LAST_ROW] = m - 1
         self.state[L.ST_NEXT_TOKEN] = int(sample_token)
         if use_programs():
-            if self._prog_tree is None:
-                self._prog_tree = Program(self.device).register_tiled(self.tiled)
-                self._prog_tree.add("draft_tree", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state))
-                self._prog_tree.commit()
-            self._prog_tree.run()
+            d_len = int(self.state[L.ST_D_LEN].item())
+            fused = d_len + L.VS_MAX_ACCEPT + 8 * (self.cfg.depth + 1) <= self.scratch.fused_kv_capacity
+            if self._prog_tree.get(fused) is None:
+                pr = Program(self.device, attn_fused=fused).register_tiled(self.tiled)
+                pr.add("draft_tree", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state))
+                self._prog_tree[fused] = pr.commit()
+            self._prog_tree[fused].run()
             return
         L.check(self.lib.vs_draft_tree(C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state),
                                        _stream()), "vs_draft_tree")

@@ -94,7 +94,7 @@ class TargetLM:
                     raise ValueError("tree_mask size does not match the number of tree tokens")
                 weights = (1 << torch.arange(q_len, device=eng.device, dtype=torch.int64))
                 bits = (tm.long() * weights[None]).sum(dim=1).contiguous()
-            eng.verify(ids, pos, bits, q_len)
+            eng.verify(ids, pos, bits, q_len, cur_len=cur)
             hidden = eng.hidden_out[:q_len].clone()[None]
             logits = eng.logits[:q_len].float()[None]
             eng.set_len(cur + q_len)
@@ -124,12 +124,15 @@ class SpecModel:
         self._rec_evt = [torch.cuda.Event() for _ in range(2)]
         self._dec_evt = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         self.last_decode_ms = 0.0
-        self._cycle_prog: Optional[Program] = None
+        self._cycle_progs: Dict[bool, Program] = {}
 
-    def cycle_program(self, trace: bool = False, pf_ahead: Optional[int] = None, inflight: Optional[int] = None) -> Program:
-        """The whole draft+verify cycle (spec_model_ours.py:484-547 loop body) as one persistent-kernel launch."""
+    def cycle_program(self, trace: bool = False, pf_ahead: Optional[int] = None, inflight: Optional[int] = None,
+                      attn_fused: bool = True) -> Program:
+        """The whole draft+verify cycle (spec_model_ours.py:484-547 loop body) as one persistent-kernel launch.
+        attn_fused: single-phase attention (target KV + tree and draft KV must stay within
+        `scratch.fused_kv_capacity`; specgenerate switches to the two-phase program beyond it)."""
         eng_t, eng_d = self.base_model_engine, self.spec_layer.engine
-        p = Program(eng_t.device, pf_ahead=pf_ahead, trace=trace)
+        p = Program(eng_t.device, pf_ahead=pf_ahead, trace=trace, attn_fused=attn_fused)
         p.register_tiled(eng_t.tiled + eng_d.tiled)
         if inflight is not None:
             p.set_option("inflight", inflight)
@@ -273,12 +276,17 @@ class SpecModel:
         lib = eng_t.lib
 
         programs = use_programs()
-        if programs and self._cycle_prog is None:
-            self._cycle_prog = self.cycle_program()
+        cap_t, cap_d = eng_t.scratch.fused_kv_capacity, eng_d.scratch.fused_kv_capacity
 
         def launch(slot):
             if programs:
-                self._cycle_prog.run(st)
+                # cur_len / d_rows are one cycle behind when a launch is issued ahead: VS_MAX_ACCEPT rows of slack
+                fused = (cur_len + 2 * L.VS_MAX_ACCEPT + T <= cap_t and
+                         d_rows + 3 * L.VS_MAX_ACCEPT + 8 * (self.spec_layer.depth + 1) <= cap_d)
+                prog = self._cycle_progs.get(fused)
+                if prog is None:
+                    prog = self._cycle_progs[fused] = self.cycle_program(attn_fused=fused)
+                prog.run(st)
                 self._rec_host[slot].copy_(self._rec_dev[0], non_blocking=True)
                 self._rec_evt[slot].record()
                 return

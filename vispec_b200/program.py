@@ -14,7 +14,7 @@ class Program:
     """Build with the `add_*` methods (thin wrappers of `vs_program_add_*`; `p.lib` exposes the rest), `commit()`, then
     `run()` any number of times."""
 
-    def __init__(self, device, pf_ahead: Optional[int] = None, trace: bool = False):
+    def __init__(self, device, pf_ahead: Optional[int] = None, trace: bool = False, attn_fused: bool = False):
         if torch.device(device).type != "cuda":
             raise RuntimeError("vispec_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = L.load()
@@ -28,6 +28,8 @@ class Program:
             self.set_option("pf_ahead", pf_ahead)
         if trace:
             self.set_option("trace", 1)
+        if attn_fused:
+            self.set_option("attn_fused", 1)
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
