@@ -403,7 +403,8 @@ __device__ __forceinline__ unsigned int att_ld_relaxed(const unsigned int* p) {
   return v;
 }
 
-// head_cnt: per-head arrival counter, monotonic across launches (epoch = launches completed before this one).
+// head_cnt: 2 * n_heads arrival counters (statistics published | partial O published), monotonic across launches
+// (epoch = launches completed before this one).
 // stats layout (p.stats): [head][split][32 rows] float2 (max, sum exp).
 template <class Sync>
 __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem& sm, int head, int split, int n_splits,
@@ -655,7 +656,8 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
       }
     }
   ACLK(9);
-  // ---- publish the partial O tile; the last split of the head reduces in split order
+  // ---- publish the partial O tile, wait for the head's other splits (second arrival counter), then every split
+  // reduces its share of the head's output in split order (float4 group i belongs to split i % n_splits)
   float* obase = p.opart + ((long)head * n_splits) * VS_TOK * 128;
   float* mine = obase + (long)split * VS_TOK * 128;
 #pragma unroll
@@ -668,17 +670,17 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
         const int d = warp * 16 + nb * 8 + 2 * t4;
         *reinterpret_cast<float2*>(mine + q * 128 + d) = make_float2(oacc[mb][nb][eh * 2], oacc[mb][nb][eh * 2 + 1]);
       }
-  __threadfence();
   sync();
   if (tid == 0) {
-    int old = atomicAdd(&p.counters[head], 1);
-    sm.last = (old == n_splits - 1);
+    unsigned int* cnt2 = head_cnt + p.n_heads + head;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt2) : "memory");
+    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
+    while (att_ld_relaxed(cnt2) < want) {
+    }
   }
   sync();
   ACLK(10);
-  if (!sm.last) return;
-  __threadfence();
-  for (int i = tid; i < VS_TOK * 32; i += ATT_THREADS) {
+  for (int i = split + tid * n_splits; i < VS_TOK * 32; i += ATT_THREADS * n_splits) {
     const int q = i >> 5, d4 = (i & 31) * 4;
     if (q >= tq_rows) continue;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -698,7 +700,6 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
     bf16 o4[4] = {f2bf(v.x), f2bf(v.y), f2bf(v.z), f2bf(v.w)};
     *reinterpret_cast<uint2*>(p.O + (long)q * p.ldo + head * 128 + d4) = *reinterpret_cast<const uint2*>(o4);
   }
-  if (tid == 0) p.counters[head] = 0;
   ACLK(11);
 }
 

@@ -606,7 +606,7 @@ int prog_add_attention(vs_program* pg, const AttnArgs& a) {
     f.attn.pv_splits = sp;
     // per-head arrival counters live with the per-tile counters of the fused epilogues (+1: 0 stays "none")
     f.tile_cnt = reinterpret_cast<unsigned int*>(uintptr_t(pg->tile_cnt_count + 1));
-    pg->tile_cnt_count += a.n_heads;
+    pg->tile_cnt_count += 2 * a.n_heads;
     pg->phases.push_back(f);
     return VS_OK;
   }
