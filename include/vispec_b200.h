@@ -42,6 +42,10 @@ enum vs_state_slot {
   VS_ST_MAX_DEPTH = 9,  /* used columns of retrieve_indices */
   VS_ST_LAST_ROW = 10,  /* row of the stable forward whose hidden feeds the LM head */
   VS_ST_CYCLE = 11,     /* cycles completed */
+  VS_ST_TEMP_BITS = 12, /* T > 0 only: float bits of the temperature (0 = greedy); tree build sorts the leaf paths
+                           when it is non-zero (cnets_ours.py:1215-1224) */
+  VS_ST_RNG_SEED = 13,  /* T > 0 only: Philox key of the acceptance / sampling uniforms */
+  VS_ST_RNG_CTR = 14,   /* T > 0 only: draws so far (advanced by one per cycle) */
   VS_ST_SLOTS = 16
 };
 
@@ -315,6 +319,19 @@ int vs_program_add_tree_build(vs_program* pg, const vs_tree_bufs* tb, int32_t* s
                               int sample_token_host);
 int vs_program_add_accept_greedy(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, const int32_t* amax,
                                  int32_t* out_rec);
+/* T > 0 acceptance (utils.py:453-493 with the TemperatureLogitsWarper of prepare_logits_processor :39-55) +
+ * sampling of the next root token (utils.py:550-552): SpecInfer-style accept / reject along the tree with residual
+ * renormalisation, on the verify logits [total+1][V] (bf16).  Uniforms come from a Philox4x32-10 stream keyed by
+ * VS_ST_RNG_SEED / VS_ST_RNG_CTR (distributional parity with torch.rand_like / torch.multinomial), or -- for tests --
+ * from `uni_override` (device floats: [leaf][VS_RETRIEVE_LD] acceptance uniforms followed by one sampling uniform at
+ * index 32 * VS_RETRIEVE_LD).  Fills the same state / sel / stable_ids / out_rec as vs_accept_greedy. */
+int vs_program_add_accept_sampling(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, const void* logits, int64_t ldl,
+                                   int V, float temperature, const float* uni_override, int32_t* out_rec);
+/* vs_program_add_spec_cycle with the T > 0 acceptance above instead of arg-max + greedy accept */
+int vs_program_add_spec_cycle_sampling(vs_program* pg, const vs_target* t, const vs_scratch* ts, const vs_draft* dm,
+                                       const vs_scratch* ds, const vs_tree_bufs* tb, int32_t* state, void* kv_slab,
+                                       int64_t kv_max_pos, void* hidden_out, void* logits, float temperature,
+                                       int32_t* out_rec);
 int vs_program_add_kv_splice(vs_program* pg, void* slab, int n_slabs, int n_kv, int64_t max_pos, const int32_t* state,
                              const int32_t* sel_dev);
 int vs_program_add_decoder_layer(vs_program* pg, const vs_dims* d, const vs_layer* l, const vs_scratch* s,

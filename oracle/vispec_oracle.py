@@ -451,6 +451,50 @@ def evaluate_posterior_greedy(logits, candidates):
     return best, accept_length, logits[best, accept_length]
 
 
+def evaluate_posterior_sampling(logits, candidates, temperature: float, uni):
+    """utils.py:453-493 (T > 0): SpecInfer-style acceptance along the tree with residual renormalisation.
+
+    logits [n_leaves, depth, V] fp32 (tree logits gathered along every root->leaf path, utils.py:411);
+    candidates [n_leaves, depth] (pad -1); `uni` [n_leaves, depth] are the uniforms the reference draws with
+    torch.rand_like (:456) -- passed in so that the decisions can be reproduced.  The logits processor is the
+    TemperatureLogitsWarper of prepare_logits_processor (:39-55): logits / temperature.
+    Returns (best_candidate, accept_length, sample_p [V]) like the reference (accept_length already minus one)."""
+    logits_p = torch.softmax(logits / temperature, dim=-1)
+    accept_length = 1
+    accept_cand = candidates[0].clone()
+    best_candidate = 0
+    adjustflag = False
+    gtp = None
+    for i in range(1, candidates.shape[1]):
+        if i != accept_length:
+            break
+        adjustflag = False
+        is_eq = (candidates[:, :accept_length] == accept_cand[:accept_length]).all(dim=1)
+        fi = int(torch.nonzero(is_eq)[0, 0])
+        gtp = logits_p[fi, i - 1].clone()
+        seen = set()
+        for j in range(candidates.shape[0]):
+            if not bool(is_eq[j]):
+                continue
+            xi = int(candidates[j, i])
+            if xi == -1 or xi in seen:
+                continue
+            seen.add(xi)
+            if float(uni[j, i]) <= float(gtp[xi]):
+                accept_cand[accept_length] = xi
+                accept_length += 1
+                best_candidate = j
+                break
+            gtp[xi] = 0
+            gtp = gtp / gtp.sum()
+            adjustflag = True
+    if adjustflag and accept_length != candidates.shape[1]:
+        sample_p = gtp
+    else:
+        sample_p = logits_p[best_candidate, accept_length - 1]
+    return best_candidate, accept_length - 1, sample_p
+
+
 def kv_splice(kv, select_indices, prev_len: int):
     """KV-cache splice (utils.py:529-541): rows select_indices -> prev_len.. in every (layer,K/V,head)."""
     tgt = kv[..., select_indices.to(kv.device), :]

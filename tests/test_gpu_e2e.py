@@ -27,7 +27,7 @@ from vispec_b200.model.kv_cache import initialize_past_key_values  # noqa: E402
 from vispec_b200.model.spec_model_ours import SpecModel  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
+CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if "sampling" not in p)
 DEV = "cuda"
 
 
@@ -174,11 +174,11 @@ def test_specgenerate_switches_attention_program_at_capacity():
     if emb is not None:
         kw.update(inputs_embeds=emb.to(DEV), image_mask=mask.to(DEV))
     ref_out, _, _, ref_acc = model.specgenerate(ids.to(DEV), **kw)
-    assert set(model._cycle_progs) == {True}                       # everything fit the fused phase
+    assert set(model._cycle_progs) == {(True, 0.0)}                # everything fit the fused phase
     # shrink the capacity so that the target crosses it after a few cycles
     model.base_model_engine.scratch.fused_kv_capacity = ids.shape[1] + 2 * L.VS_MAX_ACCEPT + 30 + 12
     out, _, _, acc = model.specgenerate(ids.to(DEV), **kw)
-    assert set(model._cycle_progs) == {True, False}                # both programs were used
+    assert set(model._cycle_progs) == {(True, 0.0), (False, 0.0)}  # both programs were used
     assert torch.equal(out, ref_out) and acc == ref_acc
 
 
@@ -205,8 +205,8 @@ def test_error_conventions():
     model = build(tcfg, dcfg, tw, dw)
     with pytest.raises(ValueError):
         model.specgenerate(None)
-    with pytest.raises(NotImplementedError):
-        model.specgenerate(ids.to(DEV), temperature=1.0)
+    with pytest.raises(NotImplementedError):                 # only the temperature warper is on the B200 path
+        model.specgenerate(ids.to(DEV), temperature=1.0, top_p=0.9)
     two_runs = torch.zeros(1, 30, dtype=torch.bool)
     two_runs[0, 3:8] = True
     two_runs[0, 12:20] = True

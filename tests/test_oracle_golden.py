@@ -10,7 +10,7 @@ from oracle import synth
 from oracle import vispec_oracle as vo
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
+CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if "sampling" not in p)
 
 
 def load_case(name):
@@ -70,3 +70,22 @@ def test_spec_equals_greedy(name):
     out = vo.greedy_generate(target, ids, emb, n_new)
     assert torch.equal(out, g["greedy_ids"])
     assert torch.equal(out, g["output_ids"])
+
+
+def test_oracle_sampling_acceptance_matches_reference():
+    """T > 0: the oracle's restatement of utils.py:453-493 must reproduce what the unmodified
+    reference returned for the same uniforms (tests/golden/make_golden_sampling.py)."""
+    g = torch.load(os.path.join(GOLDEN, "posterior_sampling.pt"), weights_only=False)
+    assert len(g["cases"]) >= 24
+    seen = set()
+    for c in g["cases"]:
+        tree_logits = c["tree_logits"].float()
+        retrieve, draft_tokens = c["retrieve"], c["draft_tokens"]
+        logits = tree_logits[retrieve]
+        pad = torch.full((1, 1), -1, dtype=torch.long)
+        cand = torch.cat((draft_tokens, pad), dim=1)[0, retrieve]
+        best, acc, sample_p = vo.evaluate_posterior_sampling(logits, cand, c["temperature"], c["uni"])
+        assert (best, acc) == (c["best"], c["accept_length"])
+        assert torch.equal(sample_p, c["sample_p"])
+        seen.add(acc)
+    assert len(seen) >= 4          # the fixture covers rejections at the root up to full-depth accepts

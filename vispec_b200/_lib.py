@@ -15,7 +15,7 @@ VS_TOK_BLOCK = 32
 VS_RETRIEVE_LD = 8
 VS_MAX_ACCEPT = 8
 (ST_CUR_LEN, ST_PREV_LEN, ST_ACCEPT, ST_BEST, ST_NEXT_TOKEN, ST_D_LEN, ST_D_POS, ST_M, ST_N_LEAVES, ST_MAX_DEPTH,
- ST_LAST_ROW, ST_CYCLE) = range(12)
+ ST_LAST_ROW, ST_CYCLE, ST_TEMP_BITS, ST_RNG_SEED, ST_RNG_CTR) = range(15)
 ST_SLOTS = 16
 EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_HEADS = range(4)
 (PH_NOP, PH_GEMM, PH_EPI, PH_NORM, PH_ROWS, PH_ATTN_S, PH_ATTN_PV, PH_ARGMAX, PH_LSM_STATS, PH_TREE, PH_SPLICE,
@@ -143,6 +143,10 @@ _SIGS = {
     "vs_program_add_tree_build": (C.c_int, [c_vp, C.POINTER(TreeBufs), c_vp, c_vp, C.c_int]),
     "vs_program_add_accept_greedy": (C.c_int, [c_vp, C.POINTER(TreeBufs), c_vp, c_vp, c_vp]),
     "vs_program_add_kv_splice": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_i64, c_vp, c_vp]),
+    "vs_program_add_accept_sampling": (C.c_int, [c_vp, C.POINTER(TreeBufs), c_vp, c_vp, c_i64, C.c_int, c_f32, c_vp, c_vp]),
+    "vs_program_add_spec_cycle_sampling": (C.c_int, [c_vp, C.POINTER(Target), C.POINTER(Scratch), C.POINTER(Draft),
+                                                     C.POINTER(Scratch), C.POINTER(TreeBufs), c_vp, c_vp, c_i64, c_vp,
+                                                     c_vp, c_f32, c_vp]),
     "vs_program_add_decoder_layer": (C.c_int, [c_vp, C.POINTER(Dims), C.POINTER(Layer), C.POINTER(Scratch), C.POINTER(Rope),
                                                C.c_int, c_vp, c_vp, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int]),
     "vs_program_add_verify_step": (C.c_int, [c_vp, C.POINTER(Target), C.POINTER(Scratch), c_vp, c_vp, c_vp, C.c_int, c_vp,

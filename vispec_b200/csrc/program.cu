@@ -59,6 +59,7 @@ constexpr int TMEM_COLS = 64;
 static_assert(sizeof(AttnSmem) <= BIG_SMEM, "team scratch too small for attention");
 static_assert(sizeof(AttnFusedSmem) <= BIG_SMEM, "team scratch too small for fused attention");
 static_assert(sizeof(TreeSmem) <= BIG_SMEM, "team scratch too small for the tree ops");
+static_assert(sizeof(SampleSmem) <= BIG_SMEM, "team scratch too small for the sampling accept");
 static_assert(sizeof(ScanSmem) <= BIG_SMEM, "team scratch too small for the vocabulary scans");
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -108,6 +109,9 @@ __device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team
     tree_build_body(ph.tb, ph.state, ph.sample_token_dev, ph.sample_token_host, sm, wtid, PG_WORKERS, WorkerSync());
   else if (ph.tree_op == TREE_ACCEPT) tree_accept_body(ph.tb, ph.state, ph.amax, ph.out_rec, sm, wtid, WorkerSync());
   else if (ph.tree_op == TREE_COMMIT) tree_commit_body(ph.state, wtid);
+  else if (ph.tree_op == TREE_ACCEPT_SAMPLE)
+    tree_accept_sample_body(ph.tb, ph.state, ph.logits, ph.ldl, ph.V, ph.lstats, ph.n_slices, ph.inv_temp, ph.uni_override,
+                            ph.out_rec, *reinterpret_cast<SampleSmem*>(team_base), wtid, PG_WORKERS, WorkerSync());
 }
 
 struct GemmCursor {            // walks the GEMM phases of the program and this CTA's chunk range in each
@@ -686,6 +690,27 @@ int prog_add_tree(vs_program* pg, int op, const TreeBufs& tb, int* state, int le
     ph.T = merge->T; ph.n_slices = merge->n_slices; ph.k = merge->k; ph.keys = PROG_WS_KEYS;
     ph.top_val = merge->top_val; ph.top_idx = merge->top_idx; ph.amax_out = merge->amax_out;
   }
+  pg->phases.push_back(ph);
+  return VS_OK;
+}
+
+int prog_add_accept_sampling(vs_program* pg, const TreeBufs& tb, int* state, const bf16* logits, long ldl, int V,
+                             float temperature, const float* uni_override, int* out_rec) {
+  if (!(temperature > 0.f)) return pfail(VS_ERR_INVALID, "vs_program_add_accept_sampling", "temperature must be > 0");
+  const int T = tb.total + 1;
+  if (T < 1 || T > VS_TOK) return pfail(VS_ERR_INVALID, "vs_program_add_accept_sampling", "tree larger than 32 nodes");
+  if (V % 8 || ldl % 8 || (reinterpret_cast<uintptr_t>(logits) & 15))
+    return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_accept_sampling", "rows must be 16-byte aligned with V % 8 == 0");
+  const int ns = pick_slices(V);
+  if (ns > 64) return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_accept_sampling", "vocabulary too large");
+  Phase st = blank(PH_LSM_STATS, T);
+  st.logits = logits; st.ldl = ldl; st.V = V; st.n_slices = ns; st.lstats = PROG_WS_LSTATS; st.inv_temp = 1.0f / temperature;
+  pg->phases.push_back(st);
+  if ((size_t)T * ns > pg->lstats_count) pg->lstats_count = (size_t)T * ns;
+  Phase ph = st;
+  ph.type = PH_TREE;
+  ph.T = 0;
+  ph.tree_op = TREE_ACCEPT_SAMPLE; ph.tb = tb; ph.state = state; ph.out_rec = out_rec; ph.uni_override = uni_override;
   pg->phases.push_back(ph);
   return VS_OK;
 }

@@ -30,7 +30,8 @@ enum PhaseType : int {
 enum TreeOp : int {
   TREE_LEVEL0 = 0, TREE_EXPAND = 1, TREE_BUILD = 2, TREE_ACCEPT = 3, TREE_COMMIT = 4,
   TREE_MERGE_ARGMAX = 5,   // only the merge of PH_ARGMAX keys -> amax_out
-  TREE_MERGE_TOPK = 6      // only the merge of PH_LSM_CAND keys -> top_val / top_idx
+  TREE_MERGE_TOPK = 6,     // only the merge of PH_LSM_CAND keys -> top_val / top_idx
+  TREE_ACCEPT_SAMPLE = 7   // T > 0 acceptance + next-token sampling (needs the PH_LSM_STATS of the verify logits)
 };
 
 struct Phase {
@@ -74,6 +75,8 @@ struct Phase {
   int n_slices;               // vocabulary slices per row
   unsigned long long* keys;   // PH_ARGMAX: [T][n_slices]; PH_LSM_CAND: [T][n_slices][8]  (program workspace)
   float2* lstats;             // PH_LSM_STATS: [T][n_slices] (max, sum exp)                 (program workspace)
+  float inv_temp;             // PH_LSM_STATS / TREE_ACCEPT_SAMPLE: logits are scaled by 1 / temperature (0 -> 1)
+  const float* uni_override;  // TREE_ACCEPT_SAMPLE: test hook, see vs_program_add_accept_sampling
   // ---- PH_TREE
   int tree_op, level;
   TreeBufs tb; int* state; const int* amax; int* out_rec; const int* sample_token_dev; int sample_token_host;
@@ -116,6 +119,8 @@ int prog_add_lsm_topk(vs_program* pg, const bf16* logits, long ldl, int T, int V
                       int* top_idx, MergeInfo* fuse);
 int prog_add_tree(vs_program* pg, int op, const TreeBufs& tb, int* state, int level, const int* amax, int* out_rec,
                   const int* sample_token_dev, int sample_token_host, const MergeInfo* merge);
+int prog_add_accept_sampling(vs_program* pg, const TreeBufs& tb, int* state, const bf16* logits, long ldl, int V,
+                             float temperature, const float* uni_override, int* out_rec);
 int prog_add_splice(vs_program* pg, bf16* slab, int n_slabs, int n_kv, long max_pos, const int* state, const int* sel_dev);
 int prog_fail(int code, const char* where, const char* what);
 }  // namespace vs

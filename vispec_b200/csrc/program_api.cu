@@ -220,6 +220,11 @@ int vs_program_add_accept_greedy(vs_program* pg, const vs_tree_bufs* tb, int32_t
   REQUIRE(pg && tb && state && amax, "null operand");
   return vs::prog_add_tree(pg, vs::TREE_ACCEPT, *tb, state, 0, amax, out_rec, nullptr, 0, nullptr);
 }
+int vs_program_add_accept_sampling(vs_program* pg, const vs_tree_bufs* tb, int32_t* state, const void* logits, int64_t ldl,
+                                   int V, float temperature, const float* uni_override, int32_t* out_rec) {
+  REQUIRE(pg && tb && state && logits, "null operand");
+  return vs::prog_add_accept_sampling(pg, *tb, state, B(logits), ldl, V, temperature, uni_override, out_rec);
+}
 int vs_program_add_kv_splice(vs_program* pg, void* slab, int n_slabs, int n_kv, int64_t max_pos, const int32_t* state,
                              const int32_t* sel_dev) {
   REQUIRE(pg, "null program");
@@ -268,6 +273,21 @@ int vs_program_add_spec_cycle(vs_program* pg, const vs_target* t, const vs_scrat
   RET(vs::prog_add_tree(pg, vs::TREE_ACCEPT, *tb, state, 0, amax, out_rec, nullptr, 0, &mi));
   RET(vs::prog_add_splice(pg, B(kv_slab), 2 * t->dims.n_layers, t->dims.n_kv_heads, kv_max_pos, state, tb->sel));
   // accepted hidden states -> draft input rows (utils.py:543-546)
+  RET(vs::prog_add_rows(pg, B(hidden_out), t->dims.hidden, tb->sel, VS_TOK_BLOCK, 0, B(dm->x1), 2L * dm->dims.hidden,
+                        VS_MAX_ACCEPT, t->dims.hidden));
+  return draft_tree(pg, dm, ds, tb, state);
+}
+
+int vs_program_add_spec_cycle_sampling(vs_program* pg, const vs_target* t, const vs_scratch* ts, const vs_draft* dm,
+                                       const vs_scratch* ds, const vs_tree_bufs* tb, int32_t* state, void* kv_slab,
+                                       int64_t kv_max_pos, void* hidden_out, void* logits, float temperature,
+                                       int32_t* out_rec) {
+  REQUIRE(pg && t && ts && dm && ds && tb && state && kv_slab && hidden_out && logits, "null operand");
+  const int T = tb->total + 1;
+  REQUIRE(T <= VS_TOK_BLOCK, "tree larger than 32 nodes");
+  RET(verify_step(pg, t, ts, tb->draft_tokens, tb->verify_pos, tb->tree_bits, T, state, hidden_out, logits, nullptr, nullptr));
+  RET(vs::prog_add_accept_sampling(pg, *tb, state, B(logits), t->dims.vocab, t->dims.vocab, temperature, nullptr, out_rec));
+  RET(vs::prog_add_splice(pg, B(kv_slab), 2 * t->dims.n_layers, t->dims.n_kv_heads, kv_max_pos, state, tb->sel));
   RET(vs::prog_add_rows(pg, B(hidden_out), t->dims.hidden, tb->sel, VS_TOK_BLOCK, 0, B(dm->x1), 2L * dm->dims.hidden,
                         VS_MAX_ACCEPT, t->dims.hidden));
   return draft_tree(pg, dm, ds, tb, state);

@@ -437,13 +437,14 @@ __device__ __noinline__ void lsm_stats_phase(const Phase& ph, int gteam, int n_t
     int lo, hi;
     slice_bounds(ph.V, ph.n_slices, s, lo, hi);
     stage_slice(sm, ph.logits + (long)row * ph.ldl, lo, hi, tid, sync);
+    const float it = ph.inv_temp != 0.f ? ph.inv_temp : 1.f;     // T > 0 acceptance: statistics of logits / temperature
     float m = -INFINITY;
 #pragma unroll 1
-    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) m = fmaxf(m, bf2f(sm.x[i]));
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) m = fmaxf(m, bf2f(sm.x[i]) * it);
     m = bteam_max_f(m, sm, tid, sync);
     float l = 0.f;
 #pragma unroll 1
-    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) l += expf(bf2f(sm.x[i]) - m);
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) l += expf(bf2f(sm.x[i]) * it - m);
     l = bteam_sum_f(l, sm, tid, sync);
     if (tid == 0) ph.lstats[t * ph.n_slices + s] = make_float2(m, l);
   }

@@ -29,6 +29,7 @@ struct TreeSmem {
   int is_parent[64];
   int acc[64];
   int n_leaf, max_depth;
+  int paths[64][VS_RETRIEVE_LD];     // T > 0: leaf paths before they are sorted
 };
 
 // ---- draft level 0: after the stable forward's log-softmax/top-k on the last valid row ------------
@@ -153,11 +154,14 @@ __device__ __forceinline__ void tree_build_body(const TreeBufs& tb, int* st, con
     if (tid > 0) sm.is_parent[sm.parent_slot[tid]] = 1;
   }
   sync();
+  const bool sort_paths = st[VS_ST_TEMP_BITS] != 0;      // T > 0: rows sorted like cnets_ours.py:1215-1224
+  int my_rank = -1;
   if (tid < n && !sm.is_parent[tid]) {
     int rank = 0;
     for (int j = 0; j < tid; ++j) rank += !sm.is_parent[j];
+    my_rank = rank;
     int pos = __popcll(sm.bits[tid]) - 1;
-    int* row = tb.retrieve + rank * VS_RETRIEVE_LD;
+    int* row = sort_paths ? sm.paths[rank] : tb.retrieve + rank * VS_RETRIEVE_LD;
     for (int j = 0; j < VS_RETRIEVE_LD; ++j) row[j] = -1;
     int node = tid;
     for (int j = pos; j >= 0; --j) {
@@ -167,6 +171,22 @@ __device__ __forceinline__ void tree_build_body(const TreeBufs& tb, int* st, con
     atomicAdd(&sm.n_leaf, 1);
   }
   sync();
+  if (sort_paths && my_rank >= 0) {
+    // lexicographic order with -1 (padding) sorting last; paths are distinct, so ranks are a permutation
+    const int big = tb.total + 5;
+    int before = 0;
+    for (int o = 0; o < sm.n_leaf; ++o) {
+      if (o == my_rank) continue;
+      bool less = false;                                   // paths[o] < paths[my_rank] ?
+      for (int j = 0; j < VS_RETRIEVE_LD; ++j) {
+        const int a = sm.paths[o][j] >= 0 ? sm.paths[o][j] : big, b = sm.paths[my_rank][j] >= 0 ? sm.paths[my_rank][j] : big;
+        if (a != b) { less = a < b; break; }
+      }
+      before += less;
+    }
+    int* row = tb.retrieve + before * VS_RETRIEVE_LD;
+    for (int j = 0; j < VS_RETRIEVE_LD; ++j) row[j] = sm.paths[my_rank][j];
+  }
   if (tid == 0) {
     st[VS_ST_N_LEAVES] = sm.n_leaf;
     st[VS_ST_MAX_DEPTH] = sm.max_depth;
@@ -221,6 +241,220 @@ __device__ __forceinline__ void tree_accept_body(const TreeBufs& tb, int* st, co
       for (int j = 0; j < VS_MAX_ACCEPT; ++j) out_rec[2 + j] = j <= a ? tb.draft_tokens[row[j]] : -1;
     }
     st[VS_ST_CYCLE] += 1;
+  }
+}
+
+// ---- T > 0 acceptance + sampling (utils.py:453-493, :550-552) -----------------------------------------------------
+// Philox4x32-10 (counter-based, Salmon et al.): one call gives four 32-bit words
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float philox_uniform(unsigned int seed, unsigned int cycle, unsigned int index) {
+  const uint4 r = philox4x32(make_uint4(index, cycle, 0u, 0u), make_uint2(seed, 0x5bd1e995u));
+  return (float)(r.x >> 8) * (1.0f / 16777216.0f);        // [0, 1)
+}
+
+struct SampleSmem {
+  float px[32 * VS_RETRIEVE_LD];      // target probability of candidate (leaf, depth) under its prefix node
+  float uni[32 * VS_RETRIEVE_LD];
+  int cand[32 * VS_RETRIEVE_LD];      // candidate tokens (-1 = padding)
+  float rowM[32], rowL[32];           // softmax statistics of the tree rows under the temperature
+  float slice_mass[64];
+  float warp_tot[16];
+  int removed[VS_RETRIEVE_LD * 8];    // tokens rejected at the failing depth (at most top_k)
+  int n_removed, row, accept, best, slice, picked;
+  float target;
+};
+
+// logits [T][ldl] bf16; lstats [T][n_slices] (max, sum exp) of logits * inv_temp.  512 threads of CTA 0.
+template <class Sync>
+__device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int* st, const bf16* logits, long ldl, int V,
+                                                        const float2* lstats, int n_slices, float inv_temp,
+                                                        const float* uni_override, int* out_rec, SampleSmem& sm, int tid,
+                                                        int nthreads, Sync sync) {
+  const int n_leaves = st[VS_ST_N_LEAVES];
+  const int max_depth = st[VS_ST_MAX_DEPTH];
+  const int T = tb.total + 1;
+  const unsigned int seed = (unsigned int)st[VS_ST_RNG_SEED], cycle = (unsigned int)st[VS_ST_RNG_CTR];
+  // row statistics: combine the vocabulary slices (fixed order)
+  if (tid < T) {
+    float m = -INFINITY;
+    for (int s = 0; s < n_slices; ++s) m = fmaxf(m, __ldcg(&lstats[tid * n_slices + s]).x);
+    float l = 0.f;
+    for (int s = 0; s < n_slices; ++s) {
+      const float2 ml = __ldcg(&lstats[tid * n_slices + s]);
+      if (ml.x != -INFINITY) l += ml.y * expf(ml.x - m);
+    }
+    sm.rowM[tid] = m;
+    sm.rowL[tid] = l;
+  }
+  sync();
+  // candidate tokens, their probabilities under the prefix node, and the uniforms
+  for (int idx = tid; idx < n_leaves * VS_RETRIEVE_LD; idx += nthreads) {
+    const int j = idx / VS_RETRIEVE_LD, i = idx % VS_RETRIEVE_LD;
+    const int node = i < max_depth ? tb.retrieve[j * VS_RETRIEVE_LD + i] : -1;
+    const int tok = node >= 0 ? tb.draft_tokens[node] : -1;
+    sm.cand[idx] = tok;
+    float p = 0.f;
+    if (i >= 1 && tok >= 0) {
+      const int row = tb.retrieve[j * VS_RETRIEVE_LD + i - 1];
+      const float x = __bfloat162float(logits[(long)row * ldl + tok]) * inv_temp;
+      p = expf(x - sm.rowM[row]) / sm.rowL[row];
+    }
+    sm.px[idx] = p;
+    sm.uni[idx] = uni_override ? uni_override[idx] : philox_uniform(seed, cycle, (unsigned int)idx);
+  }
+  sync();
+  if (tid == 0) {
+    // the sequential accept / reject walk of utils.py:457-488 (at most depth * top_k steps)
+    int accept_length = 1, best = 0, n_removed = 0, fail_row = -1;
+    bool adjust = false;
+    for (int i = 1; i < max_depth; ++i) {
+      if (i != accept_length) break;
+      adjust = false;
+      n_removed = 0;
+      float removed_mass = 0.f;
+      int fi = -1;
+      for (int j = 0; j < n_leaves && fi < 0; ++j) {
+        bool eq = true;
+        for (int d = 0; d < accept_length; ++d) eq = eq && sm.cand[j * VS_RETRIEVE_LD + d] == sm.cand[best * VS_RETRIEVE_LD + d];
+        if (eq) fi = j;
+      }
+      fail_row = tb.retrieve[fi * VS_RETRIEVE_LD + i - 1];
+      bool accepted = false;
+      for (int j = 0; j < n_leaves && !accepted; ++j) {
+        bool eq = true;
+        for (int d = 0; d < accept_length; ++d) eq = eq && sm.cand[j * VS_RETRIEVE_LD + d] == sm.cand[best * VS_RETRIEVE_LD + d];
+        if (!eq) continue;
+        const int x = sm.cand[j * VS_RETRIEVE_LD + i];
+        if (x < 0) continue;
+        bool seen = false;
+        for (int r = 0; r < n_removed; ++r) seen = seen || sm.removed[r] == x;
+        if (seen) continue;
+        // gtp[x] after the renormalisations so far: p(x) / (1 - mass removed)
+        const float px = sm.px[j * VS_RETRIEVE_LD + i] / (1.0f - removed_mass);
+        if (sm.uni[j * VS_RETRIEVE_LD + i] <= px) {
+          best = j;                                    // the accepted prefix now runs through leaf j
+          ++accept_length;
+          accepted = true;
+        } else {
+          sm.removed[n_removed++] = x;
+          removed_mass += sm.px[j * VS_RETRIEVE_LD + i];
+          adjust = true;
+        }
+      }
+    }
+    const bool residual = adjust && accept_length != max_depth;
+    sm.accept = accept_length - 1;
+    sm.best = best;
+    sm.n_removed = residual ? n_removed : 0;
+    sm.row = residual ? fail_row : tb.retrieve[best * VS_RETRIEVE_LD + accept_length - 1];
+  }
+  sync();
+  // ---- sample the next root token from row `sm.row` with the rejected tokens removed: inverse CDF over the vocabulary
+  const int row = sm.row;
+  const float M = sm.rowM[row];
+  const bf16* lr = logits + (long)row * ldl;
+  if (tid < n_slices) {
+    const int per = ((V + n_slices - 1) / n_slices + 7) & ~7;
+    const int lo = min(V, tid * per), hi = min(V, lo + per);
+    const float2 ml = __ldcg(&lstats[row * n_slices + tid]);
+    float mass = ml.x == -INFINITY ? 0.f : ml.y * expf(ml.x - M);
+    for (int r = 0; r < sm.n_removed; ++r) {
+      const int x = sm.removed[r];
+      if (x >= lo && x < hi) mass -= expf(__bfloat162float(lr[x]) * inv_temp - M);
+    }
+    sm.slice_mass[tid] = fmaxf(mass, 0.f);
+  }
+  sync();
+  if (tid == 0) {
+    float total = 0.f;
+    for (int s = 0; s < n_slices; ++s) total += sm.slice_mass[s];
+    const float u = uni_override ? uni_override[32 * VS_RETRIEVE_LD] : philox_uniform(seed, cycle, 4096u);
+    float target = u * total;
+    int s = 0;
+    while (s + 1 < n_slices && target >= sm.slice_mass[s]) { target -= sm.slice_mass[s]; ++s; }
+    sm.slice = s;
+    sm.target = target;
+    sm.picked = 0x7fffffff;
+  }
+  sync();
+  {
+    const int per = ((V + n_slices - 1) / n_slices + 7) & ~7;
+    const int lo = min(V, sm.slice * per), hi = min(V, lo + per);
+    const int n = hi - lo;
+    const int chunk = (n + nthreads - 1) / nthreads;               // consecutive elements per thread
+    const int e0 = lo + tid * chunk, e1 = min(hi, e0 + chunk);
+    float local = 0.f;
+    for (int e = e0; e < e1; ++e) {
+      bool rem = false;
+      for (int r = 0; r < sm.n_removed; ++r) rem = rem || sm.removed[r] == e;
+      if (!rem) local += expf(__bfloat162float(lr[e]) * inv_temp - M);
+    }
+    // exclusive prefix over the threads: warp scan, then the warp totals
+    float incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
+    sync();
+    float base = 0.f;
+    for (int w = 0; w < (tid >> 5); ++w) base += sm.warp_tot[w];
+    float cum = base + incl - local;                              // mass before this thread's first element
+    for (int e = e0; e < e1; ++e) {
+      bool rem = false;
+      for (int r = 0; r < sm.n_removed; ++r) rem = rem || sm.removed[r] == e;
+      if (rem) continue;
+      cum += expf(__bfloat162float(lr[e]) * inv_temp - M);
+      if (cum > sm.target) { atomicMin(&sm.picked, e); break; }
+    }
+    sync();
+    if (tid == 0 && sm.picked == 0x7fffffff) {                    // rounding at the very end of the slice: last kept token
+      int e = hi - 1;
+      for (;; --e) {
+        bool rem = false;
+        for (int r = 0; r < sm.n_removed; ++r) rem = rem || sm.removed[r] == e;
+        if (!rem || e == lo) break;
+      }
+      sm.picked = e;
+    }
+  }
+  sync();
+  if (tid == 0) {
+    const int a = sm.accept, best = sm.best, next_tok = sm.picked;
+    const int* rowp = tb.retrieve + best * VS_RETRIEVE_LD;
+    const int prev = st[VS_ST_CUR_LEN];
+    st[VS_ST_PREV_LEN] = prev;
+    st[VS_ST_CUR_LEN] = prev + a + 1;
+    st[VS_ST_ACCEPT] = a;
+    st[VS_ST_BEST] = best;
+    st[VS_ST_NEXT_TOKEN] = next_tok;
+    st[VS_ST_M] = a + 1;
+    st[VS_ST_LAST_ROW] = a;
+    const int dpos = st[VS_ST_D_POS];
+    for (int j = 0; j < VS_MAX_ACCEPT; ++j) {
+      const int jj = j <= a ? j : a;
+      tb.sel[j] = rowp[jj];
+      tb.stable_ids[j] = j < a ? tb.draft_tokens[rowp[j + 1]] : next_tok;
+      tb.stable_pos[j] = dpos + j;
+    }
+    if (out_rec) {
+      out_rec[0] = a;
+      out_rec[1] = next_tok;
+      for (int j = 0; j < VS_MAX_ACCEPT; ++j) out_rec[2 + j] = j <= a ? tb.draft_tokens[rowp[j]] : -1;
+    }
+    st[VS_ST_CYCLE] += 1;
+    st[VS_ST_RNG_CTR] = (int)(cycle + 1u);
   }
 }
 

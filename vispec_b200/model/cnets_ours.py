@@ -59,9 +59,11 @@ class Model:
                      embed_weights=None, image_mask=None):
         """cnets_ours.py:1044-1238.  Returns (draft_tokens [1,T] i64, retrieve_indices [n_leaves,d] i64 (CPU),
         tree_mask [1,1,T,T] f32 (CPU), tree_position_ids [T] i64)."""
-        if logits_processor is not None:
-            raise NotImplementedError("T>0 drafting is not on the B200 path yet (SURVEY.md section 8f rank 2)")
         eng = self.engine
+        # T > 0 only changes the order of the leaf paths (cnets_ours.py:1215-1224): the tree build reads the flag
+        import struct
+        eng.state[L.ST_TEMP_BITS] = 0 if logits_processor is None else \
+            struct.unpack("<i", struct.pack("<f", float(logits_processor.temperature)))[0]
         input_ids = input_ids.to(eng.device)
         sample_token = int(input_ids[0, -1].item())
         if not self._has_stable:

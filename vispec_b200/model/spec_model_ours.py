@@ -124,10 +124,37 @@ class SpecModel:
         self._rec_evt = [torch.cuda.Event() for _ in range(2)]
         self._dec_evt = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         self.last_decode_ms = 0.0
-        self._cycle_progs: Dict[bool, Program] = {}
+        self._cycle_progs: Dict[tuple, Program] = {}
+        self._accept_progs: Dict[float, Program] = {}
+
+    # -- T > 0 (utils.py:453-493, 550-552) -----------------------------------------------------------------
+    def sampling_setup(self, logits_processor, reseed: bool = False):
+        """Device-side sampling state: temperature bits (the tree build sorts the leaf paths when set) and, once per
+        generation, a Philox key drawn from torch's CPU generator (so `torch.manual_seed(i)` per prompt, as the
+        evaluation scripts do, makes a generation reproducible)."""
+        import struct
+        st = self.base_model_engine.state
+        if logits_processor is None:
+            st[L.ST_TEMP_BITS] = 0
+            return
+        st[L.ST_TEMP_BITS] = struct.unpack("<i", struct.pack("<f", float(logits_processor.temperature)))[0]
+        if reseed:
+            st[L.ST_RNG_SEED] = int(torch.randint(0, 2 ** 31 - 1, (1,)))
+            st[L.ST_RNG_CTR] = 0
+
+    def accept_sampling_program(self, temperature: float) -> Program:
+        """The T > 0 acceptance + next-token sampling on the verify logits, for the stage-by-stage route."""
+        p = self._accept_progs.get(temperature)
+        if p is None:
+            eng_t, eng_d = self.base_model_engine, self.spec_layer.engine
+            p = Program(eng_t.device)
+            p.add("accept_sampling", C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.logits), eng_t.cfg.vocab,
+                  eng_t.cfg.vocab, C.c_float(temperature), None, L.ptr(eng_d.out_rec))
+            self._accept_progs[temperature] = p.commit()
+        return p
 
     def cycle_program(self, trace: bool = False, pf_ahead: Optional[int] = None, inflight: Optional[int] = None,
-                      attn_fused: bool = True) -> Program:
+                      attn_fused: bool = True, temperature: float = 0.0) -> Program:
         """The whole draft+verify cycle (spec_model_ours.py:484-547 loop body) as one persistent-kernel launch.
         attn_fused: single-phase attention (target KV + tree and draft KV must stay within
         `scratch.fused_kv_capacity`; specgenerate switches to the two-phase program beyond it)."""
@@ -136,9 +163,14 @@ class SpecModel:
         p.register_tiled(eng_t.tiled + eng_d.tiled)
         if inflight is not None:
             p.set_option("inflight", inflight)
-        p.add("spec_cycle", C.byref(eng_t.c), C.byref(eng_t.scratch.c), C.byref(eng_d.c), C.byref(eng_d.scratch.c),
-              C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.kv), eng_t.kv_max, L.ptr(eng_t.hidden_out),
-              L.ptr(eng_t.logits), L.ptr(eng_t.amax), L.ptr(self._rec_dev[0]))
+        if temperature > 1e-5:
+            p.add("spec_cycle_sampling", C.byref(eng_t.c), C.byref(eng_t.scratch.c), C.byref(eng_d.c),
+                  C.byref(eng_d.scratch.c), C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.kv), eng_t.kv_max,
+                  L.ptr(eng_t.hidden_out), L.ptr(eng_t.logits), C.c_float(temperature), L.ptr(self._rec_dev[0]))
+        else:
+            p.add("spec_cycle", C.byref(eng_t.c), C.byref(eng_t.scratch.c), C.byref(eng_d.c), C.byref(eng_d.scratch.c),
+                  C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.kv), eng_t.kv_max, L.ptr(eng_t.hidden_out),
+                  L.ptr(eng_t.logits), L.ptr(eng_t.amax), L.ptr(self._rec_dev[0]))
         return p.commit()
 
     # -- construction ----------------------------------------------------------------------------------
@@ -260,6 +292,7 @@ class SpecModel:
             inputs_embeds, special_image_mask = self.vision(input_ids, **kwargs)
         input_len = input_ids.shape[1]
         reset_tree_mode(self)
+        self.sampling_setup(logits_processor, reseed=True)
         initialize_tree(input_ids, self, self.past_key_values, logits_processor, inputs_embeds, None,
                         image_mask=special_image_mask)
         new_token = 0
@@ -283,13 +316,16 @@ class SpecModel:
                 # cur_len / d_rows are one cycle behind when a launch is issued ahead: VS_MAX_ACCEPT rows of slack
                 fused = (cur_len + 2 * L.VS_MAX_ACCEPT + T <= cap_t and
                          d_rows + 3 * L.VS_MAX_ACCEPT + 8 * (self.spec_layer.depth + 1) <= cap_d)
-                prog = self._cycle_progs.get(fused)
+                temp = logits_processor.temperature if logits_processor is not None else 0.0
+                prog = self._cycle_progs.get((fused, temp))
                 if prog is None:
-                    prog = self._cycle_progs[fused] = self.cycle_program(attn_fused=fused)
+                    prog = self._cycle_progs[(fused, temp)] = self.cycle_program(attn_fused=fused, temperature=temp)
                 prog.run(st)
                 self._rec_host[slot].copy_(self._rec_dev[0], non_blocking=True)
                 self._rec_evt[slot].record()
                 return
+            if logits_processor is not None:
+                raise NotImplementedError("T > 0 runs on the persistent program path only (unset VS_MULTI_KERNEL)")
             L.check(lib.vs_spec_cycle(C.byref(eng_t.c), C.byref(eng_t.scratch.c), C.byref(eng_d.c),
                                       C.byref(eng_d.scratch.c), C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.kv),
                                       eng_t.kv_max, L.ptr(eng_t.hidden_out), L.ptr(eng_t.logits), L.ptr(eng_t.amax),

@@ -33,13 +33,34 @@ class Timer:
         print(f"{self.name} took {time.perf_counter() - self.start} seconds")
 
 
+class TemperatureProcessor:
+    """What utils.py:39-55 builds for the evaluation scripts' sampling runs: a LogitsProcessorList holding one
+    TemperatureLogitsWarper.  Callable like it (`proc(None, logits) -> logits / temperature`); the CUDA path reads
+    `.temperature`."""
+
+    def __init__(self, temperature: float):
+        self.temperature = float(temperature)
+
+    def __call__(self, input_ids, scores):
+        return scores / self.temperature
+
+
 def prepare_logits_processor(temperature: float = 0.0, repetition_penalty: float = 0.0, top_p: float = 0.0,
                              top_k: int = 0):
-    """utils.py:39-55.  Only greedy decoding (T=0) is on the B200 path; T>0 is SURVEY.md section 8f rank 2."""
-    if temperature > 1e-5:
-        raise NotImplementedError("temperature > 0 (sampling acceptance, utils.py:453-493) is not implemented on "
-                                  "the B200 path yet")
-    return None
+    """utils.py:39-55.  The reference returns an (empty) processor list for temperature <= 1e-5 and callers only build
+    one for temperature > 1e-5 (spec_model_ours.py:272-277); here: None for greedy, a TemperatureProcessor for
+    sampling.  top-p / top-k / repetition-penalty warpers are not on the B200 path."""
+    if temperature <= 1e-5:
+        return None
+    if repetition_penalty > 1.0 or 1e-8 <= top_p < 1.0 or top_k > 0:
+        raise NotImplementedError("only temperature sampling is implemented on the B200 path "
+                                  "(top_p / top_k / repetition_penalty warpers are not)")
+    return TemperatureProcessor(temperature)
+
+
+def _temp_bits(logits_processor) -> int:
+    import struct
+    return 0 if logits_processor is None else struct.unpack("<i", struct.pack("<f", logits_processor.temperature))[0]
 
 
 def reset_tree_mode(model):
@@ -68,9 +89,11 @@ def initialize_tree(input_ids, model, past_key_values, logits_processor, inputs_
     """utils.py:266-327: target prefill, first token, first draft tree."""
     outputs, orig, hidden_states = model(input_ids, past_key_values=past_key_values, output_orig=True,
                                          inputs_embeds=inputs_embeds)
-    if logits_processor is not None:
-        raise NotImplementedError("T>0 is not on the B200 path yet")
-    token = torch.argmax(orig[:, -1])[None, None]
+    if logits_processor is not None:                                        # utils.py:284-288
+        probabilities = torch.nn.functional.softmax(logits_processor(None, orig[:, -1]), dim=1)
+        token = torch.multinomial(probabilities, 1)
+    else:
+        token = torch.argmax(orig[:, -1])[None, None]
     input_ids = torch.cat((input_ids, token.to(input_ids.device)), dim=1)
     draft_tokens, retrieve_indices, tree_mask, tree_position_ids = model.spec_layer.topK_genrate(
         hidden_states, input_ids, _lm_head(model), logits_processor, inputs_embeds=inputs_embeds,
@@ -89,15 +112,19 @@ def tree_decoding(model, tree_candidates, past_key_values, tree_position_ids, in
 
 
 def evaluate_posterior(logits: torch.Tensor, candidates: torch.Tensor, logits_processor):
-    """utils.py:415-493, greedy branch (:438-451) through vs_accept_greedy."""
-    if logits_processor is not None:
-        raise NotImplementedError("T>0 acceptance is not on the B200 path yet")
+    """utils.py:415-493: greedy branch (:438-451) through vs_accept_greedy; sampling branch (:453-493) through the
+    accept-sampling phase, which also draws the next root token (utils.py:550-552), so `sample_p` is returned for its
+    shape only and carries that token."""
     model = getattr(logits, "_vs_model", None)
     if model is None:
         raise TypeError("evaluate_posterior expects the logits returned by vispec_b200's tree_decoding")
     eng_t, eng_d = model.base_model_engine, model.spec_layer.engine
-    L.check(eng_d.lib.vs_accept_greedy(C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.amax), L.ptr(eng_d.out_rec),
-                                       _stream()), "vs_accept_greedy")
+    if logits_processor is not None:
+        model.sampling_setup(logits_processor)
+        model.accept_sampling_program(logits_processor.temperature).run()
+    else:
+        L.check(eng_d.lib.vs_accept_greedy(C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.amax), L.ptr(eng_d.out_rec),
+                                           _stream()), "vs_accept_greedy")
     st = eng_t.state.tolist()
     accept_length, best = st[L.ST_ACCEPT], st[L.ST_BEST]
     best_candidate = torch.tensor(best, dtype=torch.long, device=candidates.device)
@@ -111,8 +138,6 @@ def update_inference_inputs(input_ids, candidates, best_candidate, accept_length
                             new_token, past_key_values_data_list, current_length_data, model, hidden_state_new,
                             sample_p):
     """utils.py:497-593: append the accepted tokens, splice the KV cache, build the next draft tree."""
-    if logits_processor is not None:
-        raise NotImplementedError("T>0 is not on the B200 path yet")
     eng_t = model.base_model_engine
     prev_input_len = input_ids.shape[1]
     a = int(accept_length)
