@@ -392,11 +392,18 @@ struct __align__(128) AttnFusedSmem {
   uint8_t kv[2][ATT_CHUNK * ATT_ROW_B];      // K chunks, then V chunks
   float red[ATT_WARPS][VS_TOK];
   float rowm[VS_TOK];
-  float gM[VS_TOK], gL[VS_TOK];
+  float gM[VS_TOK], gL[VS_TOK], gR[VS_TOK];  // global row max, softmax denominator and its reciprocal
+  float red2[ATT_WARPS][VS_TOK];             // per-warp sum exp (red holds the per-warp max)
   int last;
 };
 constexpr int ATT_FUSED_CPS = 2;             // chunks per split the fused item can hold
 
+// x / d, correctly rounded for normal operands: q = x * r with r = RN(1 / d), then one residual correction
+// (the fast path of the IEEE division sequence without its range checks; |x|, d here are O(1e-3 .. 1e3))
+__device__ __forceinline__ float att_div(float x, float d, float r) {
+  const float q = x * r;
+  return fmaf(fmaf(-q, d, x), r, q);
+}
 __device__ __forceinline__ unsigned int att_ld_relaxed(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -454,7 +461,7 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
       for (int i = 0; i < 4; ++i)
         vis[j][i] = att_visible_mask(p, n_ctx, kv_len, (i >> 1) * 16 + g + (i & 1) * 8, qb[i], key_lo + j * ATT_CHUNK);
   }
-  const float inv_div = sqrtf((float)VS_HEAD_DIM);
+  const float inv_div = sqrtf((float)VS_HEAD_DIM), r_div = 1.0f / inv_div;
   ACLK(1);
   cp_async_wait<0>();
   sync();
@@ -494,8 +501,8 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
         for (int eh = 0; eh < 2; ++eh) {
           const int qi = mb * 2 + eh;
           float s0 = c[mb][eh * 2], s1 = c[mb][eh * 2 + 1];
-          s0 = p.eager ? rbf(rbf(s0) / inv_div) : s0 * p.scale;
-          s1 = p.eager ? rbf(rbf(s1) / inv_div) : s1 * p.scale;
+          s0 = p.eager ? rbf(att_div(rbf(s0), inv_div, r_div)) : s0 * p.scale;
+          s1 = p.eager ? rbf(att_div(rbf(s1), inv_div, r_div)) : s1 * p.scale;
           if (!((vis[j][qi] >> kofs) & 1ull)) s0 = -INFINITY;
           if (!((vis[j][qi] >> (kofs + 1)) & 1ull)) s1 = -INFINITY;
           acc[j][mb][eh * 2] = s0;
@@ -505,12 +512,33 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
     }
   }
   ACLK(3);
-  // ---- split statistics: row max, then sum exp
+  // ---- split statistics: every warp leaves (max, sum exp(s - max)) of its 8 key columns per row; 32 threads combine
+  // the warps in fixed order (two block barriers in all)
+  float lsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     lmax[i] = fmaxf(lmax[i], __shfl_xor_sync(0xffffffffu, lmax[i], 1));
     lmax[i] = fmaxf(lmax[i], __shfl_xor_sync(0xffffffffu, lmax[i], 2));
-    if (t4 == 0) sm.red[warp][(i >> 1) * 16 + g + (i & 1) * 8] = lmax[i];
+  }
+#pragma unroll
+  for (int j = 0; j < ATT_FUSED_CPS; ++j)
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int eh = 0; eh < 2; ++eh) {
+        const int qi = mb * 2 + eh;
+        const float s0 = acc[j][mb][eh * 2], s1 = acc[j][mb][eh * 2 + 1];
+        if (s0 != -INFINITY) lsum[qi] += expf(s0 - lmax[qi]);
+        if (s1 != -INFINITY) lsum[qi] += expf(s1 - lmax[qi]);
+      }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    lsum[i] += __shfl_xor_sync(0xffffffffu, lsum[i], 1);
+    lsum[i] += __shfl_xor_sync(0xffffffffu, lsum[i], 2);
+    if (t4 == 0) {
+      sm.red[warp][(i >> 1) * 16 + g + (i & 1) * 8] = lmax[i];
+      sm.red2[warp][(i >> 1) * 16 + g + (i & 1) * 8] = lsum[i];
+    }
   }
   sync();                                                          // also: every warp is done with Q and K in shared memory
   // the V chunks take the place of the K chunks; in flight during the statistics exchange
@@ -520,40 +548,18 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
       att_load_rows_async(sm.kv[j], vbase, key_lo + j * ATT_CHUNK, min(ATT_CHUNK, kv_len - key_lo - j * ATT_CHUNK),
                           ATT_CHUNK, tid);
   cp_async_commit();
+  float* stat_head = p.stats + (long)head * p.max_chunks * VS_TOK * 2;
   if (tid < VS_TOK) {
     float m = sm.red[0][tid];
 #pragma unroll
     for (int w = 1; w < ATT_WARPS; ++w) m = fmaxf(m, sm.red[w][tid]);
-    sm.rowm[tid] = m;
-  }
-  sync();
-  float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float l = 0.f;
 #pragma unroll
-  for (int j = 0; j < ATT_FUSED_CPS; ++j)
-#pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-      for (int eh = 0; eh < 2; ++eh) {
-        const int qi = mb * 2 + eh;
-        const float rm = sm.rowm[mb * 16 + g + eh * 8];
-        const float s0 = acc[j][mb][eh * 2], s1 = acc[j][mb][eh * 2 + 1];
-        if (s0 != -INFINITY) lsum[qi] += expf(s0 - rm);
-        if (s1 != -INFINITY) lsum[qi] += expf(s1 - rm);
-      }
-  sync();                                                          // rowm consumed before red is overwritten
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    lsum[i] += __shfl_xor_sync(0xffffffffu, lsum[i], 1);
-    lsum[i] += __shfl_xor_sync(0xffffffffu, lsum[i], 2);
-    if (t4 == 0) sm.red[warp][(i >> 1) * 16 + g + (i & 1) * 8] = lsum[i];
-  }
-  sync();
-  float* stat_head = p.stats + (long)head * p.max_chunks * VS_TOK * 2;
-  if (tid < VS_TOK) {
-    float l = sm.red[0][tid];
-#pragma unroll
-    for (int w = 1; w < ATT_WARPS; ++w) l += sm.red[w][tid];        // fixed order
-    *reinterpret_cast<float2*>(stat_head + ((long)split * VS_TOK + tid) * 2) = make_float2(sm.rowm[tid], l);
+    for (int w = 0; w < ATT_WARPS; ++w) {                           // fixed order
+      const float mw = sm.red[w][tid];
+      if (mw != -INFINITY) l += sm.red2[w][tid] * expf(mw - m);
+    }
+    *reinterpret_cast<float2*>(stat_head + ((long)split * VS_TOK + tid) * 2) = make_float2(m, l);
   }
   sync();
   ACLK(4);
@@ -591,7 +597,7 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
       l = a + b;
       m = mn;
     }
-    if (part == 0) { sm.gM[q] = m; sm.gL[q] = l; }
+    if (part == 0) { sm.gM[q] = m; sm.gL[q] = l; sm.gR[q] = 1.0f / l; }
   }
   sync();
   ACLK(6);
@@ -604,7 +610,7 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
 #pragma unroll
         for (int eh = 0; eh < 2; ++eh) {
           const int q = mb * 16 + g + eh * 8;
-          const float gm = sm.gM[q], gl = sm.gL[q];
+          const float gm = sm.gM[q], gl = sm.gL[q], gr = sm.gR[q];
           float pr[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -612,7 +618,7 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
             float v = 0.f;
             if (s != -INFINITY) {
               const float ex = expf(s - gm);
-              v = p.eager ? ex / gl : ex;
+              v = p.eager ? att_div(ex, gl, gr) : ex;
             }
             pr[e] = v;
           }
@@ -680,18 +686,21 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
   }
   sync();
   ACLK(10);
+  const int n_act = max(1, (n_chunks + cps - 1) / cps);             // splits that own keys (the others hold zeros)
   for (int i = split + tid * n_splits; i < VS_TOK * 32; i += ATT_THREADS * n_splits) {
     const int q = i >> 5, d4 = (i & 31) * 4;
     if (q >= tq_rows) continue;
+    const float* src = obase + q * 128 + d4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < n_splits; s0 += 4) {
-      float4 t[4];
+#pragma unroll 1
+    for (int s0 = 0; s0 < n_act; s0 += 8) {                         // 8 splits per round trip
+      float4 t[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        t[j] = __ldcg(reinterpret_cast<const float4*>(obase + (long)min(s0 + j, n_splits - 1) * VS_TOK * 128 + q * 128 + d4));
+      for (int j = 0; j < 8; ++j)
+        t[j] = __ldcg(reinterpret_cast<const float4*>(src + (long)min(s0 + j, n_act - 1) * VS_TOK * 128));
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (s0 + j < n_splits) { v.x += t[j].x; v.y += t[j].y; v.z += t[j].z; v.w += t[j].w; }
+      for (int j = 0; j < 8; ++j)
+        if (s0 + j < n_act) { v.x += t[j].x; v.y += t[j].y; v.z += t[j].z; v.w += t[j].w; }
     }
     if (!p.eager) {
       const float l = sm.gL[q];

@@ -44,7 +44,7 @@ constexpr int BM = PG_BM, BK = PG_BK, NS = 6;
 constexpr int W_STAGE = BM * BK * 2;             // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;         // 4096
 constexpr int STAGE_BYTES = W_STAGE + X_STAGE;   // 20480 (multiple of 1024)
-constexpr int BIG_SMEM = 43008;                  // scratch of one attention team (AttnSmem); both together also stage the
+constexpr int BIG_SMEM = 44032;                  // scratch of one attention team (AttnSmem); both together also stage the
                                                  // tree ops and the top-k merge on CTA 0
 constexpr int TEAM_SMEM = 1024;                  // reduction scratch of one small team
 constexpr int TEAM_OFF = NS * STAGE_BYTES + PG_BIG_TEAMS * BIG_SMEM;
