@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 1
+#define VS_ABI_VERSION 2
 #define VS_TOK_BLOCK 32    /* token rows per block of the skinny kernels; decode paths use <= 32 rows */
 #define VS_RETRIEVE_LD 8   /* row stride of retrieve_indices; tree depth + 2 must be <= 8 */
 #define VS_MAX_ACCEPT 8    /* accepted path length (accept_length + 1) must be <= 8 */
@@ -46,6 +46,7 @@ enum vs_state_slot {
                            when it is non-zero (cnets_ours.py:1215-1224) */
   VS_ST_RNG_SEED = 13,  /* T > 0 only: Philox key of the acceptance / sampling uniforms */
   VS_ST_RNG_CTR = 14,   /* T > 0 only: draws so far (advanced by one per cycle) */
+  VS_ST_ROPE_DELTA = 15,/* added to the verify positions: Qwen2.5-VL `rope_deltas` (utils.py:398-402); 0 otherwise */
   VS_ST_SLOTS = 16
 };
 
@@ -217,6 +218,9 @@ typedef struct vs_target {
   const void* norm;                    /* [H] */
   const void* lm_head;                 /* [V][H] */
   vs_rope rope;
+  int32_t sdpa_attention;              /* 0: eager softmax with the reference's bf16 rounding points (Llama / LLaVA,
+                                          modeling_llama_kv.py:602-623); 1: SDPA semantics (Qwen2.5-VL default attention
+                                          class, modeling_qwen2_5_vl_kv.py:1065-1170) */
 } vs_target;
 
 /* A6: tree-attention verify of T tree tokens (utils.py:389-412 tree_decoding -> modeling_llama_kv.py:927-1080,

@@ -31,10 +31,13 @@ def make_target_weights(cfg: TargetCfg, seed: int, dtype=torch.bfloat16, gain: f
         w[p + "self_attn.q_proj.weight"] = _randn(g, cfg.heads * D, H, std=1.0 / math.sqrt(H), dtype=dtype)
         w[p + "self_attn.k_proj.weight"] = _randn(g, cfg.kv_heads * D, H, std=1.0 / math.sqrt(H), dtype=dtype)
         w[p + "self_attn.v_proj.weight"] = _randn(g, cfg.kv_heads * D, H, std=1.0 / math.sqrt(H), dtype=dtype)
-        w[p + "self_attn.o_proj.weight"] = _randn(g, H, H, std=gain / math.sqrt(H), dtype=dtype)
+        w[p + "self_attn.o_proj.weight"] = _randn(g, cfg.hidden, cfg.heads * D, std=gain / math.sqrt(H), dtype=dtype)
         w[p + "mlp.gate_proj.weight"] = _randn(g, I, H, std=1.0 / math.sqrt(H), dtype=dtype)
         w[p + "mlp.up_proj.weight"] = _randn(g, I, H, std=1.0 / math.sqrt(H), dtype=dtype)
         w[p + "mlp.down_proj.weight"] = _randn(g, H, I, std=gain / math.sqrt(I), dtype=dtype)
+        if getattr(cfg, "qkv_bias", False):             # Qwen2.5-VL (drawn last per layer: older seeds keep their weights)
+            for n, rows in (("q", cfg.heads * D), ("k", cfg.kv_heads * D), ("v", cfg.kv_heads * D)):
+                w[p + f"self_attn.{n}_proj.bias"] = _randn(g, rows, std=0.3, dtype=dtype)
         w[p + "input_layernorm.weight"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype)
         w[p + "post_attention_layernorm.weight"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype)
     w["model.norm.weight"] = (1.0 + 0.1 * torch.randn(H, generator=g)).to(dtype)

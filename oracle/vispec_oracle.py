@@ -44,6 +44,11 @@ class TargetCfg:
     max_pos: int = 8192          # forced by modeling_llava_next_kv.py:10
     eps: float = 1e-5
     rope_theta: float = 10000.0
+    # Qwen2.5-VL target (modeling_qwen2_5_vl_kv.py): q/k/v biases (:830-838), multimodal RoPE sections over head_dim/2
+    # (:740-782), SDPA attention with a model-dtype mask as the default attention class (:1065-1170)
+    qkv_bias: bool = False
+    mrope_section: Optional[tuple] = None
+    attn_impl: str = "eager"
 
     @property
     def head_dim(self) -> int:
@@ -96,6 +101,17 @@ def apply_rope(q, k, cos, sin, position_ids):
     """cnets_ours.py:111-119 / modeling_llama_kv.py:338-358.  Three bf16 roundings each."""
     c = cos[position_ids].unsqueeze(1)
     s = sin[position_ids].unsqueeze(1)
+    return (q * c) + (_rotate_half(q) * s), (k * c) + (_rotate_half(k) * s)
+
+
+def apply_mrope(q, k, cos, sin, position_ids3, mrope_section):
+    """modeling_qwen2_5_vl_kv.py:740-782 (`apply_multimodal_rotary_pos_emb`): position_ids3 is [3, q] (temporal, height,
+    width); channel chunk i of cos / sin (sections doubled over the two halves) comes from axis i % 3.  The reference
+    computes cos / sin on the fly in fp32 and casts once (:690-718) -- the same values as the table rows."""
+    c3, s3 = cos[position_ids3], sin[position_ids3]                      # [3, q, D]
+    sec = list(mrope_section) * 2
+    c = torch.cat([m[i % 3] for i, m in enumerate(c3.split(sec, dim=-1))], dim=-1)[None, None]
+    s = torch.cat([m[i % 3] for i, m in enumerate(s3.split(sec, dim=-1))], dim=-1)[None, None]
     return (q * c) + (_rotate_half(q) * s), (k * c) + (_rotate_half(k) * s)
 
 
@@ -163,17 +179,27 @@ class TargetOracle:
         past = self.cur_len
         if position_ids is None:
             position_ids = torch.arange(past, past + q_len, device=self.device)
-        position_ids = position_ids.view(1, q_len).long()
+        position_ids = position_ids.long()
+        pos3 = None
+        if cfg.mrope_section is not None:                # Qwen2.5-VL: [3, q]; text tokens carry the same id on all axes
+            pos3 = position_ids.view(3, q_len) if position_ids.numel() == 3 * q_len else \
+                position_ids.view(1, q_len).expand(3, q_len)
+        else:
+            position_ids = position_ids.view(1, q_len)
+        sdpa = cfg.attn_impl == "sdpa"
+        mdt = self.dtype if sdpa else torch.float32      # SDPA class: mask in the model dtype (:1455-1540)
 
         # mask: modeling_llama_kv.py:890-924.  q_len==1 -> only the all-zero expanded mask.
         if q_len > 1:
             mask = causal_mask(q_len, past, self.device)
+            if sdpa:
+                mask = torch.where(mask == 0, 0.0, torch.finfo(mdt).min).to(mdt)
             if tree_mask is not None:
                 tl = tree_mask.size(-1)
                 mask = mask.clone()
                 mask[:, :, -tl:, -tl:][tree_mask.to(self.device) == 0] = mask.min()
         else:
-            mask = torch.zeros(1, 1, 1, past + 1, dtype=self.dtype, device=self.device)
+            mask = torch.zeros(1, 1, 1, past + 1, dtype=mdt, device=self.device)
 
         h = inputs_embeds
         nh, nkv, D = cfg.heads, cfg.kv_heads, cfg.head_dim
@@ -181,10 +207,14 @@ class TargetOracle:
             p = f"model.layers.{li}."
             res = h
             x = rms_norm(h, w[p + "input_layernorm.weight"], cfg.eps)
-            q = F.linear(x, w[p + "self_attn.q_proj.weight"]).view(1, q_len, nh, D).transpose(1, 2)
-            k = F.linear(x, w[p + "self_attn.k_proj.weight"]).view(1, q_len, nkv, D).transpose(1, 2)
-            v = F.linear(x, w[p + "self_attn.v_proj.weight"]).view(1, q_len, nkv, D).transpose(1, 2)
-            q, k = apply_rope(q, k, self.cos, self.sin, position_ids)
+            qb, kb, vb = (w.get(p + f"self_attn.{n}_proj.bias") for n in "qkv")
+            q = F.linear(x, w[p + "self_attn.q_proj.weight"], qb).view(1, q_len, nh, D).transpose(1, 2)
+            k = F.linear(x, w[p + "self_attn.k_proj.weight"], kb).view(1, q_len, nkv, D).transpose(1, 2)
+            v = F.linear(x, w[p + "self_attn.v_proj.weight"], vb).view(1, q_len, nkv, D).transpose(1, 2)
+            if pos3 is not None:
+                q, k = apply_mrope(q, k, self.cos, self.sin, pos3, cfg.mrope_section)
+            else:
+                q, k = apply_rope(q, k, self.cos, self.sin, position_ids)
             # KVCache.cat (kv_cache.py:52-66)
             self.kv[2 * li, :, :, past:past + q_len] = k
             self.kv[2 * li + 1, :, :, past:past + q_len] = v
@@ -194,11 +224,22 @@ class TargetOracle:
                 rep = nh // nkv
                 K = K[:, :, None].expand(1, nkv, rep, past + q_len, D).reshape(1, nh, past + q_len, D)
                 V = V[:, :, None].expand(1, nkv, rep, past + q_len, D).reshape(1, nh, past + q_len, D)
-            # eager attention, modeling_llama_kv.py:602-623
-            aw = torch.matmul(q, K.transpose(2, 3)) / math.sqrt(D)
-            aw = aw + mask
-            aw = F.softmax(aw, dim=-1, dtype=torch.float32).to(q.dtype)
-            ao = torch.matmul(aw, V).transpose(1, 2).contiguous().reshape(1, q_len, cfg.hidden)
+            if sdpa:
+                # modeling_qwen2_5_vl_kv.py:1153-1160.  The mask is dropped when SDPA can infer it (:1489-1503,
+                # `_ignore_causal_mask_sdpa`): a prefill without past runs with is_causal=True, a single token unmasked.
+                if q_len == 1:
+                    ao = F.scaled_dot_product_attention(q.contiguous(), K.contiguous(), V.contiguous())
+                elif past == 0 and tree_mask is None:
+                    ao = F.scaled_dot_product_attention(q.contiguous(), K.contiguous(), V.contiguous(), is_causal=True)
+                else:
+                    ao = F.scaled_dot_product_attention(q.contiguous(), K.contiguous(), V.contiguous(), attn_mask=mask)
+                ao = ao.transpose(1, 2).contiguous().reshape(1, q_len, cfg.hidden)
+            else:
+                # eager attention, modeling_llama_kv.py:602-623
+                aw = torch.matmul(q, K.transpose(2, 3)) / math.sqrt(D)
+                aw = aw + mask
+                aw = F.softmax(aw, dim=-1, dtype=torch.float32).to(q.dtype)
+                ao = torch.matmul(aw, V).transpose(1, 2).contiguous().reshape(1, q_len, cfg.hidden)
             h = res + F.linear(ao, w[p + "self_attn.o_proj.weight"])
             res = h
             x = rms_norm(h, w[p + "post_attention_layernorm.weight"], cfg.eps)

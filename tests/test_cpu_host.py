@@ -25,7 +25,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, name), f"{name} declared in include/vispec_b200.h but not exported"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     lib.vs_abi_version.restype = ctypes.c_int
-    assert lib.vs_abi_version() == 1
+    assert lib.vs_abi_version() == 2
 
 
 def test_sass_is_sm100a():

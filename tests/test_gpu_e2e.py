@@ -27,7 +27,7 @@ from vispec_b200.model.kv_cache import initialize_past_key_values  # noqa: E402
 from vispec_b200.model.spec_model_ours import SpecModel  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if "sampling" not in p)
+CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if "sampling" not in p and "qwen" not in p)
 DEV = "cuda"
 
 

@@ -10,7 +10,7 @@ from oracle import synth
 from oracle import vispec_oracle as vo
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if "sampling" not in p)
+CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if "sampling" not in p and "qwen" not in p)
 
 
 def load_case(name):
@@ -89,3 +89,24 @@ def test_oracle_sampling_acceptance_matches_reference():
         assert torch.equal(sample_p, c["sample_p"])
         seen.add(acc)
     assert len(seen) >= 4          # the fixture covers rejections at the root up to full-depth accepts
+
+
+def test_qwen_target_oracle_matches_reference_golden():
+    """Qwen2.5-VL target: GQA + q/k/v biases + multimodal RoPE in the prefill + SDPA with the tree
+    mask + rope_delta decode offsets, against the unmodified `modeling_qwen2_5_vl_kv.Qwen2_5_VLModel` run on CPU
+    (tests/golden/make_golden_qwen.py)."""
+    g = torch.load(os.path.join(GOLDEN, "qwen_target.pt"), weights_only=False)
+    tcfg = vo.TargetCfg(**g["cfg"])
+    w = synth.make_target_weights(tcfg, seed=g["seed"])
+    t = vo.TargetOracle(tcfg, w, kv_max=256)
+    L = g["pos3"].shape[1]
+    _, hid = t.forward(inputs_embeds=g["inputs_embeds"], position_ids=g["pos3"])
+    assert torch.equal(hid, g["prefill_hidden"])
+    assert torch.equal(t.kv[:, :, :, :L].float().sum(dim=(1, 2, 4)), g["kv_after_prefill_sum"])
+    pos = g["tree_depth"] + L + g["rope_delta"]
+    logits, hid2 = t.forward(input_ids=g["tree_ids"], position_ids=pos, tree_mask=g["tree_mask"][None, None])
+    assert torch.equal(hid2, g["tree_hidden"])
+    assert torch.equal(logits.argmax(-1), g["tree_logits_argmax"])
+    t.cur_len = L
+    _, hid3 = t.forward(input_ids=g["tree_ids"][:, :1], position_ids=torch.tensor([L + g["rope_delta"]]))
+    assert torch.equal(hid3, g["one_hidden"])

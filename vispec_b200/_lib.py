@@ -15,7 +15,7 @@ VS_TOK_BLOCK = 32
 VS_RETRIEVE_LD = 8
 VS_MAX_ACCEPT = 8
 (ST_CUR_LEN, ST_PREV_LEN, ST_ACCEPT, ST_BEST, ST_NEXT_TOKEN, ST_D_LEN, ST_D_POS, ST_M, ST_N_LEAVES, ST_MAX_DEPTH,
- ST_LAST_ROW, ST_CYCLE, ST_TEMP_BITS, ST_RNG_SEED, ST_RNG_CTR) = range(15)
+ ST_LAST_ROW, ST_CYCLE, ST_TEMP_BITS, ST_RNG_SEED, ST_RNG_CTR, ST_ROPE_DELTA) = range(16)
 ST_SLOTS = 16
 EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_HEADS = range(4)
 (PH_NOP, PH_GEMM, PH_EPI, PH_NORM, PH_ROWS, PH_ATTN_S, PH_ATTN_PV, PH_ARGMAX, PH_LSM_STATS, PH_TREE, PH_SPLICE,
@@ -77,7 +77,7 @@ class Rope(C.Structure):
 
 class Target(C.Structure):
     _fields_ = [("dims", Dims), ("layers", C.POINTER(Layer)), ("embed", c_vp), ("norm", c_vp), ("lm_head", c_vp),
-                ("rope", Rope)]
+                ("rope", Rope), ("sdpa_attention", c_i32)]
 
 
 class Draft(C.Structure):
@@ -186,7 +186,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.vs_abi_version() != 1:
+    if lib.vs_abi_version() != 2:
         raise RuntimeError("libvispec_b200.so ABI version mismatch")
     _lib = lib
     return lib

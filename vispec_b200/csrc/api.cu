@@ -217,7 +217,7 @@ int vs_verify_step(const vs_target* t, const vs_scratch* s, const int32_t* token
   CK(vs::launch_embed_rows(B(t->embed), H, token_ids, B(s->h), H, T, H, V, st));
   const int32_t* cur = state + VS_ST_CUR_LEN;
   for (int li = 0; li < d->n_layers; ++li)
-    RET(vs_decoder_layer(d, &t->layers[li], s, &t->rope, T, pos_ids, cur, 0, cur, 0, T, bits ? 0 : 1, bits, 1, stream));
+    RET(vs_decoder_layer(d, &t->layers[li], s, &t->rope, T, pos_ids, cur, 0, cur, 0, T, bits ? 0 : 1, bits, t->sdpa_attention ? 0 : 1, stream));
   CK(vs::launch_rmsnorm(B(s->h), H, B(t->norm), B(hidden_out), H, T, H, d->eps, st));
   RET(linear(s, B(hidden_out), H, B(t->lm_head), nullptr, T, V, H, vs::EPI_STORE, B(logits), V, nullptr, 0, st));
   if (amax) CK(vs::launch_argmax_rows(B(logits), V, T, V, amax, st));

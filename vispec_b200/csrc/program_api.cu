@@ -100,7 +100,7 @@ int verify_step(vs_program* pg, const vs_target* t, const vs_scratch* s, const i
   const int32_t* cur = state + VS_ST_CUR_LEN;
   bool has_ssq = false;
   for (int li = 0; li < d->n_layers; ++li)
-    RET(decoder_layer(pg, d, &t->layers[li], s, &t->rope, T, pos_ids, cur, 0, cur, 0, T, bits ? 0 : 1, bits, 1, &has_ssq));
+    RET(decoder_layer(pg, d, &t->layers[li], s, &t->rope, T, pos_ids, cur, 0, cur, 0, T, bits ? 0 : 1, bits, t->sdpa_attention ? 0 : 1, &has_ssq));
   RET(vs::prog_add_norm(pg, B(s->h), H, B(t->norm), B(hidden_out), H, T, H, d->eps, has_ssq ? PROG_WS_SSQ : nullptr, H / 128));
   RET(linear(pg, B(hidden_out), H, B(t->lm_head), nullptr, T, V, H, vs::EPI_STORE, B(logits), V, nullptr, 0, nullptr));
   if (amax) RET(vs::prog_add_argmax(pg, B(logits), V, T, V, amax, fuse_argmax));

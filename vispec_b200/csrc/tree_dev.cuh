@@ -149,7 +149,7 @@ __device__ __forceinline__ void tree_build_body(const TreeBufs& tb, int* st, con
     int pos = __popcll(b) - 1;
     tb.tree_bits[tid] = b;
     tb.tree_pos[tid] = pos;
-    tb.verify_pos[tid] = pos + st[VS_ST_CUR_LEN];
+    tb.verify_pos[tid] = pos + st[VS_ST_CUR_LEN] + st[VS_ST_ROPE_DELTA];
     atomicMax(&sm.max_depth, pos + 1);
     if (tid > 0) sm.is_parent[sm.parent_slot[tid]] = 1;
   }

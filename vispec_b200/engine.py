@@ -49,6 +49,11 @@ class TargetConfig:
     max_pos: int = 8192           # forced by vispec/model/modeling_llava_next_kv.py:10
     eps: float = 1e-5
     rope_theta: float = 10000.0
+    # Qwen2.5-VL target (modeling_qwen2_5_vl_kv.py): multimodal RoPE sections over head_dim / 2 (:740-782; prefill only,
+    # decode tokens carry one position on all three axes) and SDPA attention semantics (:1065-1170).  q/k/v biases are
+    # picked up from the state dict.
+    mrope_section: Optional[tuple] = None
+    attn_impl: str = "eager"
 
     @property
     def head_dim(self) -> int:
@@ -230,8 +235,11 @@ class TargetEngine:
                     self.tiled.append((t[k], pack_weight_tiles(t[k])))
             self.tiled.append((self.lm_head, pack_weight_tiles(self.lm_head)))
         self.dims = _dims(cfg.hidden, cfg.inter, cfg.heads, cfg.kv_heads, cfg.vocab, cfg.layers, cfg.eps)
+        if cfg.attn_impl not in ("eager", "sdpa"):
+            raise NotImplementedError(f"attention implementation {cfg.attn_impl!r}")
         self.c = L.Target(self.dims, arr, L.ptr(self.embed), L.ptr(self.norm), L.ptr(self.lm_head),
-                          L.Rope(L.ptr(self.cos), L.ptr(self.sin)))
+                          L.Rope(L.ptr(self.cos), L.ptr(self.sin)), 1 if cfg.attn_impl == "sdpa" else 0)
+        self.rope_delta = 0
         self.scratch = ScratchBuffers(cfg.hidden, cfg.inter, cfg.heads, cfg.vocab, 32, self.kv_max, dev,
                                       extra_n=(cfg.heads + 2 * cfg.kv_heads) * 128)
         self.state = torch.zeros(L.ST_SLOTS, dtype=torch.int32, device=dev)
@@ -264,14 +272,20 @@ class TargetEngine:
     def get_len(self) -> int:
         return int(self.state[L.ST_CUR_LEN].item())
 
+    def set_rope_delta(self, d: int):
+        """Qwen2.5-VL `rope_deltas` (modeling_qwen2_5_vl_kv.py:2151-2170): decode position = cache position + delta."""
+        self.rope_delta = int(d)
+        self.state[L.ST_ROPE_DELTA] = int(d)
+
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         return torch.nn.functional.embedding(ids.to(self.device), self.embed)
 
     # -- prefill (outside the draft-and-verify path: library GEMMs, reference numerics) ---------------
     @torch.no_grad()
-    def prefill(self, inputs_embeds: torch.Tensor, past: int = 0):
+    def prefill(self, inputs_embeds: torch.Tensor, past: int = 0, position_ids: Optional[torch.Tensor] = None):
         """LlamaModel.forward over the prompt (modeling_llama_kv.py:927-1080) with plain torch ops / cuBLAS.
-        Writes K/V rows [past, past+L) of the slab; returns (last-row logits fp32 [V], hidden [1,L,H] post-norm)."""
+        Writes K/V rows [past, past+L) of the slab; returns (last-row logits fp32 [V], hidden [1,L,H] post-norm).
+        `position_ids`: [L], or [3, L] multimodal positions for a Qwen2.5-VL target (`mrope_section`)."""
         cfg = self.cfg
         x = inputs_embeds.to(device=self.device, dtype=self.dtype)
         if x.dim() == 2:
@@ -280,8 +294,20 @@ class TargetEngine:
         if past + Lq > self.kv_max:
             raise ValueError("prompt longer than the KV slab")
         nh, nkv, D = cfg.heads, cfg.kv_heads, 128
-        pos = torch.arange(past, past + Lq, device=self.device)
-        cos, sin = self.cos[pos][None, None], self.sin[pos][None, None]
+        if position_ids is None:
+            pos = torch.arange(past, past + Lq, device=self.device)
+        else:
+            pos = position_ids.to(self.device).long().reshape(-1, Lq)
+            pos = pos[0] if cfg.mrope_section is None else pos
+        if cfg.mrope_section is not None:
+            # apply_multimodal_rotary_pos_emb (modeling_qwen2_5_vl_kv.py:768-775): channel chunk i from axis i % 3
+            pos3 = pos if pos.dim() == 2 else pos[None].expand(3, Lq)
+            sec = list(cfg.mrope_section) * 2
+            cos = torch.cat([m[i % 3] for i, m in enumerate(self.cos[pos3].split(sec, dim=-1))], dim=-1)[None, None]
+            sin = torch.cat([m[i % 3] for i, m in enumerate(self.sin[pos3].split(sec, dim=-1))], dim=-1)[None, None]
+        else:
+            cos, sin = self.cos[pos][None, None], self.sin[pos][None, None]
+        sdpa = cfg.attn_impl == "sdpa"
         S = past + Lq
         mask = torch.full((Lq, S), torch.finfo(torch.float32).min, device=self.device)
         mask = torch.triu(mask, diagonal=past + 1)[None, None]
@@ -313,9 +339,14 @@ class TargetEngine:
                 rep = nh // nkv
                 K = K[:, :, None].expand(1, nkv, rep, S, D).reshape(1, nh, S, D)
                 V = V[:, :, None].expand(1, nkv, rep, S, D).reshape(1, nh, S, D)
-            aw = torch.matmul(q, K.transpose(2, 3)) / math.sqrt(D)
-            aw = F.softmax(aw + mask, dim=-1, dtype=torch.float32).to(self.dtype)
-            ao = torch.matmul(aw, V).transpose(1, 2).reshape(1, Lq, nh * D)
+            if sdpa:       # modeling_qwen2_5_vl_kv.py:1153-1160 (the mask is inferred when there is no past, :1489-1503)
+                ao = F.scaled_dot_product_attention(q, K, V, is_causal=True) if past == 0 else \
+                    F.scaled_dot_product_attention(q, K, V, attn_mask=mask.to(self.dtype))
+                ao = ao.transpose(1, 2).reshape(1, Lq, nh * D)
+            else:
+                aw = torch.matmul(q, K.transpose(2, 3)) / math.sqrt(D)
+                aw = F.softmax(aw + mask, dim=-1, dtype=torch.float32).to(self.dtype)
+                ao = torch.matmul(aw, V).transpose(1, 2).reshape(1, Lq, nh * D)
             h = res + F.linear(ao, t["w_o"])
             res = h
             xn = rms(h, t["ln_post"])

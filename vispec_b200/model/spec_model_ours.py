@@ -57,6 +57,8 @@ class TargetLM:
         self.dtype, self.device = engine.dtype, engine.device
         self.current_length_data = None        # set by initialize_past_key_values' caller (SpecModel)
 
+    rope_deltas = 0
+
     def get_input_embeddings(self):
         return self.engine.embed_tokens
 
@@ -79,14 +81,20 @@ class TargetLM:
             if tree_mask is not None:
                 raise ValueError("tree-masked calls take at most 32 tokens")
             emb = inputs_embeds if inputs_embeds is not None else eng.embed_tokens(input_ids)
-            _, hidden = eng.prefill(emb, past=cur)
+            if position_ids is not None and eng.cfg.mrope_section is not None and cur == 0:
+                # Qwen2.5-VL: [3, 1, L] multimodal positions; rope_deltas = max + 1 - L (get_rope_index,
+                # modeling_qwen2_5_vl_kv.py:1795-1990), cached on the model like the reference does (:2151-2164)
+                p3 = position_ids.reshape(3, -1)
+                self.rope_deltas = int(p3.max()) + 1 - p3.shape[1]
+                eng.set_rope_delta(self.rope_deltas)
+            _, hidden = eng.prefill(emb, past=cur, position_ids=position_ids)
             logits = torch.nn.functional.linear(hidden, eng.lm_head).float()
         else:
             ids = input_ids.to(eng.device, torch.int32).flatten().contiguous()
-            if position_ids is None:
-                pos = torch.arange(cur, cur + q_len, dtype=torch.int32, device=eng.device)
-            else:
-                pos = position_ids.to(eng.device, torch.int32).flatten().contiguous()
+            if position_ids is None:       # modeling_qwen2_5_vl_kv.py:2166-2175: cache position + rope_deltas (0 for Llama)
+                pos = torch.arange(cur, cur + q_len, dtype=torch.int32, device=eng.device) + eng.rope_delta
+            else:                          # [3, 1, q] for Qwen2.5-VL: text tokens carry one id on all three axes
+                pos = position_ids.to(eng.device, torch.int32).reshape(-1, q_len)[0].contiguous()
             bits = None
             if tree_mask is not None and q_len > 1:
                 tm = tree_mask.to(eng.device).reshape(tree_mask.shape[-2], tree_mask.shape[-1]) != 0
@@ -293,8 +301,12 @@ class SpecModel:
         input_len = input_ids.shape[1]
         reset_tree_mode(self)
         self.sampling_setup(logits_processor, reseed=True)
+        # Qwen2.5-VL target: [3, 1, L] multimodal prompt positions (what the reference's base model derives from
+        # image_grid_thw, see `qwen_rope_index`); the decode positions are then offset by rope_deltas on the device
+        self.base_model.rope_deltas = 0
+        eng_t.set_rope_delta(0)
         initialize_tree(input_ids, self, self.past_key_values, logits_processor, inputs_embeds, None,
-                        image_mask=special_image_mask)
+                        image_mask=special_image_mask, position_ids=kwargs.pop("position_ids", None))
         new_token = 0
         acceptance_len = []
         if return_decode_time:

@@ -88,7 +88,7 @@ def initialize_tree(input_ids, model, past_key_values, logits_processor, inputs_
                     image_mask=None, **kwargs):
     """utils.py:266-327: target prefill, first token, first draft tree."""
     outputs, orig, hidden_states = model(input_ids, past_key_values=past_key_values, output_orig=True,
-                                         inputs_embeds=inputs_embeds)
+                                         inputs_embeds=inputs_embeds, position_ids=kwargs.get("position_ids"))
     if logits_processor is not None:                                        # utils.py:284-288
         probabilities = torch.nn.functional.softmax(logits_processor(None, orig[:, -1]), dim=1)
         token = torch.multinomial(probabilities, 1)
@@ -104,6 +104,8 @@ def initialize_tree(input_ids, model, past_key_values, logits_processor, inputs_
 def tree_decoding(model, tree_candidates, past_key_values, tree_position_ids, input_ids, retrieve_indices):
     """utils.py:389-412: verify the tree with the target (tree mask taken from `base_model.model.tree_mask`)."""
     position_ids = tree_position_ids + input_ids.shape[1]
+    if getattr(model.base_model, "rope_deltas", 0):                        # utils.py:398-402 (Qwen2.5-VL)
+        position_ids = position_ids + model.base_model.rope_deltas
     outputs, tree_logits, hidden_state = model(tree_candidates, output_orig=True, past_key_values=past_key_values,
                                                position_ids=position_ids)
     logits = tree_logits[0, retrieve_indices.to(tree_logits.device)]
@@ -161,3 +163,31 @@ def update_inference_inputs(input_ids, candidates, best_candidate, accept_length
         head=_lm_head(model), logits_processor=logits_processor)
     new_token += a + 1
     return input_ids, draft_tokens, retrieve_indices, tree_mask, tree_position_ids, new_token, None, token
+
+
+def qwen_rope_index(input_ids: torch.Tensor, image_grid_thw=None, image_token_id: int = 151655,
+                    spatial_merge_size: int = 2):
+    """`Qwen2_5_VLForConditionalGeneration.get_rope_index` (modeling_qwen2_5_vl_kv.py:1795-1990) for one sequence with
+    images (no video, no padding): text tokens carry one running position on the three axes; the merged patches of an
+    image get (t, h, w) grid offsets from the position where the image starts; text after it continues from max + 1.
+    Returns (position_ids [3, 1, L], rope_delta = max + 1 - L), host-side like the reference."""
+    ids = input_ids.reshape(-1).tolist()
+    grids = [] if image_grid_thw is None else [[int(x) for x in g] for g in torch.as_tensor(image_grid_thw).tolist()]
+    chunks, st = [], 0
+    for t, h, w in grids:
+        ed = ids.index(image_token_id, st)
+        gh, gw = h // spatial_merge_size, w // spatial_merge_size
+        st_idx = int(chunks[-1].max()) + 1 if chunks else 0
+        text_len = ed - st
+        chunks.append(torch.arange(text_len).view(1, -1).expand(3, -1) + st_idx)
+        t_index = torch.arange(t).view(-1, 1).expand(-1, gh * gw).flatten() * 0   # images: second_per_grid_t = 0
+        h_index = torch.arange(gh).view(1, -1, 1).expand(t, -1, gw).flatten()
+        w_index = torch.arange(gw).view(1, 1, -1).expand(t, gh, -1).flatten()
+        chunks.append(torch.stack([t_index, h_index, w_index]) + text_len + st_idx)
+        st = ed + t * gh * gw
+    if st < len(ids):
+        st_idx = int(chunks[-1].max()) + 1 if chunks else 0
+        chunks.append(torch.arange(len(ids) - st).view(1, -1).expand(3, -1) + st_idx)
+    pos = torch.cat(chunks, dim=1).reshape(3, 1, -1)
+    return pos, int(pos.max()) + 1 - len(ids)
+
