@@ -106,3 +106,47 @@ def test_qwen_target_specgenerate_equals_greedy_oracle():
     n = min(len(got), len(want))
     agree = sum(int(a == b) for a, b in zip(got[:n], want[:n]))
     assert n >= n_new - 8 and agree == n, (got, want)
+
+
+def test_qwen7b_shapes_spec_equals_greedy():
+    """BASELINE config 3 shapes (Qwen2.5-VL-7B: H=3584, 28 q / 4 kv heads, I=18944, V=152064, 28 layers, q/k/v biases,
+    theta=1e6) with a 24 x 24 image grid in the prompt: the speculative output equals plain greedy decoding of the same
+    target through the same kernels (size-independent property; the CPU oracle would take minutes at this size)."""
+    from bench import synth_draft_weights, synth_target_weights
+    tcfg = TargetConfig(hidden=3584, inter=18944, layers=28, heads=28, kv_heads=4, vocab=152064, max_pos=8192, eps=1e-6,
+                        rope_theta=1e6, mrope_section=(16, 24, 24), attn_impl="sdpa")
+    dcfg = DraftConfig(hidden=3584, inter=18944, heads=28, vocab=152064, max_pos=4096, eps=1e-6, rope_theta=1e6)
+    tw = synth_target_weights(tcfg, 3, DEV)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    for li in range(tcfg.layers):
+        for n, rows in (("q", 28 * 128), ("k", 4 * 128), ("v", 4 * 128)):
+            tw[f"model.layers.{li}.self_attn.{n}_proj.bias"] = \
+                (torch.randn(rows, generator=g, device=DEV) * 0.3).to(torch.bfloat16)
+    dw = synth_draft_weights(dcfg, 5, DEV)
+    model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=DEV, kv_max=2048, eos_token_id=None)
+    del tw, dw
+    torch.cuda.empty_cache()
+    n_pre, grid, n_post, IMG = 5, 24, 60, 151655
+    cg = torch.Generator().manual_seed(9)
+    ids = torch.randint(1, 150000, (1, n_pre + grid * grid + n_post), generator=cg)
+    ids[0, n_pre:n_pre + grid * grid] = IMG
+    pos3, delta = vu.qwen_rope_index(ids, image_grid_thw=[[1, 2 * grid, 2 * grid]], image_token_id=IMG)
+    assert delta == n_pre + grid + n_post - ids.shape[1]
+    emb = model.base_model_engine.embed_tokens(ids.to(DEV)).clone()
+    emb[0, n_pre:n_pre + grid * grid] = (torch.randn(grid * grid, tcfg.hidden, generator=cg) * 0.02).to(torch.bfloat16).to(DEV)
+    mask = (ids == IMG).to(DEV)
+    n_tok = 16
+    out, new_token, idx, acc = model.specgenerate(ids.to(DEV), inputs_embeds=emb, image_mask=mask, position_ids=pos3.to(DEV),
+                                                  log=True, return_acceptance_len=True, max_new_tokens=n_tok)
+    assert out.shape[1] - ids.shape[1] == new_token > n_tok
+    assert int(model.base_model_engine.state[L.ST_ROPE_DELTA]) == delta
+    pkv, _, cur_len = initialize_past_key_values(model.base_model)
+    cur_len.zero_()
+    lm = model.base_model
+    o = lm(inputs_embeds=emb, past_key_values=pkv, position_ids=pos3.to(DEV))
+    seq = []
+    for _ in range(new_token):
+        tok = torch.argmax(o.logits[:, -1])[None, None]
+        seq.append(int(tok))
+        o = lm(input_ids=tok, past_key_values=pkv)           # position = cache position + rope_deltas
+    assert out[0, ids.shape[1]:].tolist() == seq
