@@ -151,6 +151,35 @@ def build_llava7b(device="cuda", seed=0, layers=32, fixture="random"):
     return model, ids, emb, mask
 
 
+def build_qwen7b(device="cuda", seed=0):
+    """BASELINE config-3 shapes (Qwen2.5-VL-7B target: 28 q / 4 kv heads, q/k/v biases, theta = 1e6, SDPA semantics,
+    multimodal RoPE over a 24 x 24 image grid in the prompt; MHA draft with the same width)."""
+    from vispec_b200.engine import DraftConfig, TargetConfig
+    from vispec_b200.model import utils as vu
+    from vispec_b200.model.spec_model_ours import SpecModel
+
+    tcfg = TargetConfig(hidden=3584, inter=18944, layers=28, heads=28, kv_heads=4, vocab=152064, max_pos=8192, eps=1e-6,
+                        rope_theta=1e6, mrope_section=(16, 24, 24), attn_impl="sdpa")
+    dcfg = DraftConfig(hidden=3584, inter=18944, heads=28, vocab=152064, max_pos=4096, eps=1e-6, rope_theta=1e6)
+    tw = synth_target_weights(tcfg, seed, device)
+    g = torch.Generator(device=device).manual_seed(seed + 2)
+    for li in range(tcfg.layers):
+        for n, rows in (("q", tcfg.heads * 128), ("k", tcfg.kv_heads * 128), ("v", tcfg.kv_heads * 128)):
+            tw[f"model.layers.{li}.self_attn.{n}_proj.bias"] = _randn(g, rows, std=0.3, device=device)
+    dw = synth_draft_weights(dcfg, seed + 1, device)
+    model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=device, eos_token_id=None)
+    del tw, dw
+    torch.cuda.empty_cache()
+    n_pre, grid, n_post, img_id = 5, 24, 123, 151655
+    cg = torch.Generator().manual_seed(seed + 7)
+    ids = torch.randint(1, 150000, (1, n_pre + grid * grid + n_post), generator=cg)
+    ids[0, n_pre:n_pre + grid * grid] = img_id
+    pos3, _ = vu.qwen_rope_index(ids, image_grid_thw=[[1, 2 * grid, 2 * grid]], image_token_id=img_id)
+    emb = model.base_model_engine.embed_tokens(ids.to(device)).clone()
+    emb[0, n_pre:n_pre + grid * grid] = (torch.randn(grid * grid, tcfg.hidden, generator=cg) * 0.02).to(torch.bfloat16).to(device)
+    return model, ids.to(device), emb, (ids == img_id).to(device), pos3.to(device), tcfg, dcfg
+
+
 # ------------------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------------------
@@ -497,6 +526,25 @@ def run_ours(args):
                    "ms_per_cycle": ms2 / max(1, len(acc2))}
         del m2
         torch.cuda.empty_cache()
+    # second model family (rank 0, N=1, informational): the same kernel on Qwen2.5-VL-7B shapes (BASELINE config 3)
+    qwen = None
+    if rank == 0 and world == 1 and not args.no_fixture:
+        m3, ids3, emb3, mask3, pos3, tc3, dc3 = build_qwen7b(device=device, seed=11)
+        kw3 = dict(gen_kw, position_ids=pos3)
+        for _ in range(2):
+            m3.specgenerate(ids3, inputs_embeds=emb3, image_mask=mask3, **kw3)
+        tok3, ms3, acc3 = 0, 0.0, []
+        for _ in range(max(1, args.steps // 2)):
+            _, n3, _, a3 = m3.specgenerate(ids3, inputs_embeds=emb3, image_mask=mask3, **kw3)
+            tok3 += n3; ms3 += m3.last_decode_ms; acc3 += a3
+        ms_cycle3 = ms3 / max(1, len(acc3))
+        by3 = cycle_algorithmic_bytes(tc3, dc3, ids3.shape[1] + GEN_TOKENS / 2 + 31, 130 + GEN_TOKENS / 2)
+        qwen = {"workload": "Qwen2.5-VL-7B shapes (28q/4kv GQA, qkv bias, V=152064) + ViSpec head, T=0, 576 img + 128 text "
+                            "tokens, 256-token gen", "value": tok3 / (ms3 * 1e-3), "unit": "tokens/s",
+                "accept_len_mean": sum(acc3) / max(1, len(acc3)), "ms_per_cycle": ms_cycle3,
+                "algorithmic_bytes_per_cycle": by3["total"], "hbm_frac": by3["total"] / (ms_cycle3 * 1e-3) / 1e9 / hbm_peak()[0]}
+        del m3
+        torch.cuda.empty_cache()
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
@@ -520,7 +568,7 @@ def run_ours(args):
             "accept_len_mean": sum(accs) / max(1, len(accs)), "cycles_per_step": len(accs) / args.steps,
             "e2e": {"value": e2e_v, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "roofline_attention": roof_attn,
-            "phases_us_per_cycle": phases, "accept_fixture": fixture, "cpu_baseline": cpu}
+            "phases_us_per_cycle": phases, "accept_fixture": fixture, "qwen2_5_vl_7b": qwen, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()
