@@ -244,6 +244,48 @@ def test_llava7b_spec_equals_greedy(llava7b):
     assert st[L.ST_D_LEN] >= 129      # 128 text rows + 1 compressed image token + accepted tokens
 
 
+def test_llava7b_sampling_is_seeded_and_in_vocabulary(llava7b):
+    """T = 1 at full LLaVA-7B shapes (the README's second column): the device sampler runs inside the cycle kernel, a
+    generation is reproducible under torch.manual_seed and differs between seeds, and the lengths bookkeeping holds."""
+    model, ids, emb, mask = llava7b
+    outs = []
+    for seed in (0, 0, 1):
+        torch.manual_seed(seed)
+        out, new_token, idx, acc = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, temperature=1.0, log=True,
+                                                      return_acceptance_len=True, max_new_tokens=20)
+        assert new_token == sum(acc) + len(acc) == out.shape[1] - ids.shape[1]
+        assert int(out.min()) >= 0 and int(out.max()) < model.vocab_size
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert outs[0].shape != outs[2].shape or not torch.equal(outs[0], outs[2])
+
+
+def test_llava13b_shapes_spec_equals_greedy():
+    """BASELINE config 4 shapes on ONE GPU (H=5120, 40 heads, I=13824; 8 of the 40 layers to keep the test short):
+    7 key splits per head in the fused attention, 40-tile residual GEMMs, 80 k-chunks per row."""
+    from bench import synth_draft_weights, synth_prompt, synth_target_weights
+    tcfg = TargetConfig(hidden=5120, inter=13824, layers=8, heads=40, kv_heads=40, vocab=32064)
+    dcfg = DraftConfig(hidden=5120, inter=13824, heads=40, vocab=32064)
+    tw = synth_target_weights(tcfg, 5, DEV)
+    dw = synth_draft_weights(dcfg, 6, DEV)
+    model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=DEV, kv_max=2048, eos_token_id=None)
+    del tw, dw
+    torch.cuda.empty_cache()
+    ids, emb, mask = synth_prompt(tcfg, model.base_model_engine.embed, 12, DEV)
+    out, new_token, idx, acc = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, log=True,
+                                                  return_acceptance_len=True, max_new_tokens=16)
+    pkv, _, cur_len = initialize_past_key_values(model.base_model)
+    cur_len.zero_()
+    lm = model.base_model
+    o = lm(inputs_embeds=emb, past_key_values=pkv)
+    seq = []
+    for _ in range(new_token):
+        tok = torch.argmax(o.logits[:, -1])[None, None]
+        seq.append(int(tok))
+        o = lm(input_ids=tok, past_key_values=pkv)
+    assert out[0, ids.shape[1]:].tolist() == seq
+
+
 def test_llava7b_bigram_fixture_accepts_and_equals_greedy():
     """Full LLaVA-7B shapes with the bigram fixture: the draft follows the target's bigram table, so
     cycles accept 2-4 drafted tokens (the target's RMSNorm rounds the embedding, the draft has no final norm, so a few
