@@ -225,11 +225,36 @@ class SpecModel:
                 if k in ("language_model.lm_head.weight", "lm_head.weight"):
                     sd["lm_head.weight"] = v
             vision = _HFLlavaVision(hf.to(device))
+        elif arch == "Qwen2_5_VLForConditionalGeneration":
+            # spec_model_ours.py:137-140,380-449.  Needs a checkpoint on disk: not exercised offline (the Qwen target
+            # itself is, at synthetic weights: tests/test_gpu_qwen.py).
+            from transformers import AutoModelForImageTextToText
+            hf = AutoModelForImageTextToText.from_pretrained(base_model_path, torch_dtype=torch.bfloat16)
+            lcfg = getattr(hf.config, "text_config", hf.config)
+            image_token_index = hf.config.image_token_id
+            sd = {}
+            for k, v in hf.state_dict().items():
+                for pre in ("model.language_model.", "language_model.model."):
+                    if k.startswith(pre):
+                        sd["model." + k[len(pre):]] = v
+                if k.startswith("model.layers.") or k in ("model.embed_tokens.weight", "model.norm.weight"):
+                    sd[k] = v                         # transformers 4.49 layout (flat text model)
+                if k in ("lm_head.weight", "language_model.lm_head.weight"):
+                    sd["lm_head.weight"] = v
+            if "lm_head.weight" not in sd:            # tied embeddings (3B)
+                sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+            vision = _HFQwenVision(hf.to(device))
+            rs = getattr(lcfg, "rope_scaling", None) or getattr(lcfg, "rope_parameters", None) or {}
+            qwen_extra = dict(mrope_section=tuple(rs.get("mrope_section", (16, 24, 24))), attn_impl="sdpa")
         else:
             raise NotImplementedError(f"Model type {arch} is not supported. Please use a supported model type.")
+        rope_theta = getattr(lcfg, "rope_theta", None)
+        if rope_theta is None:                        # transformers 5.x keeps it in rope_parameters
+            rope_theta = (getattr(lcfg, "rope_parameters", None) or {}).get("rope_theta", 10000.0)
         tcfg = TargetConfig(hidden=lcfg.hidden_size, inter=lcfg.intermediate_size, layers=lcfg.num_hidden_layers,
                             heads=lcfg.num_attention_heads, kv_heads=lcfg.num_key_value_heads, vocab=lcfg.vocab_size,
-                            max_pos=8192, eps=lcfg.rms_norm_eps, rope_theta=getattr(lcfg, "rope_theta", 10000.0))
+                            max_pos=8192, eps=lcfg.rms_norm_eps, rope_theta=rope_theta,
+                            **(qwen_extra if arch == "Qwen2_5_VLForConditionalGeneration" else {}))
         configpath = os.path.join(spec_model_path, "config.json")
         ecfg = EConfig.from_pretrained(configpath)
         dcfg = DraftConfig(hidden=ecfg.hidden_size, inter=ecfg.intermediate_size, heads=ecfg.num_attention_heads,
@@ -297,7 +322,10 @@ class SpecModel:
             if inputs_embeds is not None:
                 raise ValueError("You cannot specify both pixel_values and inputs_embeds at the same time, and must "
                                  "specify either one")
-            inputs_embeds, special_image_mask = self.vision(input_ids, **kwargs)
+            front = self.vision(input_ids, **kwargs)
+            inputs_embeds, special_image_mask = front[0], front[1]
+            if len(front) > 2:                            # Qwen2.5-VL: multimodal prompt positions
+                kwargs["position_ids"] = front[2]
         input_len = input_ids.shape[1]
         reset_tree_mode(self)
         self.sampling_setup(logits_processor, reseed=True)
@@ -419,3 +447,33 @@ class _HFLlavaVision:
         inputs_embeds = inputs_embeds.masked_scatter(mask.unsqueeze(-1).expand_as(inputs_embeds),
                                                      feats.to(inputs_embeds.dtype))
         return inputs_embeds, mask
+
+
+class _HFQwenVision:
+    """Host-side front-end of a Qwen2.5-VL checkpoint (spec_model_ours.py:380-417 + get_rope_index): token embeddings,
+    vision tower over `pixel_values` / `image_grid_thw`, scatter into the image placeholders, multimodal prompt
+    positions.  Out of the decode path; requires a real checkpoint (images only, no video)."""
+
+    def __init__(self, hf_model):
+        self.m = hf_model
+
+    @torch.no_grad()
+    def __call__(self, input_ids, pixel_values=None, image_grid_thw=None, **kw):
+        from .utils import qwen_rope_index
+        m = self.m
+        inputs_embeds = m.get_input_embeddings()(input_ids)
+        visual = m.visual if hasattr(m, "visual") else m.model.visual
+        image_embeds = visual(pixel_values.type(visual.dtype), grid_thw=image_grid_thw)
+        image_embeds = getattr(image_embeds, "pooler_output", image_embeds)
+        image_token_id = m.config.image_token_id
+        mask = input_ids == image_token_id
+        if int(mask.sum()) != image_embeds.shape[0]:
+            raise ValueError(f"Image features and image tokens do not match: tokens: {int(mask.sum())}, "
+                             f"features {image_embeds.shape[0]}")
+        inputs_embeds = inputs_embeds.masked_scatter(mask.unsqueeze(-1).expand_as(inputs_embeds),
+                                                     image_embeds.to(inputs_embeds.device, inputs_embeds.dtype))
+        merge = getattr(m.config.vision_config, "spatial_merge_size", 2)
+        pos3, _ = qwen_rope_index(input_ids.cpu(), image_grid_thw=image_grid_thw.cpu(), image_token_id=image_token_id,
+                                  spatial_merge_size=merge)
+        return inputs_embeds, mask, pos3.to(input_ids.device)
+
