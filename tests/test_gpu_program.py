@@ -293,3 +293,33 @@ def test_program_linear_tiled_weights_bit_identical(T, N, K, pf_ahead):
     run_program(lambda p: p.register_tiled([(w, wt)]).add("linear", C.byref(a1)), pf_ahead=pf_ahead)
     assert torch.equal(y0, y1)
     assert_bf16_close(y1, (x.float() @ w.float().T + b.float()).to(BF))
+
+
+@pytest.mark.parametrize("hidden,heads,inter,T", [(4096, 32, 11008, 30), (5120, 40, 13824, 30), (3584, 28, 18944, 30),
+                                                  (512, 4, 1024, 5), (4096, 32, 11008, 1)])
+def test_program_rmsnorm_folded_into_residual_epilogue(monkeypatch, hidden, heads, inter, T):
+    """An RMSNorm behind a residual epilogue runs inside that epilogue (per-group arrival counters, values still in
+    registers): one phase fewer per norm, and bit-identical hidden states / logits to the program with PH_NORM phases
+    (same per-tile sums of squares, same summation order), launch after launch."""
+    from bench import synth_target_weights
+    from vispec_b200.engine import TargetConfig, TargetEngine
+    cfg = TargetConfig(hidden=hidden, inter=inter, layers=2, heads=heads, kv_heads=heads, vocab=1024)
+    tw = synth_target_weights(cfg, 3, DEV)
+    outs, phases = [], []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("VS_FUSE_NORM", fuse)
+        eng = TargetEngine(cfg, tw, device=DEV, kv_max=256)
+        eng.prefill(0.5 * randn(40, hidden, seed=5))
+        ids = ((torch.arange(T, device=DEV) * 37 + 11) % cfg.vocab).to(torch.int32)
+        pos = (40 + torch.arange(T, device=DEV)).to(torch.int32)
+        for rep in range(3):                   # relaunches: the arrival counters are monotonic across launches
+            eng.verify(ids, pos, None, T, cur_len=40)
+            torch.cuda.synchronize()
+            outs.append((eng.hidden_out[:T].clone(), eng.logits[:T].clone()))
+        prog = next(iter(eng._verify_progs.values()))
+        phases.append(prog.phase_types())
+    n_norm = [p.count(L.PH_NORM) for p in phases]
+    assert n_norm == [2 * cfg.layers + 1, 1] and len(phases[0]) - len(phases[1]) == 2 * cfg.layers
+    for h, lg in outs[1:]:
+        assert torch.equal(h, outs[0][0]) and torch.equal(lg, outs[0][1])
+    assert bool(torch.isfinite(outs[0][1].float()).all()) and float(outs[0][0].float().abs().mean()) > 0.1

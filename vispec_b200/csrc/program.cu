@@ -416,6 +416,7 @@ struct vs_program {
   size_t ssq_floats = 0;
   size_t tile_cnt_count = 0;  // per-tile arrival counters of all fused GEMM+epilogue pairs
   bool fuse_epilogue = true;  // epilogue phases wait on per-tile counters instead of a grid barrier
+  bool fuse_norm = true;      // an RMSNorm that follows a residual epilogue runs inside that epilogue (no PH_NORM phase)
   bool attn_fused = false;    // attention as ONE phase (kv length limited to vs_attention_fused_capacity)
   size_t keys_count = 0;      // u64 entries of the arg-max / top-k candidate buffer
   size_t lstats_count = 0;    // float2 entries of the log-softmax slice statistics
@@ -568,6 +569,22 @@ int prog_add_norm(vs_program* pg, const bf16* x, long ldx, const bf16* w, bf16* 
                   const float* ssq_in, int ssq_tiles) {
   if (T < 1 || T > VS_TOK || H % 8 || ldx % 8 || ldy % 8)
     return pfail(VS_ERR_INVALID, "vs_program_add_rmsnorm", "1..32 rows, H and strides multiples of 8");
+  // RMSNorm right behind the residual epilogue that produced the rows (and their per-tile sums of squares): fold it
+  // into that epilogue.  Each (tile, 8-token group) item publishes its sums of squares, waits on the group's arrival
+  // counter for the other tiles and normalises the values it still holds in registers -- one phase, one grid barrier
+  // and one read of the rows less.  All items of a group wait for each other, so every item needs its own team.
+  if (pg->fuse_norm && pg->fuse_epilogue && ssq_in && !pg->phases.empty()) {
+    Phase& e = pg->phases.back();
+    const int G = pg->grid ? pg->grid : device_sms();
+    const int groups = (T + EPI_TPI - 1) / EPI_TPI;
+    if (e.type == PH_EPI && e.epi == EPI_RESID && e.ssq == ssq_in && e.Y == x && e.ldy == ldx && e.T == T && e.N == H &&
+        e.n_tiles == ssq_tiles && !e.w && e.n_tiles * groups <= PG_TEAMS * G) {
+      e.w = w; e.dst = y; e.ldd = ldy; e.H = H; e.eps = eps;
+      e.norm_cnt = reinterpret_cast<unsigned int*>(uintptr_t(pg->tile_cnt_count + 1));
+      pg->tile_cnt_count += 4;
+      return VS_OK;
+    }
+  }
   Phase ph = blank(PH_NORM, T);
   ph.src = x; ph.lds = ldx; ph.w = w; ph.dst = y; ph.ldd = ldy; ph.H = H; ph.eps = eps;
   ph.ssq_in = ssq_in; ph.ssq_tiles = ssq_tiles;
@@ -758,6 +775,8 @@ int vs_program_create(vs_program** out) {
   if (e) (*out)->inflight = atoi(e);
   e = getenv("VS_FUSE_EPILOGUE");
   if (e) (*out)->fuse_epilogue = atoi(e) != 0;
+  e = getenv("VS_FUSE_NORM");
+  if (e) (*out)->fuse_norm = atoi(e) != 0;
   e = getenv("VS_SPIN_NS");
   if (e) (*out)->spin_ns = atoi(e);
   return VS_OK;
@@ -780,6 +799,10 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   } else if (!strcmp(name, "fuse_epilogue")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "fuse_epilogue must be set before adding phases");
     pg->fuse_epilogue = value != 0;
+  }
+  else if (!strcmp(name, "fuse_norm")) {
+    if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "fuse_norm must be set before adding phases");
+    pg->fuse_norm = value != 0;
   }
   else if (!strcmp(name, "spin_ns")) pg->spin_ns = value;
 
@@ -841,6 +864,8 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
     if (!(ph.type == PH_GEMM && ph.no_barrier)) ++bars;
     if (ph.tile_cnt)
       ph.tile_cnt = reinterpret_cast<unsigned int*>(pg->ws + pg->off_tilecnt) + (reinterpret_cast<uintptr_t>(ph.tile_cnt) - 1);
+    if (ph.norm_cnt)
+      ph.norm_cnt = reinterpret_cast<unsigned int*>(pg->ws + pg->off_tilecnt) + (reinterpret_cast<uintptr_t>(ph.norm_cnt) - 1);
     if (ph.type == PH_GEMM || ph.type == PH_EPI) ph.partials = partials;
     if (ph.ssq == PROG_WS_SSQ) ph.ssq = reinterpret_cast<float*>(pg->ws + pg->off_ssq);
     if (ph.ssq_in == PROG_WS_SSQ) ph.ssq_in = reinterpret_cast<float*>(pg->ws + pg->off_ssq);

@@ -55,6 +55,7 @@ struct Phase {
   bf16* Y; long ldy;
   const bf16* R; long ldr;
   float* ssq;                 // residual epilogue: [n_tiles][32] sums of squares of the new rows (or null)
+  unsigned int* norm_cnt;     // PH_EPI with a folded-in RMSNorm (`w` != null): [4] arrivals per group of 8 token rows, monotonic
   int n_q_tiles, n_k_tiles, rope;
   const bf16* cos; const bf16* sin; const int* pos_ids;
   bf16* Qout; long q_head_stride;

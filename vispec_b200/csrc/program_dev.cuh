@@ -233,11 +233,14 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       bf16* Y = ph.Y;
       const long ldy = ph.ldy;
       float* ssq = ph.ssq;
+      const bf16* nw = ph.w;                                           // folded-in RMSNorm (prog_add_norm) or null
+      float nwf[2], yv[2][EPI_TPT];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int n = tile * PG_BM + col + 64 * j;
         ok[j] = n < N;
         bias[j] = ph.bias ? bf2f(ph.bias[min(n, N - 1)]) : 0.f;
+        nwf[j] = nw ? bf2f(nw[min(n, N - 1)]) : 0.f;
       }
       if (ssq) sync();                                                 // previous item's readers of `red` are done
 #pragma unroll
@@ -248,6 +251,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
           float v = a[j][i] + bias[j];
           if (resid) v = bf_bits(rraw[j][i]) + rbf(v);                 // Linear output rounds to bf16, then the add rounds again
           const bf16 y = f2bf(v);
+          yv[j][i] = bf2f(y);
           if (ok[j] && ts + i < T) {
             Y[(long)(ts + i) * ldy + tile * PG_BM + col + 64 * j] = y;
             q += bf2f(y) * bf2f(y);
@@ -264,6 +268,40 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
           const int h = tt >> 2, i = tt & 3;
           const int t = grp * EPI_TPI + tt;
           if (t < T) ssq[tile * VS_TOK + t] = red[(2 * h) * EPI_TPT + i] + red[(2 * h + 1) * EPI_TPT + i];
+        }
+      }
+      if (nw) {
+        // LlamaRMSNorm of the finished rows (same arithmetic and summation order as norm_phase): publish this tile's
+        // sums of squares, wait until every tile of the token group has arrived, normalise the values still in registers
+        sync();
+        if (tt == 0) {
+          unsigned int* cnt = ph.norm_cnt + grp;
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+          const unsigned int want = (epoch + 1u) * (unsigned int)ph.n_tiles;
+          while (ld_relaxed_u32(cnt) < want) {
+          }
+        }
+        sync();
+        const int n_tiles = ph.n_tiles;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {                                  // warp w: tokens 2w, 2w+1 of the group
+          const int t = grp * EPI_TPI + 2 * warp + q;
+          float ss = 0.f;
+          if (t < T)
+            for (int i = lane; i < n_tiles; i += 32) ss += __ldcg(ssq + i * VS_TOK + t);
+          ss = warp_sum(ss);
+          if (lane == 0) red[32 + 2 * warp + q] = 1.0f / sqrtf(ss / (float)ph.H + ph.eps);
+        }
+        sync();
+        bf16* X = ph.dst;
+        const long ldd = ph.ldd;
+#pragma unroll
+        for (int i = 0; i < EPI_TPT; ++i) {
+          const float rstd = red[32 + half * EPI_TPT + i];
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (ok[j] && ts + i < T)                                   // weight * bf16(x * rstd): two bf16 roundings
+              X[(long)(ts + i) * ldd + tile * PG_BM + col + 64 * j] = f2bf(nwf[j] * rbf(yv[j][i] * rstd));
         }
       }
     }
