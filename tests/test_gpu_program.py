@@ -227,9 +227,12 @@ def program_attention(Q, K, V, nh, nkv, Tq, n_ctx, n_new, causal, bits, eager, n
 @pytest.mark.parametrize("eager", [True, False])
 @pytest.mark.parametrize("nh,nkv,n_ctx,fused", [(32, 32, 704, False), (4, 2, 61, False), (2, 2, 0, False), (8, 8, 3000, False),
                                                 (32, 32, 704, True), (32, 32, 1100, True), (4, 2, 61, True), (2, 2, 0, True),
-                                                (8, 8, 1900, True)])
+                                                (8, 8, 1900, True),
+                                                # beyond 2 chunks per split the single-phase attention streams its chunks
+                                                (32, 32, 1200, True), (32, 32, 3000, True), (32, 32, 8100, True),
+                                                (4, 2, 2500, True), (28, 4, 3333, True), (8, 8, 4000, True), (40, 40, 2000, True)])
 def test_program_attention_tree(eager, nh, nkv, n_ctx, fused):
-    T, rows = 30, 4096
+    T, rows = 30, max(4096, (n_ctx + 30 + 63) // 64 * 64)
     Q = randn(nh, 32, 128, seed=20)
     K, V = randn(nkv, rows, 128, seed=21), randn(nkv, rows, 128, seed=22)
     bits = tk.tree_bits(T, 5)
@@ -240,11 +243,11 @@ def test_program_attention_tree(eager, nh, nkv, n_ctx, fused):
 
 
 @pytest.mark.parametrize("fused", [False, True])
-@pytest.mark.parametrize("Tq,n_ctx", [(1, 100), (5, 129), (8, 40), (32, 0)])
+@pytest.mark.parametrize("Tq,n_ctx", [(1, 100), (5, 129), (8, 40), (32, 0), (1, 3000), (8, 2100), (32, 3990)])
 def test_program_attention_causal(Tq, n_ctx, fused):
     nh = nkv = 4
     Q = randn(nh, 32, 128, seed=23)
-    K, V = randn(nkv, 1024, 128, seed=24), randn(nkv, 1024, 128, seed=25)
+    K, V = randn(nkv, 4096, 128, seed=24), randn(nkv, 4096, 128, seed=25)
     O = program_attention(Q, K, V, nh, nkv, Tq, n_ctx, Tq, True, None, False, n_ctx_dev=(n_ctx > 0), fused=fused)
     ref = tk.attention_ref(Q[:, :Tq], K, V, n_ctx, Tq, True, None, False, nh, nkv)
     torch.testing.assert_close(O.float(), ref.float(), rtol=2 ** -6, atol=2e-2)

@@ -169,7 +169,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # VS_LIB_PATH: an alternative build of the same library (kernel A/B experiments); still no fallback of any kind
+    return os.environ.get("VS_LIB_PATH") or _build.LIB_PATH
 
 
 def load():

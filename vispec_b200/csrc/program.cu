@@ -40,7 +40,10 @@ namespace vs {
 
 namespace {
 
-constexpr int BM = PG_BM, BK = PG_BK, NS = 6;
+#ifndef VS_PG_STAGES
+#define VS_PG_STAGES 6          // weight/activation ring depth per SM (run-ahead buffer); 8 measured slower, 3-4 see DESIGN.md
+#endif
+constexpr int BM = PG_BM, BK = PG_BK, NS = VS_PG_STAGES;
 constexpr int W_STAGE = BM * BK * 2;             // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;         // 4096
 constexpr int STAGE_BYTES = W_STAGE + X_STAGE;   // 20480 (multiple of 1024)
@@ -84,12 +87,22 @@ __device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_tea
   for (int item = gteam; item < n_items; item += n_teams)
     attn_pv_item(a, sm, item / a.pv_splits, 0, 1, item % a.pv_splits, a.pv_splits, tt, tsync);
 }
+__device__ __noinline__ void attn_stream_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
+                                               BigTeamSync tsync) {
+  const AttnArgs a = ph.attn;
+  attn_stream_item(a, *reinterpret_cast<AttnFusedSmem*>(tsm), gteam / a.pv_splits, gteam % a.pv_splits, a.pv_splits,
+                   ph.tile_cnt, epoch, tt, tsync);
+}
 __device__ __noinline__ void attn_fused_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
                                               BigTeamSync tsync) {
   const AttnArgs a = ph.attn;
-  if (gteam < a.n_heads * a.pv_splits)       // one resident item per team: the items of a head wait for each other
-    attn_fused_item(a, *reinterpret_cast<AttnFusedSmem*>(tsm), gteam / a.pv_splits, gteam % a.pv_splits, a.pv_splits,
-                    ph.tile_cnt, epoch, tt, tsync);
+  if (gteam >= a.n_heads * a.pv_splits) return;   // one resident item per team: the items of a head wait for each other
+  // up to ATT_FUSED_CPS chunks per split the scores stay in registers; longer contexts stream (same for every item)
+  const int n_ctx = a.n_ctx ? ld_vol(a.n_ctx) : a.n_ctx_host;
+  const int n_chunks = (n_ctx + a.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
+  if (n_chunks > ATT_FUSED_CPS * a.pv_splits) { attn_stream_phase(ph, epoch, gteam, tt, tsm, tsync); return; }
+  attn_fused_item(a, *reinterpret_cast<AttnFusedSmem*>(tsm), gteam / a.pv_splits, gteam % a.pv_splits, a.pv_splits,
+                  ph.tile_cnt, epoch, tt, tsync);
 }
 __device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team_base) {
   // the tree bodies read device state with plain loads: drop whatever this SM's L1 still holds from an earlier phase of
@@ -814,7 +827,11 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
 }
 
 int vs_attention_fused_capacity(int n_heads, int pv_splits_cap, int max_chunks) {
-  return vs::fused_splits(vs::device_sms(), n_heads, pv_splits_cap, max_chunks) * vs::ATT_FUSED_CPS * vs::ATT_CHUNK;
+  // beyond splits * ATT_FUSED_CPS chunks (scores in registers) the phase streams its chunks: the scratch is the limit
+  const char* e = getenv("VS_ATTN_STREAM");
+  if (e && atoi(e) == 0)
+    return vs::fused_splits(vs::device_sms(), n_heads, pv_splits_cap, max_chunks) * vs::ATT_FUSED_CPS * vs::ATT_CHUNK;
+  return vs::fused_splits(vs::device_sms(), n_heads, pv_splits_cap, max_chunks) < 1 ? 0 : max_chunks * vs::ATT_CHUNK;
 }
 
 int vs_program_register_tiled(vs_program* pg, const void* w_row_major, const void* w_tiled) {
