@@ -1,0 +1,90 @@
+"""torchrun entry (one rank per GPU, NCCL): tensor-parallel target prefill through the product API against the
+single-device prefill of the same engine, then a speculative generation whose tokens must agree on every rank and with
+the single-device run.  Prints TP_PREFILL_OK on rank 0.  Shapes: LLaVA-1.6-13B rows (H=5120, 40 heads, I=13824), 4 layers."""
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+    from bench import synth_draft_weights, synth_prompt, synth_target_weights
+    from vispec_b200.engine import DraftConfig, TargetConfig
+    from vispec_b200.model.spec_model_ours import SpecModel
+    layers = int(os.environ.get("TP_CHECK_LAYERS", "4"))
+    tcfg = TargetConfig(hidden=5120, inter=13824, layers=layers, heads=40, kv_heads=40, vocab=32064)
+    dcfg = DraftConfig(hidden=5120, inter=13824, heads=40, vocab=32064)
+    tw, dw = synth_target_weights(tcfg, 5, dev), synth_draft_weights(dcfg, 6, dev)      # same seed on every rank
+    model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=dev, kv_max=2048, eos_token_id=None)
+    del tw, dw
+    eng = model.base_model_engine
+    ids, emb, mask = synth_prompt(tcfg, eng.embed, 12, dev)
+    # single-device prefill
+    lg0, hid0 = eng.prefill(emb)
+    kv0 = eng.kv[:, :, :, :emb.shape[1]].clone()
+    out0 = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, log=True, max_new_tokens=24)[0]
+    # tensor-parallel prefill
+    model.enable_tensor_parallel_prefill()
+    eng.kv.zero_()
+    lg1, hid1 = eng.prefill(emb)
+    kv1 = eng.kv[:, :, :, :emb.shape[1]]
+    err_h = float((hid1.float() - hid0.float()).abs().max())
+    exact_h = float((hid1 == hid0).float().mean())
+    err_kv = float((kv1.float() - kv0.float()).abs().max())
+    exact_kv = float((kv1 == kv0).float().mean())
+    # Sliced GEMMs pick other cuBLAS kernels (another fp32 summation order): ~1 % of the bf16 outputs of a layer move by one
+    # ulp and the differences compound through the residual stream, so exactness is asserted for the first layer's KV
+    # and closeness (a few bf16 ulps) for everything downstream.
+    exact_kv0 = float((kv1[:2] == kv0[:2]).float().mean())
+    assert exact_kv0 > 0.97, exact_kv0
+    torch.testing.assert_close(hid1.float(), hid0.float(), rtol=2 ** -5, atol=0.06)
+    torch.testing.assert_close(kv1.float(), kv0.float(), rtol=2 ** -5, atol=0.06)
+    assert int(torch.argmax(lg1)) == int(torch.argmax(lg0))
+    # all ranks hold the same hidden states and KV
+    ref = hid1.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(ref, hid1)
+    chk = kv1.float().sum().reshape(1)
+    chks = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(chks, chk)
+    assert all(torch.equal(c, chk) for c in chks)
+    out1 = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, log=True, max_new_tokens=24)[0]
+    o = out1.clone()
+    dist.broadcast(o, 0)
+    assert torch.equal(o, out1), "ranks diverged"
+    n_same = int((out1[0, :min(out0.shape[1], out1.shape[1])] == out0[0, :min(out0.shape[1], out1.shape[1])]).sum())
+    # timing: prefill single vs TP (CUDA events, max over ranks)
+    def timed(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+    t_tp = timed(lambda: eng.prefill(emb))
+    eng._tp = None
+    t_1 = timed(lambda: eng.prefill(emb))
+    if rank == 0:
+        print(f"TP_PREFILL_OK world={world} layers={layers} rows={emb.shape[1]} hidden_exact={exact_h:.4f} kv_exact={exact_kv:.4f} kv_layer0_exact={exact_kv0:.4f} "
+              f"max_err={err_h:.4f} tokens_equal_to_single_device={n_same}/{out0.shape[1]} "
+              f"prefill_ms single={t_1:.2f} tp{world}={t_tp:.2f}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

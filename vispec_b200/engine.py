@@ -252,6 +252,21 @@ class TargetEngine:
         self._v_pos = torch.zeros(32, dtype=torch.int32, device=dev)
         self._v_bits = torch.zeros(32, dtype=torch.int64, device=dev)
         self._verify_progs: Dict[tuple, Program] = {}
+        self._tp = None                      # (group, rank, world) once enable_tensor_parallel_prefill() was called
+
+    def enable_tensor_parallel_prefill(self, group=None):
+        """Shard the prompt pass over the ranks of `group` (default: the world group; one process per GPU, NCCL):
+        column-parallel q/k/v/gate/up, row-parallel o/down with one all-reduce each, KV all-gathered at the end
+        (vispec_b200/tp_prefill.py).  Every rank must then call prefill / specgenerate with the same prompt; the
+        draft-and-verify decode stays replicated."""
+        import torch.distributed as dist
+        from . import tp_prefill
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("enable_tensor_parallel_prefill needs an initialised torch.distributed process group")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        tp_prefill.check_shardable(self.cfg.heads, self.cfg.kv_heads, self.cfg.inter, world)
+        self._tp = (group, rank, world)
+        return self
 
     def _verify_program(self, T: int, has_bits: bool, fused: bool) -> Program:
         key = (T, has_bits, fused)
@@ -313,6 +328,15 @@ class TargetEngine:
         mask = torch.triu(mask, diagonal=past + 1)[None, None]
         h = x
         F = torch.nn.functional
+        if self._tp is not None and self._tp[2] > 1:
+            from . import tp_prefill
+            group, rank, world = self._tp
+            h = tp_prefill.prefill_layers(x[0], self.layers_t, self.kv, heads=nh, kv_heads=nkv, inter=cfg.inter, eps=cfg.eps,
+                                          cos=cos, sin=sin, past=past, sdpa=sdpa, rank=rank, world=world, group=group)[None]
+            hidden = tp_prefill._rms(h, self.norm, cfg.eps)
+            logits_last = F.linear(hidden[0, -1], self.lm_head).float()
+            self.set_len(S)
+            return logits_last, hidden
 
         def rms(t, w):
             tf = t.float()

@@ -272,6 +272,12 @@ class SpecModel:
                                     image_token_index=image_token_index, vision=vision)
 
     # -- nn.Module-ish surface the evaluation scripts touch ----------------------------------------------
+    def enable_tensor_parallel_prefill(self, group=None):
+        """Tensor-parallel target prefill over the ranks of `group` (BASELINE config 4; TargetEngine docstring).  All
+        ranks then run specgenerate on the same prompt and produce the same tokens."""
+        self.base_model_engine.enable_tensor_parallel_prefill(group)
+        return self
+
     def get_tokenizer(self):
         return self.tokenizer
 
