@@ -99,9 +99,11 @@ def synth_draft_weights(cfg, seed, device, gain=0.5):
     return w
 
 
-def synth_prompt(cfg, embed, seed, device):
+def synth_prompt(cfg, embed, seed, device, n_post=None):
+    """5 text + 576 image + `n_post` text tokens (default: the 128-text-token workload of BASELINE config 2; config 5
+    draws 64-512 text tokens per stream)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    L = N_PRE + N_IMG + N_POST
+    L = N_PRE + N_IMG + (N_POST if n_post is None else n_post)
     ids = torch.randint(1, cfg.vocab - 64, (1, L), generator=g)
     mask = torch.zeros(1, L, dtype=torch.bool)
     mask[0, N_PRE:N_PRE + N_IMG] = True
@@ -545,6 +547,14 @@ def run_ours(args):
                 "algorithmic_bytes_per_cycle": by3["total"], "hbm_frac": by3["total"] / (ms_cycle3 * 1e-3) / 1e9 / hbm_peak()[0]}
         del m3
         torch.cuda.empty_cache()
+    # the verify attention on its own at longer contexts (rank 0, N=1, informational): 32 attention phases over distinct
+    # K/V slabs per launch (tools/bench_attention.py); beyond 1152 keys the single-phase attention streams its chunks
+    attn_long = None
+    if rank == 0 and world == 1 and not args.no_fixture and use_programs():
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        from bench_attention import measure as attn_measure
+        attn_long = [attn_measure(kv, True, peak=hbm_peak()[0], dev=device) for kv in (2048, 8192)]
+        torch.cuda.empty_cache()
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
@@ -568,7 +578,8 @@ def run_ours(args):
             "accept_len_mean": sum(accs) / max(1, len(accs)), "cycles_per_step": len(accs) / args.steps,
             "e2e": {"value": e2e_v, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "roofline_attention": roof_attn,
-            "phases_us_per_cycle": phases, "accept_fixture": fixture, "qwen2_5_vl_7b": qwen, "cpu_baseline": cpu}
+            "phases_us_per_cycle": phases, "accept_fixture": fixture, "qwen2_5_vl_7b": qwen,
+            "attention_long_context": attn_long, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()

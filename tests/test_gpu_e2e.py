@@ -309,3 +309,41 @@ def test_llava7b_bigram_fixture_accepts_and_equals_greedy():
     assert out[0, ids.shape[1]:].tolist() == seq
     del model
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("n_text,seed", [(64, 1), (203, 2), (512, 3)])
+def test_config5_mixed_prompt_lengths_spec_equals_greedy(n_text, seed):
+    """BASELINE config 5: independent batch-1 streams with 576 image + 64..512 text tokens.  LLaVA-7B rows (4 of the 32
+    layers).  The longest prompt crosses 1152 keys, where the single-phase attention switches from scores-in-registers
+    to streamed chunks inside the same cycle program; the output must equal plain greedy decoding either way."""
+    from bench import synth_draft_weights, synth_prompt, synth_target_weights
+    tcfg = TargetConfig(hidden=4096, inter=11008, layers=4, heads=32, kv_heads=32, vocab=32064)
+    dcfg = DraftConfig(hidden=4096, inter=11008, heads=32, vocab=32064)
+    tw = synth_target_weights(tcfg, 20 + seed, DEV)
+    dw = synth_draft_weights(dcfg, 30 + seed, DEV)
+    model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=DEV, kv_max=2048, eos_token_id=None)
+    del tw, dw
+    ids, emb, mask = synth_prompt(tcfg, model.base_model_engine.embed, 40 + seed, DEV, n_post=n_text)
+    assert ids.shape[1] == 5 + 576 + n_text
+    out, new_token, idx, acc = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, log=True,
+                                                  return_acceptance_len=True, max_new_tokens=80)
+    assert set(k[0] for k in model._cycle_progs) == {True}        # one (single-phase) program for every context length
+    # Teacher-forced greedy check.  The verify step sees 30 more keys than the single-token decode of the same position,
+    # so around a chunk-grouping change (here: scores-in-registers -> streamed at 1152 keys) the two run different fp32
+    # reduction groupings and a bf16 logit can move by one ulp; an exact bf16 tie at the top then resolves differently.
+    # Every generated token must be the causal decode's arg-max or within two bf16 ulps of it, and all but a few exact.
+    pkv, _, cur_len = initialize_past_key_values(model.base_model)
+    cur_len.zero_()
+    lm = model.base_model
+    o = lm(inputs_embeds=emb, past_key_values=pkv)
+    gen = out[0, ids.shape[1]:].tolist()
+    assert len(gen) == new_token
+    n_off = 0
+    for tok in gen:
+        lg = o.logits[0, -1].float()
+        top = float(lg.max())
+        if int(torch.argmax(lg)) != tok:
+            n_off += 1
+            assert float(lg[tok]) >= top - 2 * 2 ** -7 * abs(top), (tok, float(lg[tok]), top)
+        o = lm(input_ids=torch.tensor([[tok]], device=DEV), past_key_values=pkv)
+    assert n_off <= 3, n_off
