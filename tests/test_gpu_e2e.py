@@ -347,3 +347,42 @@ def test_config5_mixed_prompt_lengths_spec_equals_greedy(n_text, seed):
             assert float(lg[tok]) >= top - 2 * 2 ** -7 * abs(top), (tok, float(lg[tok]), top)
         o = lm(input_ids=torch.tensor([[tok]], device=DEV), past_key_values=pkv)
     assert n_off <= 3, n_off
+
+
+@pytest.mark.parametrize("rows", [57, 704])
+def test_prefill_native_matches_library_prefill(rows, monkeypatch):
+    """The prompt pass on the library's own kernels (TargetEngine.prefill_native, VS_PREFILL=native) against the cuBLAS /
+    torch prompt pass: KV rows, hidden states and the next token; then a generation started from the native prefill."""
+    from bench import synth_draft_weights, synth_target_weights
+    tcfg = TargetConfig(hidden=4096, inter=11008, layers=3, heads=32, kv_heads=32, vocab=32064)
+    dcfg = DraftConfig(hidden=4096, inter=11008, heads=32, vocab=32064)
+    tw = synth_target_weights(tcfg, 51, DEV)
+    dw = synth_draft_weights(dcfg, 52, DEV)
+    model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=DEV, kv_max=1024, eos_token_id=None)
+    eng = model.base_model_engine
+    g = torch.Generator(device=DEV).manual_seed(rows)
+    emb = (0.5 * torch.randn(1, rows, 4096, generator=g, device=DEV)).to(torch.bfloat16)
+    lg0, hid0 = eng.prefill(emb)
+    kv0 = eng.kv[:, :, :, :rows].clone()
+    eng.kv.zero_()
+    lg1, hid1 = eng.prefill_native(emb)
+    kv1 = eng.kv[:, :, :, :rows]
+    assert float((kv1[:2] == kv0[:2]).float().mean()) > 0.97                # first layer: one GEMM's summation order
+    torch.testing.assert_close(kv1.float(), kv0.float(), rtol=2 ** -5, atol=0.06)
+    torch.testing.assert_close(hid1.float(), hid0.float(), rtol=2 ** -5, atol=0.06)
+    assert float((hid1 == hid0).float().mean()) > 0.15              # 1-ulp differences compound through the residual stream
+    assert int(torch.argmax(lg1)) == int(torch.argmax(lg0))
+    # appended segment (past > 0)
+    emb2 = emb[:, :9] * 0.7
+    eng.set_len(rows)
+    _, h2n = eng.prefill_native(emb2, past=rows)
+    kv2n = eng.kv[:, :, :, :rows + 9].clone()
+    eng.kv[:, :, :, :rows] = kv0
+    _, h2l = eng.prefill(emb2, past=rows)
+    torch.testing.assert_close(h2n.float(), h2l.float(), rtol=2 ** -5, atol=0.06)
+    torch.testing.assert_close(kv2n[..., rows:, :].float(), eng.kv[:, :, :, rows:rows + 9].float(), rtol=2 ** -5, atol=0.06)
+    # a whole generation on the native prompt pass
+    monkeypatch.setenv("VS_PREFILL", "native")
+    ids = torch.randint(1, 32000, (1, rows), device=DEV)
+    out, new_token, idx, acc = model.specgenerate(ids, log=True, return_acceptance_len=True, max_new_tokens=12)
+    assert new_token >= 12 and out.shape[1] == rows + new_token

@@ -302,6 +302,8 @@ class TargetEngine:
         Writes K/V rows [past, past+L) of the slab; returns (last-row logits fp32 [V], hidden [1,L,H] post-norm).
         `position_ids`: [L], or [3, L] multimodal positions for a Qwen2.5-VL target (`mrope_section`)."""
         cfg = self.cfg
+        if os.environ.get("VS_PREFILL") == "native" and cfg.mrope_section is None and self._tp is None:
+            return self.prefill_native(inputs_embeds, past)
         x = inputs_embeds.to(device=self.device, dtype=self.dtype)
         if x.dim() == 2:
             x = x[None]
@@ -381,6 +383,43 @@ class TargetEngine:
         logits_last = F.linear(hidden[0, -1], self.lm_head).float()
         self.set_len(S)
         return logits_last, hidden
+
+    # -- prefill on the library's own kernels --------------------------------------------------------------------
+    @torch.no_grad()
+    def prefill_native(self, inputs_embeds: torch.Tensor, past: int = 0):
+        """The prompt pass through the C ABI (`vs_decoder_layer` per layer over all prompt rows: RMSNorm, tcgen05 q|k|v
+        GEMM with RoPE + in-place KV append, causal attention, o_proj + residual, SwiGLU MLP), then the final norm.  Same
+        results as `prefill` up to fp32 summation order; 1-D RoPE targets (Llama / LLaVA) only.  Selected by
+        VS_PREFILL=native; the default prompt pass uses library GEMMs (cuBLAS), which are faster at hundreds of rows."""
+        cfg = self.cfg
+        if cfg.mrope_section is not None:
+            raise NotImplementedError("prefill_native: multimodal RoPE prompts use prefill()")
+        x = inputs_embeds.to(device=self.device, dtype=self.dtype)
+        x = x[0] if x.dim() == 3 else x
+        Lq = x.shape[0]
+        S = past + Lq
+        if S > self.kv_max:
+            raise ValueError("prompt longer than the KV slab")
+        big = getattr(self, "_prefill_scratch", None)
+        if big is None or big.max_rows < Lq or big.score_ld < S:
+            big = self._prefill_scratch = ScratchBuffers(cfg.hidden, cfg.inter, cfg.heads, cfg.vocab, _ceil(Lq, 32),
+                                                         _ceil(S, 64), self.device,
+                                                         extra_n=(cfg.heads + 2 * cfg.kv_heads) * 128)
+        big.h[:Lq] = x
+        pos = torch.arange(past, S, dtype=torch.int32, device=self.device)
+        rope = L.Rope(L.ptr(self.cos), L.ptr(self.sin))
+        st = _stream()
+        eager = 0 if cfg.attn_impl == "sdpa" else 1
+        for li in range(cfg.layers):
+            L.check(self.lib.vs_decoder_layer(C.byref(self.dims), C.byref(self._layer_arr[li]), C.byref(big.c), C.byref(rope),
+                                              Lq, L.ptr(pos), None, past, None, past, Lq, 1, None, eager, st),
+                    "prefill layer")
+        hidden = torch.empty(Lq, cfg.hidden, dtype=self.dtype, device=self.device)
+        L.check(self.lib.vs_rmsnorm(L.ptr(big.h), cfg.hidden, L.ptr(self.norm), L.ptr(hidden), cfg.hidden, Lq, cfg.hidden,
+                                    cfg.eps, st), "vs_rmsnorm")
+        logits_last = torch.nn.functional.linear(hidden[-1], self.lm_head).float()
+        self.set_len(S)
+        return logits_last, hidden[None]
 
     # -- decode / verify through the C ABI -----------------------------------------------------------------
     def verify(self, token_ids: torch.Tensor, pos_ids: torch.Tensor, bits: Optional[torch.Tensor], T: int,
