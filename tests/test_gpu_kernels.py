@@ -60,7 +60,10 @@ def assert_bf16_close(got, ref, frac_exact=0.99):
 
 
 @pytest.mark.parametrize("T,N,K", [(1, 256, 256), (5, 1000, 256), (30, 4096, 4096), (32, 4096, 11008), (8, 32064, 4096),
-                                   (45, 768, 512), (30, 4096, 8192)])
+                                   (45, 768, 512), (30, 4096, 8192),
+                                   # more than 64 rows: the prompt-pass kernel (gemm_wide.cu, 256-token MMA tiles)
+                                   (65, 256, 256), (129, 4096, 4096), (256, 1000, 512), (257, 384, 4096), (704, 4096, 11008),
+                                   (576, 4096, 4096)])
 @pytest.mark.parametrize("bias", [False, True])
 def test_linear_store(T, N, K, bias):
     x, w = randn(T, K, seed=1), randn(N, K, std=K ** -0.5, seed=2)
@@ -86,17 +89,22 @@ def test_linear_split_k_is_deterministic(splits):
     assert_bf16_close(outs[0], (x.float() @ w.float().T).to(BF))
 
 
-def test_linear_residual():
-    T, N, K = 30, 4096, 4096
+@pytest.mark.parametrize("T", [30, 129, 704])
+def test_linear_residual(T):
+    N, K = 4096, 4096
     x, w, r = randn(T, K, seed=6), randn(N, K, std=K ** -0.5, seed=7), randn(T, N, seed=8)
     y = r.clone()
     linear(x, w, None, T, N, K, epi=L.EPI_RESID, y=y, R=y)          # in place, as the decoder layer uses it
     ref = (r.float() + rbf(x.float() @ w.float().T)).to(BF)
-    assert_bf16_close(y, ref)
+    # one bf16 ulp of the linear output (|acc| < 4: 2^-6) survives a cancelling residual add unchanged
+    assert torch.isfinite(y.float()).all()
+    torch.testing.assert_close(y.float(), ref.float(), rtol=2 ** -7, atol=2 ** -6)
+    assert (y == ref).float().mean().item() >= 0.99
 
 
-def test_linear_swiglu():
-    T, H, I = 30, 4096, 11008
+@pytest.mark.parametrize("T", [30, 300])
+def test_linear_swiglu(T):
+    H, I = 4096, 11008
     x = randn(T, H, seed=9)
     gate, up = randn(I, H, std=H ** -0.5, seed=10), randn(I, H, std=H ** -0.5, seed=11)
     w = pack_gate_up(gate, up)
@@ -104,13 +112,14 @@ def test_linear_swiglu():
     linear(x, w, None, T, 2 * I, H, epi=L.EPI_SWIGLU, y=y)
     g, u = rbf(x.float() @ gate.float().T), rbf(x.float() @ up.float().T)
     ref = (rbf(torch.nn.functional.silu(g)) * u).to(BF)
-    # silu amplifies 1-ulp differences of g; still one bf16 ulp at the output
-    assert_bf16_close(y, ref, frac_exact=0.97)
+    # silu and the product amplify 1-ulp differences of g and u: a few bf16 ulps at single outputs, >= 97 % bit-exact
+    torch.testing.assert_close(y.float(), ref.float(), rtol=2 ** -5, atol=2e-2)
+    assert (y == ref).float().mean().item() >= 0.97
 
 
-@pytest.mark.parametrize("nh,nkv,T", [(32, 32, 30), (4, 2, 7), (2, 2, 40)])
+@pytest.mark.parametrize("nh,nkv,T", [(32, 32, 30), (4, 2, 7), (2, 2, 40), (4, 2, 200), (8, 8, 704)])
 def test_linear_heads_rope_and_kv_append(nh, nkv, T):
-    H, D, max_rows, max_pos = nh * 128, 128, 256, 512
+    H, D, max_rows, max_pos = nh * 128, 128, 1024, 1024
     x = randn(T, H, seed=12)
     w = randn((nh + 2 * nkv) * D, H, std=H ** -0.5, seed=13)
     b = randn((nh + 2 * nkv) * D, std=0.1, seed=14)

@@ -30,6 +30,7 @@ cudaError_t launch_gemm_legacy(const GemmArgs& a, cudaStream_t st);
 namespace {
 
 constexpr int BM = 128, BK = 64, STAGES = 8;
+constexpr int GEMM_WIDE_MIN_ROWS = 64;        // more rows than this: gemm_wide.cu (MMA N = 256) instead of the weight stream
 constexpr int W_STAGE = BM * BK * 2;           // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;       // 4096
 constexpr int STAGE_BYTES = W_STAGE + X_STAGE; // 20480 (multiple of 1024: every tile stays 1024-byte aligned)
@@ -47,12 +48,15 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 struct Unit {
   int tile, split, tb, kb, ke;
 };
-__device__ __forceinline__ Unit decode_unit(int u, int n_tiles, int splits, int nk) {
+// Unit order: k-split fastest, then the token block, then the weight-row tile.  Units are dealt round-robin, so the CTAs
+// that run at the same time work on the SAME weight tile for different token blocks: with hundreds of rows (prompt
+// passes) a weight tile comes from HBM once and is shared through L2 instead of being re-streamed per token block.
+__device__ __forceinline__ Unit decode_unit(int u, int n_tb, int splits, int nk) {
   Unit r;
   r.split = u % splits;
   int q = u / splits;
-  r.tile = q % n_tiles;
-  r.tb = q / n_tiles;
+  r.tb = q % n_tb;
+  r.tile = q / n_tb;
   r.kb = (int)(((long)nk * r.split) / splits);
   r.ke = (int)(((long)nk * (r.split + 1)) / splits);
   return r;
@@ -75,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = p.K / BK;
   const int splits = p.splits;
+  const int n_tb = (p.T + VS_TOK - 1) / VS_TOK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
@@ -111,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       int pre_u[STAGES], pre_kc[STAGES];
       int n_pre = 0;
       int u = blockIdx.x;
-      Unit un = u < n_units ? decode_unit(u, n_tiles, splits, nk) : Unit{0, 0, 0, 0, 0};
+      Unit un = u < n_units ? decode_unit(u, n_tb, splits, nk) : Unit{0, 0, 0, 0, 0};
       int kc = un.kb;
       while (u < n_units && n_pre < STAGES) {
         mbar_expect_tx(&full[n_pre], STAGE_BYTES);
@@ -122,7 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         if (++kc >= un.ke) {
           u += gridDim.x;
           if (u < n_units) {
-            un = decode_unit(u, n_tiles, splits, nk);
+            un = decode_unit(u, n_tb, splits, nk);
             kc = un.kb;
           }
         }
@@ -144,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         if (++kc >= un.ke) {
           u += gridDim.x;
           if (u < n_units) {
-            un = decode_unit(u, n_tiles, splits, nk);
+            un = decode_unit(u, n_tb, splits, nk);
             kc = un.kb;
           }
         }
@@ -155,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        Unit un = decode_unit(u, n_tiles, splits, nk);
+        Unit un = decode_unit(u, n_tb, splits, nk);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 32;
@@ -181,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     int acc = 0, acc_phase = 0;
     pdl_wait();
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      Unit un = decode_unit(u, n_tiles, splits, nk);
+      Unit un = decode_unit(u, n_tb, splits, nk);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       float v[32];
@@ -357,7 +362,21 @@ bool use_legacy() {
   return v == 1;
 }
 
+bool use_wide() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VS_GEMM_WIDE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace
+
+cudaError_t launch_gemm_wide(const GemmArgs& a, cudaStream_t st);   // gemm_wide.cu
+bool gemm_get_map(const void* ptr, long ld, int rows, int cols, int box_rows, CUtensorMap* out) {
+  return get_map(ptr, ld, rows, cols, box_rows, out);
+}
 
 // Split factor: as many k-splits as keep >= 4 k-chunks per unit, chosen so that the number of work units is as
 // close as possible to (and not above) a whole number of waves of one CTA per SM.
@@ -399,6 +418,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st) {
   if (a.splits > 1 && (!a.partials || !a.counters)) return cudaErrorInvalidValue;
   if (a.splits > a.K / BK) return cudaErrorInvalidValue;
   if (use_legacy()) return launch_gemm_legacy(a, st);
+  if (a.T > GEMM_WIDE_MIN_ROWS && use_wide()) return launch_gemm_wide(a, st);   // prompt passes: 256-token MMA tiles
   switch (a.epi) {
     case EPI_STORE: return launch_t<EPI_STORE>(a, st);
     case EPI_RESID: return launch_t<EPI_RESID>(a, st);
