@@ -362,7 +362,7 @@ def test_prefill_native_matches_library_prefill(rows, monkeypatch):
     eng = model.base_model_engine
     g = torch.Generator(device=DEV).manual_seed(rows)
     emb = (0.5 * torch.randn(1, rows, 4096, generator=g, device=DEV)).to(torch.bfloat16)
-    lg0, hid0 = eng.prefill(emb)
+    lg0, hid0 = eng.prefill_library(emb)
     kv0 = eng.kv[:, :, :, :rows].clone()
     eng.kv.zero_()
     lg1, hid1 = eng.prefill_native(emb)
@@ -378,7 +378,7 @@ def test_prefill_native_matches_library_prefill(rows, monkeypatch):
     _, h2n = eng.prefill_native(emb2, past=rows)
     kv2n = eng.kv[:, :, :, :rows + 9].clone()
     eng.kv[:, :, :, :rows] = kv0
-    _, h2l = eng.prefill(emb2, past=rows)
+    _, h2l = eng.prefill_library(emb2, past=rows)
     torch.testing.assert_close(h2n.float(), h2l.float(), rtol=2 ** -5, atol=0.06)
     torch.testing.assert_close(kv2n[..., rows:, :].float(), eng.kv[:, :, :, rows:rows + 9].float(), rtol=2 ** -5, atol=0.06)
     # a whole generation on the native prompt pass

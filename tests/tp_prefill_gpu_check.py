@@ -28,8 +28,9 @@ def main():
     del tw, dw
     eng = model.base_model_engine
     ids, emb, mask = synth_prompt(tcfg, eng.embed, 12, dev)
-    # single-device prefill
-    lg0, hid0 = eng.prefill(emb)
+    # single-device prompt pass with the same library GEMMs the sharded pass uses (the default is the native pass)
+    os.environ["VS_PREFILL"] = "library"
+    lg0, hid0 = eng.prefill_library(emb)
     kv0 = eng.kv[:, :, :, :emb.shape[1]].clone()
     out0 = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, log=True, max_new_tokens=24)[0]
     # tensor-parallel prefill
@@ -78,11 +79,12 @@ def main():
         return float(t)
     t_tp = timed(lambda: eng.prefill(emb))
     eng._tp = None
-    t_1 = timed(lambda: eng.prefill(emb))
+    t_1 = timed(lambda: eng.prefill_library(emb))
+    t_n = timed(lambda: eng.prefill_native(emb))
     if rank == 0:
         print(f"TP_PREFILL_OK world={world} layers={layers} rows={emb.shape[1]} hidden_exact={exact_h:.4f} kv_exact={exact_kv:.4f} kv_layer0_exact={exact_kv0:.4f} "
               f"max_err={err_h:.4f} tokens_equal_to_single_device={n_same}/{out0.shape[1]} "
-              f"prefill_ms single={t_1:.2f} tp{world}={t_tp:.2f}", flush=True)
+              f"prefill_ms library_single={t_1:.2f} library_tp{world}={t_tp:.2f} native_single={t_n:.2f}", flush=True)
     dist.destroy_process_group()
 
 

@@ -26,5 +26,5 @@ def timed(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
-print(f"rows={emb.shape[1]} layers={layers} cublas_ms={timed(lambda: eng.prefill(emb)):.2f} "
+print(f"rows={emb.shape[1]} layers={layers} cublas_ms={timed(lambda: eng.prefill_library(emb)):.2f} "
       f"native_ms={timed(lambda: eng.prefill_native(emb)):.2f}")

@@ -295,15 +295,21 @@ class TargetEngine:
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         return torch.nn.functional.embedding(ids.to(self.device), self.embed)
 
-    # -- prefill (outside the draft-and-verify path: library GEMMs, reference numerics) ---------------
-    @torch.no_grad()
+    # -- prefill -------------------------------------------------------------------------------------------
     def prefill(self, inputs_embeds: torch.Tensor, past: int = 0, position_ids: Optional[torch.Tensor] = None):
-        """LlamaModel.forward over the prompt (modeling_llama_kv.py:927-1080) with plain torch ops / cuBLAS.
+        """LlamaModel.forward over the prompt (modeling_llama_kv.py:927-1080): writes K/V rows [past, past+L) of the slab,
+        returns (last-row logits fp32 [V], hidden [1,L,H] post-norm).  Runs on the library's own kernels
+        (`prefill_native`) unless the tensor-parallel prompt pass is enabled or VS_PREFILL=library."""
+        if self._tp is None and os.environ.get("VS_PREFILL", "native") != "library":
+            return self.prefill_native(inputs_embeds, past, position_ids)
+        return self.prefill_library(inputs_embeds, past, position_ids)
+
+    @torch.no_grad()
+    def prefill_library(self, inputs_embeds: torch.Tensor, past: int = 0, position_ids: Optional[torch.Tensor] = None):
+        """The prompt pass with plain torch ops / cuBLAS (and, when enabled, sharded tensor-parallel over NCCL).
         Writes K/V rows [past, past+L) of the slab; returns (last-row logits fp32 [V], hidden [1,L,H] post-norm).
         `position_ids`: [L], or [3, L] multimodal positions for a Qwen2.5-VL target (`mrope_section`)."""
         cfg = self.cfg
-        if os.environ.get("VS_PREFILL") == "native" and cfg.mrope_section is None and self._tp is None:
-            return self.prefill_native(inputs_embeds, past)
         x = inputs_embeds.to(device=self.device, dtype=self.dtype)
         if x.dim() == 2:
             x = x[None]
@@ -386,14 +392,12 @@ class TargetEngine:
 
     # -- prefill on the library's own kernels --------------------------------------------------------------------
     @torch.no_grad()
-    def prefill_native(self, inputs_embeds: torch.Tensor, past: int = 0):
-        """The prompt pass through the C ABI (`vs_decoder_layer` per layer over all prompt rows: RMSNorm, tcgen05 q|k|v
-        GEMM with RoPE + in-place KV append, causal attention, o_proj + residual, SwiGLU MLP), then the final norm.  Same
-        results as `prefill` up to fp32 summation order; 1-D RoPE targets (Llama / LLaVA) only.  Selected by
-        VS_PREFILL=native; the default prompt pass uses library GEMMs (cuBLAS), which are faster at hundreds of rows."""
+    def prefill_native(self, inputs_embeds: torch.Tensor, past: int = 0, position_ids: Optional[torch.Tensor] = None):
+        """The prompt pass through the C ABI, the default (`vs_decoder_layer` per layer over all prompt rows: RMSNorm,
+        tcgen05 q|k|v GEMM with 256-token MMA tiles and RoPE + in-place KV append in its epilogue, causal attention,
+        o_proj + residual, SwiGLU MLP), then the final norm.  Same results as the library (cuBLAS / torch) prompt pass
+        `prefill_library` up to fp32 summation order; VS_PREFILL=library selects that one."""
         cfg = self.cfg
-        if cfg.mrope_section is not None:
-            raise NotImplementedError("prefill_native: multimodal RoPE prompts use prefill()")
         x = inputs_embeds.to(device=self.device, dtype=self.dtype)
         x = x[0] if x.dim() == 3 else x
         Lq = x.shape[0]
@@ -406,8 +410,26 @@ class TargetEngine:
                                                          _ceil(S, 64), self.device,
                                                          extra_n=(cfg.heads + 2 * cfg.kv_heads) * 128)
         big.h[:Lq] = x
-        pos = torch.arange(past, S, dtype=torch.int32, device=self.device)
-        rope = L.Rope(L.ptr(self.cos), L.ptr(self.sin))
+        if cfg.mrope_section is not None:
+            # Qwen2.5-VL: rotary factors of row t = channel chunk i from position axis i % 3
+            # (apply_multimodal_rotary_pos_emb, modeling_qwen2_5_vl_kv.py:768-775), gathered once into a per-prompt table
+            # that the q|k|v epilogue indexes by row
+            if position_ids is None:
+                pos3 = torch.arange(past, S, device=self.device)[None].expand(3, Lq)
+            else:
+                pos3 = position_ids.to(self.device).long().reshape(-1, Lq)
+                pos3 = pos3 if pos3.shape[0] == 3 else pos3[:1].expand(3, Lq)
+            sec = list(cfg.mrope_section) * 2
+            cos_t = torch.cat([m[i % 3] for i, m in enumerate(self.cos[pos3].split(sec, dim=-1))], dim=-1).contiguous()
+            sin_t = torch.cat([m[i % 3] for i, m in enumerate(self.sin[pos3].split(sec, dim=-1))], dim=-1).contiguous()
+            pos = torch.arange(0, Lq, dtype=torch.int32, device=self.device)
+            rope = L.Rope(L.ptr(cos_t), L.ptr(sin_t))
+        else:
+            if position_ids is None:
+                pos = torch.arange(past, S, dtype=torch.int32, device=self.device)
+            else:
+                pos = position_ids.to(self.device).reshape(-1, Lq)[0].to(torch.int32).contiguous()
+            rope = L.Rope(L.ptr(self.cos), L.ptr(self.sin))
         st = _stream()
         eager = 0 if cfg.attn_impl == "sdpa" else 1
         for li in range(cfg.layers):
