@@ -54,7 +54,8 @@ const char* vs_last_error(void);
 int vs_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------------
- * Fused linear: Y[T,N] = X[T,K] W[N,K]^T (+bias) with an epilogue.  Replaces nn.Linear + the elementwise
+ * Fused linear: Y[T,N] = X[T,K] W[N,K]^T (+bias) with an epilogue.  Up to 64 rows: weight-streaming kernel (tcgen05 MMA
+ * N = 32, split-K); more rows (prompt passes): tcgen05 MMA N = 256 token tiles, no split-K (`splits` is ignored).  Replaces nn.Linear + the elementwise
  * ops that follow it: cnets_ours.py:363-365 (+RoPE :111-119, +KV append :395-396), :461, :508, :921-922,
  * :982-988, :1111; modeling_llama_kv.py:567-569 (+RoPE :584-587, +KVCache.cat kv_cache.py:52-66), :648, :421, :1196.
  * ------------------------------------------------------------------------------------------------ */
@@ -280,14 +281,18 @@ void vs_program_destroy(vs_program* pg);
 const char* vs_program_last_error(void);
 /* Attention inside a program runs either as two phases (scores | softmax + PV; any kv length) or, with option
  * "attn_fused" = 1, as ONE phase in which every (head, kv split) item is resident and the two passes meet at a per-head
- * arrival counter (K and V read once, scores never leave the SM).  The fused phase holds at most
- * vs_attention_fused_capacity(n_heads, scratch pv_splits, scratch max_chunks) keys (n_ctx + n_new; 1152 for 32 heads on
- * 148 SMs); the kernel traps beyond it -- the caller selects the program by the kv length it is about to run. */
+ * arrival counter (K and V read once).  Up to 2 chunks of 64 keys per split (1152 keys for 32 heads on 148 SMs) the
+ * scores never leave the SM; longer contexts are streamed through a 2-deep shared-memory ring with the scores parked in
+ * the caller's fp32 score scratch (selected inside the kernel from the kv length).  The phase holds at most
+ * vs_attention_fused_capacity(n_heads, scratch pv_splits, scratch max_chunks) keys (n_ctx + n_new) = what the scratch was
+ * sized for (max_chunks * 64; score_ld must cover it); the kernel traps beyond it. */
 int vs_attention_fused_capacity(int n_heads, int pv_splits_cap, int max_chunks);
 /* options: "pf_ahead" (L2 prefetch distance in 16 KB weight chunks per SM, default 0 = off),
  * "trace" (1: record a %globaltimer stamp per phase), "grid" (CTAs; default = SM count; before adding phases),
  * "attn_fused" (see above; before adding phases), "fuse_epilogue" (default 1: an epilogue waits on per-tile arrival
- * counters instead of a grid barrier), "inflight" / "spin_ns" (tuning of the producer warps) */
+ * counters instead of a grid barrier), "fuse_norm" (default 1; before adding phases: an RMSNorm that follows the
+ * residual epilogue which produced its rows runs inside that epilogue -- same bits, one phase fewer),
+ * "inflight" / "spin_ns" (tuning of the producer warps) */
 int vs_program_set_option(vs_program* pg, const char* name, int value);
 int vs_program_num_phases(const vs_program* pg);
 int vs_program_phase_types(const vs_program* pg, int32_t* out, int cap);
