@@ -418,6 +418,15 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
                                                 unsigned int* head_cnt, unsigned int epoch, int tid, Sync sync) {
   const int kvh = head / (p.n_heads / p.n_kv_heads);
   const int warp = tid >> 5, lane = tid & 31;
+  // the two dependent-free global loads of the item (kv length, tree words) go out together, ahead of everything else:
+  // behind the K/V copies of this SM they take ~2 us and the masks sit on the critical path
+  const int tq_rows = min(VS_TOK, p.Tq);
+  unsigned long long qb[4] = {0ull, 0ull, 0ull, 0ull};
+  if (!p.causal && p.bits) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      qb[i] = __ldcg(p.bits + min((i >> 1) * 16 + (lane >> 2) + (i & 1) * 8, tq_rows - 1));
+  }
   const int n_ctx = p.n_ctx ? __ldcg(p.n_ctx) : p.n_ctx_host;
   const int kv_len = n_ctx + p.n_new;
   const int n_chunks = (kv_len + ATT_CHUNK - 1) / ATT_CHUNK;
@@ -425,7 +434,6 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
   if (cps > ATT_FUSED_CPS) __trap();                              // the host selects the two-phase program beyond this
   const int c_lo = min(split * cps, n_chunks), c_hi = min(c_lo + cps, n_chunks);
   const int nck = c_hi - c_lo;                                    // 0, 1 or 2 chunks
-  const int tq_rows = min(VS_TOK, p.Tq);
   const int g = lane >> 2, t4 = lane & 3;
   const int key_lo = c_lo * ATT_CHUNK;
   const bf16* kbase = p.K + (long)kvh * p.kv_head_stride;
@@ -446,11 +454,6 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
   ACLK(12);
   unsigned long long vis[ATT_FUSED_CPS][4];
   {
-    unsigned long long qb[4] = {0ull, 0ull, 0ull, 0ull};
-    if (!p.causal && p.bits) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) qb[i] = __ldcg(p.bits + min((i >> 1) * 16 + g + (i & 1) * 8, tq_rows - 1));
-    }
 #ifdef VS_PROGRAM_CLK
     if (aclk_on) g_clk[14] = (long long)(qb[0] + qb[1] + qb[2] + qb[3]);
 #endif
