@@ -14,28 +14,41 @@ struct Tile {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
+// Every branch walks the 32 token rows of the tile in batches of EPI_UNROLL with all global loads of a batch issued before
+// anything is consumed (clamped indices instead of predicates): the prompt-pass kernel runs this loop 8 times per work
+// unit, and with one dependent load chain per row it was latency-bound (80 us per unit against 17 us of MMAs).
+constexpr int EPI_UNROLL = 8;
+
 template <int EPI, int NT>
 __device__ __forceinline__ void epilogue(const GemmArgs& p, const Tile& tl, const int tid) {
+  static_assert(NT % 128 == 0, "whole groups of one thread per tile row");
+  constexpr int TG = NT / 128;                                    // thread groups; group g takes token rows g, g + TG, ...
+  const int tg = tid >> 7;
+  const int rows = tl.tb_rows;                                    // 1..32 valid token rows
   if (EPI == EPI_STORE || EPI == EPI_RESID) {
-    for (int i = tid; i < VS_TOK * 128; i += NT) {
-      int t = i >> 7, r = i & 127;
-      int n = tl.n0 + r;
-      if (t >= tl.tb_rows || n >= p.N) continue;
-      float v = tl.ct[t * EPI_CT_LD + r];
-      if (p.bias) v += bf2f(p.bias[n]);
-      long row = tl.t0 + t;
+    const int r = tid & 127, n = tl.n0 + r;
+    if (n >= p.N) return;
+    const float bias = p.bias ? bf2f(p.bias[n]) : 0.f;
+    for (int tb = tg; tb < rows; tb += EPI_UNROLL * TG) {
+      float res[EPI_UNROLL];
       if (EPI == EPI_RESID) {
-        float o = rbf(v);                                         // Linear output rounds to bf16 ...
-        v = bf2f(p.R[row * p.ldr + n]) + o;                       // ... then the residual add rounds again
+#pragma unroll
+        for (int j = 0; j < EPI_UNROLL; ++j) res[j] = bf2f(p.R[(long)(tl.t0 + min(tb + j * TG, rows - 1)) * p.ldr + n]);
       }
-      p.Y[row * p.ldy + n] = f2bf(v);
+#pragma unroll
+      for (int j = 0; j < EPI_UNROLL; ++j) {
+        const int t = tb + j * TG;
+        if (t >= rows) break;
+        float v = tl.ct[t * EPI_CT_LD + r] + bias;
+        if (EPI == EPI_RESID) v = res[j] + rbf(v);                // Linear output rounds to bf16, then the add rounds again
+        p.Y[(long)(tl.t0 + t) * p.ldy + n] = f2bf(v);
+      }
     }
   } else if (EPI == EPI_SWIGLU) {
-    // tile rows [0,64) = gate features j0..j0+63, rows [64,128) = the matching up features
+    // tile rows [0,64) = gate features j0..j0+63, rows [64,128) = the matching up features; thread = (feature, row parity)
     const int j0 = tl.tile * 64;
-    for (int i = tid; i < VS_TOK * 64; i += NT) {
-      int t = i >> 6, r = i & 63;
-      if (t >= tl.tb_rows) continue;
+    const int r = tid & 63, half = tid >> 6;
+    for (int t = half; t < rows; t += 2 * TG) {
       float g = rbf(tl.ct[t * EPI_CT_LD + r]);
       float u = rbf(tl.ct[t * EPI_CT_LD + 64 + r]);
       float a = rbf(silu_f(g));                                   // act_fn(gate) rounds, then * up rounds
@@ -47,28 +60,36 @@ __device__ __forceinline__ void epilogue(const GemmArgs& p, const Tile& tl, cons
     const bool is_k = !is_q && tile < p.n_q_tiles + p.n_k_tiles;
     const int head = is_q ? tile : (is_k ? tile - p.n_q_tiles : tile - p.n_q_tiles - p.n_k_tiles);
     const int row_base = (p.kv_row_base ? *p.kv_row_base : 0) + p.kv_row_off;
-    for (int i = tid; i < VS_TOK * 128; i += NT) {
-      int t = i >> 7, d = i & 127;
-      if (t >= tl.tb_rows) continue;
-      int n = tl.n0 + d;
-      float b = p.bias ? bf2f(p.bias[n]) : 0.f;
-      float x = rbf(tl.ct[t * EPI_CT_LD + d] + b);
-      float out = x;
-      if (p.rope && !(!is_q && !is_k)) {
-        int d2 = d < 64 ? d + 64 : d - 64;
-        float b2 = p.bias ? bf2f(p.bias[tl.n0 + d2]) : 0.f;
-        float x2 = rbf(tl.ct[t * EPI_CT_LD + d2] + b2);
-        float rot = d < 64 ? -x2 : x2;
-        long pos = p.pos_ids[tl.t0 + t];
-        float c = bf2f(p.cos[pos * 128 + d]), s = bf2f(p.sin[pos * 128 + d]);
-        out = rbf(x * c) + rbf(rot * s);                          // three bf16 roundings (cnets_ours.py:117-118)
+    const int d = tid & 127, d2 = d < 64 ? d + 64 : d - 64;
+    const float b = p.bias ? bf2f(p.bias[tl.n0 + d]) : 0.f;
+    const float b2 = p.bias ? bf2f(p.bias[tl.n0 + d2]) : 0.f;
+    const bool rope = p.rope && (is_q || is_k);
+    bf16* dst = is_q ? p.Qout + (long)head * p.q_head_stride + (long)tl.t0 * 128 + d
+                     : (is_k ? p.Kout : p.Vout) + (long)head * p.kv_head_stride + (long)(row_base + tl.t0) * 128 + d;
+    for (int tb = tg; tb < rows; tb += EPI_UNROLL * TG) {
+      float c[EPI_UNROLL], s[EPI_UNROLL];
+      if (rope) {
+        long pos[EPI_UNROLL];
+#pragma unroll
+        for (int j = 0; j < EPI_UNROLL; ++j) pos[j] = p.pos_ids[tl.t0 + min(tb + j * TG, rows - 1)];
+#pragma unroll
+        for (int j = 0; j < EPI_UNROLL; ++j) {
+          c[j] = bf2f(p.cos[pos[j] * 128 + d]);
+          s[j] = bf2f(p.sin[pos[j] * 128 + d]);
+        }
       }
-      bf16 o = f2bf(out);
-      if (is_q) {
-        p.Qout[(long)head * p.q_head_stride + (long)(tl.t0 + t) * 128 + d] = o;
-      } else {
-        bf16* dst = is_k ? p.Kout : p.Vout;
-        dst[(long)head * p.kv_head_stride + (long)(row_base + tl.t0 + t) * 128 + d] = o;
+#pragma unroll
+      for (int j = 0; j < EPI_UNROLL; ++j) {
+        const int t = tb + j * TG;
+        if (t >= rows) break;
+        const float x = rbf(tl.ct[t * EPI_CT_LD + d] + b);
+        float out = x;
+        if (rope) {
+          const float x2 = rbf(tl.ct[t * EPI_CT_LD + d2] + b2);
+          const float rot = d < 64 ? -x2 : x2;
+          out = rbf(x * c[j]) + rbf(rot * s[j]);                  // three bf16 roundings (cnets_ours.py:117-118)
+        }
+        dst[(long)t * 128] = f2bf(out);
       }
     }
   }
