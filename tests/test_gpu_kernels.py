@@ -304,7 +304,7 @@ def test_attention_tree(eager, nh, nkv, n_ctx):
     assert (O.float() == ref.float()).float().mean() > 0.9
 
 
-@pytest.mark.parametrize("Tq,n_ctx", [(1, 100), (5, 129), (8, 40), (70, 0), (129, 0)])
+@pytest.mark.parametrize("Tq,n_ctx", [(1, 100), (5, 129), (8, 40), (70, 0), (129, 0), (100, 300), (704, 0), (33, 900)])
 def test_attention_causal(Tq, n_ctx):
     nh = nkv = 4
     rows_q = (Tq + 31) // 32 * 32

@@ -30,7 +30,9 @@ struct BlockSync {
 __global__ void __launch_bounds__(ATT_THREADS) attn_scores_kernel(const AttnArgs p) {
   __shared__ AttnSmem sm;
   const int n_ctx = p.n_ctx ? *p.n_ctx : p.n_ctx_host;
-  const int n_chunks = (n_ctx + p.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
+  int n_chunks = (n_ctx + p.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
+  // causal: keys behind the last row of this query block are invisible to all of it (prompt passes: half of the chunks)
+  if (p.causal) n_chunks = min(n_chunks, (n_ctx + min(p.Tq, ((int)blockIdx.z + 1) * VS_TOK) + ATT_CHUNK - 1) / ATT_CHUNK);
   bool first = true;
   for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
     attn_scores_item(p, sm, blockIdx.x, blockIdx.z, gridDim.z, c, first, threadIdx.x, BlockSync());

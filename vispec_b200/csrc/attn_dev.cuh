@@ -204,9 +204,12 @@ __device__ __forceinline__ void attn_pv_item(const AttnArgs& p, AttnSmem& sm, in
   const int warp = tid >> 5, lane = tid & 31;
   const int n_ctx = p.n_ctx ? __ldcg(p.n_ctx) : p.n_ctx_host;
   const int kv_len = n_ctx + p.n_new;
-  const int n_chunks = (kv_len + ATT_CHUNK - 1) / ATT_CHUNK;
   const int t0 = tqb * VS_TOK;
   const int tq_rows = min(VS_TOK, p.Tq - t0);
+  // causal: the chunks behind the last row of this query block were skipped by pass 1 as well (same bits: their
+  // statistics would be (-inf, 0) and their probabilities zero)
+  const int n_chunks = p.causal ? min((kv_len + ATT_CHUNK - 1) / ATT_CHUNK, (n_ctx + t0 + tq_rows + ATT_CHUNK - 1) / ATT_CHUNK)
+                                : (kv_len + ATT_CHUNK - 1) / ATT_CHUNK;
   const int g = lane >> 2, t4 = lane & 3;
 
   const float* sbase = p.scores + ((long)head * tq_blocks * VS_TOK + t0) * p.score_ld;
