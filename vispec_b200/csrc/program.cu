@@ -5,22 +5,24 @@
 // Why: decode with <= 32 token rows is a pure weight stream (13.2 GB per verify step at 7B).  Separate
 // launches stop the HBM stream at every kernel boundary (ramp-up, TMEM allocation, barrier init, tail) and ncu showed the
 // split-K "last arriver" epilogue turning single CTAs into stragglers (profiles/README.md, r1a).  Here
-//   * warp 0 (one lane) is the WEIGHT producer: it walks every GEMM phase of the program in order and keeps an
-//     8-stage / 128 KB TMA ring full.  Weights never depend on activations, so it runs ahead across phase boundaries:
-//     the HBM stream continues while the rest of the CTA is in an epilogue, an attention phase or a grid barrier;
-//   * warp 3 (one lane) prefetches the weight tiles `pf_ahead` chunks further ahead into L2
-//     (cp.async.bulk.prefetch.tensor), so HBM stays busy even when the smem ring is full;
+//   * warp 0 (one lane) is the WEIGHT producer: it walks every GEMM phase of the program in order and keeps a
+//     6-stage / 96 KB ring full (cp.async.bulk of contiguous 16 KB blocks of the tiled weight copy, or TMA tensor loads of
+//     row-major weights).  Weights never depend on activations, so it runs ahead across phase boundaries: the HBM stream
+//     continues while the rest of the CTA is in an epilogue, an attention phase or a grid barrier.  (Deeper rings and an
+//     L2 prefetcher on warp 3 -- option "pf_ahead", off -- were measured and lost: DESIGN.md section 6);
 //   * warp 2 (one lane) is the ACTIVATION producer: the [32 x 64] token tile of each stage is loaded once the phase
 //     that produces it has completed on every CTA (it polls the grid-barrier counter);
 //   * warp 1 (one lane) issues tcgen05.mma (M=128 weight rows, N=32 tokens, K=16; fp32 accumulators double-buffered in
 //     TMEM) and commits stages back to the producers;
-//   * warps 4-11 (two teams of 128 threads) are the workers: they drain TMEM into fp32 partial tiles, and run every
-//     non-GEMM phase (reduction + fused epilogues, RMSNorm, attention, arg-max, log-softmax/top-k, tree build / accept /
-//     KV splice) on team-sized work items dealt round-robin over all 2 x 148 teams.
+//   * warps 4-19 are the workers (four teams of 128 threads, or two attention teams of 256): they drain TMEM into fp32
+//     partial tiles, and run every non-GEMM phase (reduction + fused epilogues with the following RMSNorm folded in,
+//     attention, arg-max, log-softmax/top-k, tree build / accept / KV splice) on team-sized work items dealt CTA-first
+//     over all teams of the grid.
 // GEMM work is split "stream-K" style: the (tile, k-chunk) sequence of a weight matrix is cut into one contiguous,
 // equally sized range per CTA, so every SM streams the same number of bytes; tiles shared by several CTAs are reduced
-// in k order by the following PH_EPI phase (deterministic; no atomics on data, no last-arriver serialisation).
-// Phases are separated by a grid barrier (one atomic + acquire-spin per CTA).
+// in k order by the following PH_EPI phase, which waits on per-tile arrival counters instead of a grid barrier
+// (deterministic; no atomics on data, no last-arriver serialisation).
+// Other phases are separated by a grid barrier (one release-add + relaxed spin per CTA).
 #include "program.h"
 
 #include <math.h>
