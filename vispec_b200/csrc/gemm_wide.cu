@@ -15,7 +15,9 @@
 //     drained in eight 32-token slices, even slices by group 0 and odd ones by group 1, each through its own
 //     shared-memory tile and the same `epilogue<>` bodies as the decode kernel (bias / residual / SiLU*up / RoPE + KV
 //     append), so both kernels round identically.  (One group alone needs ~40 us per unit against 17 us of MMAs.)
-// No split-K: K is covered by one unit (N = 4096 outputs at 704 rows give 96 units on 148 SMs).
+// No split-K: K is covered by one unit.  The token block width is chosen per launch (a multiple of 16 up to 256) so that
+// the unit count fills the SMs: 704 rows x 32 weight tiles run as 4 blocks of 176 tokens (128 units) rather than 3 blocks
+// of 256 (96 units on 148 SMs).
 #include <cuda.h>
 
 #include "gemm_epilogue.cuh"
@@ -41,25 +43,28 @@ constexpr int THREADS = 128 + EPI_GROUPS * 128;
 constexpr int EPI_THREADS = 128;
 constexpr int TMEM_COLS = 512;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
-constexpr uint32_t IDESC_WIDE = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N = tw (multiple of 16), M=128
+__host__ __device__ constexpr uint32_t idesc_wide(int tw) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)tw >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 __device__ __forceinline__ void epi_bar(int group) { asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory"); }
-__device__ __forceinline__ void tc_mma_wide(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_wide(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(IDESC_WIDE), "r"(accumulate)
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_wide_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmArgs p,
-                 const int n_tb, const int n_units) {
+                 const int n_tb, const int n_units, const int tw) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* ct = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -105,10 +110,10 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         const int tb = u % n_tb, tile = u / n_tb;
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          mbar_expect_tx(&full[stage], W_STAGE + tw * BK * 2);
           uint8_t* dst = smem + stage * STAGE_BYTES;
           tma_load_2d(&tmW, &full[stage], dst, kc * BK, tile * BM, HINT_EVICT_LAST);
-          tma_load_2d(&tmX, &full[stage], dst + W_STAGE, kc * BK, tb * TW, HINT_EVICT_LAST);
+          tma_load_2d(&tmX, &full[stage], dst + W_STAGE, kc * BK, tb * tw, HINT_EVICT_LAST);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -117,6 +122,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t idesc = idesc_wide(tw);
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -127,7 +133,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           const uint64_t da = make_desc(smem + stage * STAGE_BYTES);
           const uint64_t db = make_desc(smem + stage * STAGE_BYTES + W_STAGE);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) tc_mma_wide(d_tmem, da + 2 * k, db + 2 * k, (kc > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) tc_mma_wide(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
           tc_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -147,7 +153,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       const int tb = u % n_tb, tile = u / n_tb;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int rows_left = p.T - tb * TW;      // > 0
+      const int rows_left = min(p.T - tb * tw, tw);   // > 0
 #pragma unroll 1
       for (int sb = group; sb < TW / VS_TOK; sb += EPI_GROUPS) {
         const int t0 = sb * VS_TOK;
@@ -157,7 +163,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
         for (int t = 0; t < 32; ++t) ctg[t * EPI_CT_LD + et] = v[t];
         epi_bar(group);
-        Tile tl{ctg, tile, tile * BM, tb * TW + t0, min(VS_TOK, rows_left - t0)};
+        Tile tl{ctg, tile, tile * BM, tb * tw + t0, min(VS_TOK, rows_left - t0)};
         epilogue<EPI, EPI_THREADS>(p, tl, et);
         epi_bar(group);
       }
@@ -192,15 +198,28 @@ cudaError_t launch_w(const GemmArgs& a, cudaStream_t st) {
     cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_sms <= 0) g_sms = 148;
   }
-  CUtensorMap tmW, tmX;
-  if (!gemm_get_map(a.W, a.ldw, a.N, a.K, BM, &tmW) || !gemm_get_map(a.X, a.ldx, a.T, a.K, TW, &tmX))
-    return cudaErrorInvalidValue;
   const int n_tiles = (a.N + BM - 1) / BM;
-  const int n_tb = (a.T + TW - 1) / TW;
+  // token blocks: the count that minimises waves x (block width + the fixed weight-tile share, measured ~128 token
+  // rows worth); width = multiple of 16
+  int n_tb = (a.T + TW - 1) / TW, tw = TW;
+  {
+    long best = -1;
+    for (int nb = (a.T + TW - 1) / TW; nb <= (a.T + 63) / 64; ++nb) {
+      const int w = (((a.T + nb - 1) / nb) + 15) / 16 * 16;
+      if (w > TW) continue;
+      const long units = (long)n_tiles * nb, waves = (units + g_sms - 1) / g_sms;
+      const long cost = waves * (w + 128);
+      if (best < 0 || cost < best) { best = cost; n_tb = nb; tw = w; }
+    }
+    n_tb = (a.T + tw - 1) / tw;
+  }
+  CUtensorMap tmW, tmX;
+  if (!gemm_get_map(a.W, a.ldw, a.N, a.K, BM, &tmW) || !gemm_get_map(a.X, a.ldx, a.T, a.K, tw, &tmX))
+    return cudaErrorInvalidValue;
   const int n_units = n_tiles * n_tb;
   const int grid = n_units < g_sms ? n_units : g_sms;
   prof_begin(PROF_GEMM, 2.0 * a.N * a.K, st);
-  gemm_wide_kernel<EPI><<<grid, THREADS, SMEM_BYTES, st>>>(tmW, tmX, a, n_tb, n_units);
+  gemm_wide_kernel<EPI><<<grid, THREADS, SMEM_BYTES, st>>>(tmW, tmX, a, n_tb, n_units, tw);
   cudaError_t e = cudaGetLastError();
   prof_end(st);
   count_launch();
