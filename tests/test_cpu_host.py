@@ -141,3 +141,19 @@ def test_replicas_gather_world2_gloo():
     for rank, ids, agg in res:
         assert ids == list(range(7)) and agg["n_prompts"] == 7
     assert res[0][2] == res[1][2]
+
+
+def test_generate_tree_buffers_matches_reference_goldens():
+    """Static-tree buffers (baseline scripts' surface) against vectors produced by the unmodified reference
+    (tests/golden/make_golden_tree_buffers.py)."""
+    import json
+    import torch
+    from vispec_b200.model.utils import generate_tree_buffers
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "tree_buffers.json")))
+    assert len(gold) >= 7
+    for name, g in gold.items():
+        b = generate_tree_buffers(g["tree_choices"], device="cpu")
+        for k in ("tree_attn_mask", "tree_indices", "tree_position_ids", "retrieve_indices"):
+            ref = torch.tensor(g[k])
+            assert b[k].shape == ref.shape and torch.equal(b[k].to(ref.dtype), ref), (name, k)
+        assert b["tree_attn_mask"].dtype == torch.float32 and b["retrieve_indices"].dtype == torch.long

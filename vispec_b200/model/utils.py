@@ -63,6 +63,49 @@ def _temp_bits(logits_processor) -> int:
     return 0 if logits_processor is None else struct.unpack("<i", struct.pack("<f", logits_processor.temperature))[0]
 
 
+TOPK = 10          # sibling slots per group of the static-tree candidate buffer (utils.py:14)
+
+
+def generate_tree_buffers(tree_choices, device="cuda"):
+    """Static draft-tree buffers of the EAGLE-1 / Medusa style decode that the baseline evaluation scripts still build
+    and cache on the model (`gen_baseline_answer_coco_caption.py:48-70`; reference: `utils.py:90-218`).  Host-side integer
+    bookkeeping only -- the dynamic tree of the draft-and-verify path is built on the device (`vs_tree_build`).
+
+    `tree_choices`: list of paths, each a list of child ranks from the root, e.g. [[0], [1], [0, 0]].  Returns tensors on
+    `device`: `tree_attn_mask` [1,1,n,n] (node sees itself, the root and its ancestors), `tree_indices` [n] (slot of each
+    node in the flat candidate buffer: rank + TOPK * sibling-group number + 1), `tree_position_ids` [n] (depth),
+    `retrieve_indices` [leaves, depth+1] (root-to-leaf node indices, -1 padded, rows in ascending order with the padding
+    last); node 0 is the root, nodes follow in (depth, path) order."""
+    order = sorted((tuple(c) for c in tree_choices), key=lambda c: (len(c), c))
+    node = {c: i + 1 for i, c in enumerate(order)}
+    n = len(order) + 1
+    mask = torch.zeros(n, n)
+    mask[:, 0] = 1
+    pos = torch.zeros(n, dtype=torch.long)
+    slot = torch.zeros(n, dtype=torch.long)
+    group, prev = -1, None
+    interior = set()
+    for c in order:
+        i = node[c]
+        mask[i, i] = 1
+        for k in range(1, len(c)):
+            mask[i, node[c[:k]]] = 1
+            interior.add(c[:k])
+        pos[i] = len(c)
+        if (len(c), c[:-1]) != prev:              # a new run of siblings (same depth, same parent)
+            group, prev = group + 1, (len(c), c[:-1])
+        slot[i] = c[-1] + TOPK * group + 1
+    leaves = [c for c in order if c not in interior]
+    width = max((len(c) for c in leaves), default=0) + 1
+    rows = [[0] + [node[c[:k]] for k in range(1, len(c) + 1)] for c in leaves]
+    rows = [r + [-1] * (width - len(r)) for r in rows]
+    big = n + 5
+    rows.sort(key=lambda r: [x if x >= 0 else big for x in r])
+    out = {"tree_attn_mask": mask[None, None], "tree_indices": slot, "tree_position_ids": pos,
+           "retrieve_indices": torch.tensor(rows, dtype=torch.long).reshape(len(rows), width)}
+    return {k: v.clone().to(device) for k, v in out.items()}
+
+
 def reset_tree_mode(model):
     """utils.py:330-339."""
     lm = model.base_model
