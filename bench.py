@@ -545,6 +545,17 @@ def run_ours(args):
                             "tokens, 256-token gen", "value": tok3 / (ms3 * 1e-3), "unit": "tokens/s",
                 "accept_len_mean": sum(acc3) / max(1, len(acc3)), "ms_per_cycle": ms_cycle3,
                 "algorithmic_bytes_per_cycle": by3["total"], "hbm_frac": by3["total"] / (ms_cycle3 * 1e-3) / 1e9 / hbm_peak()[0]}
+        # BASELINE config 3 proper: T = 1.0 (SpecInfer-style acceptance + sampling on the device, Philox uniforms)
+        kw3s = dict(kw3, temperature=1.0)
+        torch.manual_seed(0)
+        for _ in range(2):
+            m3.specgenerate(ids3, inputs_embeds=emb3, image_mask=mask3, **kw3s)
+        tok4, ms4, acc4 = 0, 0.0, []
+        for _ in range(max(1, args.steps // 2)):
+            _, n4, _, a4 = m3.specgenerate(ids3, inputs_embeds=emb3, image_mask=mask3, **kw3s)
+            tok4 += n4; ms4 += m3.last_decode_ms; acc4 += a4
+        qwen["sampling_t1"] = {"temperature": 1.0, "value": tok4 / (ms4 * 1e-3), "unit": "tokens/s",
+                               "accept_len_mean": sum(acc4) / max(1, len(acc4)), "ms_per_cycle": ms4 / max(1, len(acc4))}
         del m3
         torch.cuda.empty_cache()
     # the verify attention on its own at longer contexts (rank 0, N=1, informational): 32 attention phases over distinct
