@@ -413,6 +413,119 @@ __device__ __forceinline__ unsigned int att_ld_relaxed(const unsigned int* p) {
   return v;
 }
 
+// ---- shared tails of the single-phase items (register-resident and streamed) ---------------------------------------
+// Split statistics -> head-wide softmax denominators.  On entry sm.red / sm.red2 hold every warp's (max, sum exp) of its
+// key columns per query row (and a team barrier has passed).  The split's (m, l) goes to p.stats [head][split][32],
+// the per-head arrival counter replaces a grid barrier, then 8 lanes per row combine the splits in fixed order into
+// sm.gM / sm.gL / sm.gR.
+template <class Sync>
+__device__ __forceinline__ void att_exchange_stats(const AttnArgs& p, AttnFusedSmem& sm, int head, int split, int n_splits,
+                                                   unsigned int* head_cnt, unsigned int epoch, int tid, Sync sync) {
+  float* stat_head = p.stats + (long)head * p.max_chunks * VS_TOK * 2;
+  if (tid < VS_TOK) {
+    float m = sm.red[0][tid];
+#pragma unroll
+    for (int w = 1; w < ATT_WARPS; ++w) m = fmaxf(m, sm.red[w][tid]);
+    float l = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATT_WARPS; ++w) {                           // fixed order
+      const float mw = sm.red[w][tid];
+      if (mw != -INFINITY) l += sm.red2[w][tid] * expf(mw - m);
+    }
+    *reinterpret_cast<float2*>(stat_head + ((long)split * VS_TOK + tid) * 2) = make_float2(m, l);
+  }
+  sync();
+  // ---- publish, then wait for the other splits of this head
+  if (tid == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(head_cnt + head) : "memory");
+    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
+    while (att_ld_relaxed(head_cnt + head) < want) {
+    }
+  }
+  sync();
+  // ---- exact global denominators from the split statistics: 8 lanes per row, splits part, part+8 (fixed order)
+  {
+    const int q = tid >> 3, part = tid & 7;
+    float2 st[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      st[j] = __ldcg(reinterpret_cast<const float2*>(stat_head + ((long)min(part + 8 * j, n_splits - 1) * VS_TOK + q) * 2));
+    float m = -INFINITY, l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (part + 8 * j < n_splits && st[j].x != -INFINITY) {
+        const float mn = fmaxf(m, st[j].x);
+        l = l * expf(m - mn) + st[j].y * expf(st[j].x - mn);
+        m = mn;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
+      const float mn = fmaxf(m, mo);
+      const float a = m == -INFINITY ? 0.f : l * expf(m - mn);
+      const float b = mo == -INFINITY ? 0.f : lo * expf(mo - mn);
+      l = a + b;
+      m = mn;
+    }
+    if (part == 0) { sm.gM[q] = m; sm.gL[q] = l; sm.gR[q] = 1.0f / l; }
+  }
+  sync();
+}
+
+// Partial O [32][128] fp32 of this split -> p.opart, second per-head arrival counter, then every split reduces its
+// share of the head's output in split order (float4 group i belongs to split i % n_splits) over the n_act splits that
+// own keys.
+template <class Sync>
+__device__ __forceinline__ void att_exchange_output(const AttnArgs& p, AttnFusedSmem& sm, const float (&oacc)[2][2][4],
+                                                    int head, int split, int n_splits, int n_act, int tq_rows,
+                                                    unsigned int* head_cnt, unsigned int epoch, int tid, Sync sync) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  float* obase = p.opart + ((long)head * n_splits) * VS_TOK * 128;
+  float* mine = obase + (long)split * VS_TOK * 128;
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int eh = 0; eh < 2; ++eh) {
+        const int q = mb * 16 + g + eh * 8;
+        const int d = warp * 16 + nb * 8 + 2 * t4;
+        *reinterpret_cast<float2*>(mine + q * 128 + d) = make_float2(oacc[mb][nb][eh * 2], oacc[mb][nb][eh * 2 + 1]);
+      }
+  sync();
+  if (tid == 0) {
+    unsigned int* cnt2 = head_cnt + p.n_heads + head;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt2) : "memory");
+    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
+    while (att_ld_relaxed(cnt2) < want) {
+    }
+  }
+  sync();
+  for (int i = split + tid * n_splits; i < VS_TOK * 32; i += ATT_THREADS * n_splits) {
+    const int q = i >> 5, d4 = (i & 31) * 4;
+    if (q >= tq_rows) continue;
+    const float* src = obase + q * 128 + d4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int s0 = 0; s0 < n_act; s0 += 8) {                         // 8 splits per round trip
+      float4 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        t[j] = __ldcg(reinterpret_cast<const float4*>(src + (long)min(s0 + j, n_act - 1) * VS_TOK * 128));
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (s0 + j < n_act) { v.x += t[j].x; v.y += t[j].y; v.z += t[j].z; v.w += t[j].w; }
+    }
+    if (!p.eager) {
+      const float l = sm.gL[q];
+      v.x /= l; v.y /= l; v.z /= l; v.w /= l;
+    }
+    bf16 o4[4] = {f2bf(v.x), f2bf(v.y), f2bf(v.z), f2bf(v.w)};
+    *reinterpret_cast<uint2*>(p.O + (long)q * p.ldo + head * 128 + d4) = *reinterpret_cast<const uint2*>(o4);
+  }
+}
+
 // head_cnt: 2 * n_heads arrival counters (statistics published | partial O published), monotonic across launches
 // (epoch = launches completed before this one).
 // stats layout (p.stats): [head][split][32 rows] float2 (max, sum exp).
@@ -554,58 +667,8 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
       att_load_rows_async(sm.kv[j], vbase, key_lo + j * ATT_CHUNK, min(ATT_CHUNK, kv_len - key_lo - j * ATT_CHUNK),
                           ATT_CHUNK, tid);
   cp_async_commit();
-  float* stat_head = p.stats + (long)head * p.max_chunks * VS_TOK * 2;
-  if (tid < VS_TOK) {
-    float m = sm.red[0][tid];
-#pragma unroll
-    for (int w = 1; w < ATT_WARPS; ++w) m = fmaxf(m, sm.red[w][tid]);
-    float l = 0.f;
-#pragma unroll
-    for (int w = 0; w < ATT_WARPS; ++w) {                           // fixed order
-      const float mw = sm.red[w][tid];
-      if (mw != -INFINITY) l += sm.red2[w][tid] * expf(mw - m);
-    }
-    *reinterpret_cast<float2*>(stat_head + ((long)split * VS_TOK + tid) * 2) = make_float2(m, l);
-  }
-  sync();
   ACLK(4);
-  // ---- publish, then wait for the other splits of this head
-  if (tid == 0) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(head_cnt + head) : "memory");
-    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
-    while (att_ld_relaxed(head_cnt + head) < want) {
-    }
-  }
-  sync();
-  ACLK(5);
-  // ---- exact global denominators from the split statistics: 8 lanes per row, splits part, part+8 (fixed order)
-  {
-    const int q = tid >> 3, part = tid & 7;
-    float2 st[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      st[j] = __ldcg(reinterpret_cast<const float2*>(stat_head + ((long)min(part + 8 * j, n_splits - 1) * VS_TOK + q) * 2));
-    float m = -INFINITY, l = 0.f;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (part + 8 * j < n_splits && st[j].x != -INFINITY) {
-        const float mn = fmaxf(m, st[j].x);
-        l = l * expf(m - mn) + st[j].y * expf(st[j].x - mn);
-        m = mn;
-      }
-    }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
-      const float mn = fmaxf(m, mo);
-      const float a = m == -INFINITY ? 0.f : l * expf(m - mn);
-      const float b = mo == -INFINITY ? 0.f : lo * expf(mo - mn);
-      l = a + b;
-      m = mn;
-    }
-    if (part == 0) { sm.gM[q] = m; sm.gL[q] = l; sm.gR[q] = 1.0f / l; }
-  }
-  sync();
+  att_exchange_stats(p, sm, head, split, n_splits, head_cnt, epoch, tid, sync);
   ACLK(6);
   // ---- P in the reference's rounding, written over the Q tile: row q, key column 64*j + 8*warp + 2*t4 (+1)
 #pragma unroll
@@ -668,53 +731,9 @@ __device__ __forceinline__ void attn_fused_item(const AttnArgs& p, AttnFusedSmem
       }
     }
   ACLK(9);
-  // ---- publish the partial O tile, wait for the head's other splits (second arrival counter), then every split
-  // reduces its share of the head's output in split order (float4 group i belongs to split i % n_splits)
-  float* obase = p.opart + ((long)head * n_splits) * VS_TOK * 128;
-  float* mine = obase + (long)split * VS_TOK * 128;
-#pragma unroll
-  for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-    for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-      for (int eh = 0; eh < 2; ++eh) {
-        const int q = mb * 16 + g + eh * 8;
-        const int d = warp * 16 + nb * 8 + 2 * t4;
-        *reinterpret_cast<float2*>(mine + q * 128 + d) = make_float2(oacc[mb][nb][eh * 2], oacc[mb][nb][eh * 2 + 1]);
-      }
-  sync();
-  if (tid == 0) {
-    unsigned int* cnt2 = head_cnt + p.n_heads + head;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt2) : "memory");
-    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
-    while (att_ld_relaxed(cnt2) < want) {
-    }
-  }
-  sync();
-  ACLK(10);
-  const int n_act = max(1, (n_chunks + cps - 1) / cps);             // splits that own keys (the others hold zeros)
-  for (int i = split + tid * n_splits; i < VS_TOK * 32; i += ATT_THREADS * n_splits) {
-    const int q = i >> 5, d4 = (i & 31) * 4;
-    if (q >= tq_rows) continue;
-    const float* src = obase + q * 128 + d4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-    for (int s0 = 0; s0 < n_act; s0 += 8) {                         // 8 splits per round trip
-      float4 t[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        t[j] = __ldcg(reinterpret_cast<const float4*>(src + (long)min(s0 + j, n_act - 1) * VS_TOK * 128));
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (s0 + j < n_act) { v.x += t[j].x; v.y += t[j].y; v.z += t[j].z; v.w += t[j].w; }
-    }
-    if (!p.eager) {
-      const float l = sm.gL[q];
-      v.x /= l; v.y /= l; v.z /= l; v.w /= l;
-    }
-    bf16 o4[4] = {f2bf(v.x), f2bf(v.y), f2bf(v.z), f2bf(v.w)};
-    *reinterpret_cast<uint2*>(p.O + (long)q * p.ldo + head * 128 + d4) = *reinterpret_cast<const uint2*>(o4);
-  }
+  // ---- partial O exchange and distributed reduction over the splits that own keys
+  att_exchange_output(p, sm, oacc, head, split, n_splits, max(1, (n_chunks + cps - 1) / cps), tq_rows, head_cnt, epoch, tid,
+                      sync);
   ACLK(11);
 }
 
@@ -877,54 +896,7 @@ __device__ __forceinline__ void attn_stream_item(const AttnArgs& p, AttnFusedSme
     }
   }
   sync();
-  float* stat_head = p.stats + (long)head * p.max_chunks * VS_TOK * 2;
-  if (tid < VS_TOK) {
-    float m = sm.red[0][tid];
-#pragma unroll
-    for (int w = 1; w < ATT_WARPS; ++w) m = fmaxf(m, sm.red[w][tid]);
-    float l = 0.f;
-#pragma unroll
-    for (int w = 0; w < ATT_WARPS; ++w) {                           // fixed order
-      const float mw = sm.red[w][tid];
-      if (mw != -INFINITY) l += sm.red2[w][tid] * expf(mw - m);
-    }
-    *reinterpret_cast<float2*>(stat_head + ((long)split * VS_TOK + tid) * 2) = make_float2(m, l);
-  }
-  sync();
-  if (tid == 0) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(head_cnt + head) : "memory");
-    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
-    while (att_ld_relaxed(head_cnt + head) < want) {
-    }
-  }
-  sync();
-  {
-    const int q = tid >> 3, part = tid & 7;
-    float2 st[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      st[j] = __ldcg(reinterpret_cast<const float2*>(stat_head + ((long)min(part + 8 * j, n_splits - 1) * VS_TOK + q) * 2));
-    float m = -INFINITY, l = 0.f;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (part + 8 * j < n_splits && st[j].x != -INFINITY) {
-        const float mn = fmaxf(m, st[j].x);
-        l = l * expf(m - mn) + st[j].y * expf(st[j].x - mn);
-        m = mn;
-      }
-    }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
-      const float mn = fmaxf(m, mo);
-      const float a = m == -INFINITY ? 0.f : l * expf(m - mn);
-      const float b = mo == -INFINITY ? 0.f : lo * expf(mo - mn);
-      l = a + b;
-      m = mn;
-    }
-    if (part == 0) { sm.gM[q] = m; sm.gL[q] = l; sm.gR[q] = 1.0f / l; }
-  }
-  sync();
+  att_exchange_stats(p, sm, head, split, n_splits, head_cnt, epoch, tid, sync);
 
   // ---- pass 2: O += P V
   float oacc[2][2][4];
@@ -991,51 +963,9 @@ __device__ __forceinline__ void attn_stream_item(const AttnArgs& p, AttnFusedSme
   }
   cp_async_wait<0>();
 
-  // ---- partial O exchange and distributed reduction (as in attn_fused_item)
-  float* obase = p.opart + ((long)head * n_splits) * VS_TOK * 128;
-  float* mine = obase + (long)split * VS_TOK * 128;
-#pragma unroll
-  for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-    for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-      for (int eh = 0; eh < 2; ++eh) {
-        const int q = mb * 16 + g + eh * 8;
-        const int d = warp * 16 + nb * 8 + 2 * t4;
-        *reinterpret_cast<float2*>(mine + q * 128 + d) = make_float2(oacc[mb][nb][eh * 2], oacc[mb][nb][eh * 2 + 1]);
-      }
-  sync();
-  if (tid == 0) {
-    unsigned int* cnt2 = head_cnt + p.n_heads + head;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt2) : "memory");
-    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
-    while (att_ld_relaxed(cnt2) < want) {
-    }
-  }
-  sync();
-  const int n_act = max(1, (n_chunks + cps - 1) / cps);             // splits that own keys (the others hold zeros)
-  for (int i = split + tid * n_splits; i < VS_TOK * 32; i += ATT_THREADS * n_splits) {
-    const int q = i >> 5, d4 = (i & 31) * 4;
-    if (q >= tq_rows) continue;
-    const float* src = obase + q * 128 + d4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-    for (int s0 = 0; s0 < n_act; s0 += 8) {
-      float4 t[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        t[j] = __ldcg(reinterpret_cast<const float4*>(src + (long)min(s0 + j, n_act - 1) * VS_TOK * 128));
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (s0 + j < n_act) { v.x += t[j].x; v.y += t[j].y; v.z += t[j].z; v.w += t[j].w; }
-    }
-    if (!p.eager) {
-      const float l = sm.gL[q];
-      v.x /= l; v.y /= l; v.z /= l; v.w /= l;
-    }
-    bf16 o4[4] = {f2bf(v.x), f2bf(v.y), f2bf(v.z), f2bf(v.w)};
-    *reinterpret_cast<uint2*>(p.O + (long)q * p.ldo + head * 128 + d4) = *reinterpret_cast<const uint2*>(o4);
-  }
+  // ---- partial O exchange and distributed reduction over the splits that own keys
+  att_exchange_output(p, sm, oacc, head, split, n_splits, max(1, (n_chunks + cps - 1) / cps), tq_rows, head_cnt, epoch, tid,
+                      sync);
 }
 #undef SROW
 
