@@ -90,19 +90,23 @@ __device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_tea
     attn_pv_item(a, sm, item / a.pv_splits, 0, 1, item % a.pv_splits, a.pv_splits, tt, tsync);
 }
 __device__ __noinline__ void attn_stream_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
-                                               BigTeamSync tsync) {
-  const AttnArgs a = ph.attn;
+                                               BigTeamSync tsync, int n_ctx) {
+  AttnArgs a = ph.attn;
+  a.n_ctx = nullptr;                         // the kv length was read once by the dispatcher
+  a.n_ctx_host = n_ctx;
   attn_stream_item(a, *reinterpret_cast<AttnFusedSmem*>(tsm), gteam / a.pv_splits, gteam % a.pv_splits, a.pv_splits,
                    ph.tile_cnt, epoch, tt, tsync);
 }
 __device__ __noinline__ void attn_fused_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
                                               BigTeamSync tsync) {
-  const AttnArgs a = ph.attn;
+  AttnArgs a = ph.attn;
   if (gteam >= a.n_heads * a.pv_splits) return;   // one resident item per team: the items of a head wait for each other
   // up to ATT_FUSED_CPS chunks per split the scores stay in registers; longer contexts stream (same for every item)
   const int n_ctx = a.n_ctx ? ld_vol(a.n_ctx) : a.n_ctx_host;
   const int n_chunks = (n_ctx + a.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
-  if (n_chunks > ATT_FUSED_CPS * a.pv_splits) { attn_stream_phase(ph, epoch, gteam, tt, tsm, tsync); return; }
+  if (n_chunks > ATT_FUSED_CPS * a.pv_splits) { attn_stream_phase(ph, epoch, gteam, tt, tsm, tsync, n_ctx); return; }
+  a.n_ctx = nullptr;                         // one L2 round trip for the kv length, not two
+  a.n_ctx_host = n_ctx;
   attn_fused_item(a, *reinterpret_cast<AttnFusedSmem*>(tsm), gteam / a.pv_splits, gteam % a.pv_splits, a.pv_splits,
                   ph.tile_cnt, epoch, tt, tsync);
 }
