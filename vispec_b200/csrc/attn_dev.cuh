@@ -773,6 +773,28 @@ __device__ __forceinline__ void attn_stream_item(const AttnArgs& p, AttnFusedSme
   float* const srow0 = p.scores + ((long)head * VS_TOK + g) * p.score_ld + key_lo + kofs;
   const int srow_st = 8 * (int)p.score_ld;
 #define SROW(i) (srow0 + (i) * srow_st)
+  // eager mode: the scores are bf16 values already (rounded twice by the reference's arithmetic), so they are parked as
+  // bf16 pairs -- half the L2 traffic of the round trip; element (row, key) sits at the same index of the scratch read as
+  // a bf16 array.  SDPA mode keeps fp32.
+  const bool half_scores = p.eager != 0;
+  auto put_scores = [&](int i, int j, float s0, float s1) {
+    float* at = SROW(i) + j * ATT_CHUNK;
+    if (half_scores) {
+      const long idx = at - p.scores;                              // even
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(p.scores) + idx) = __floats2bfloat162_rn(s0, s1);
+    } else {
+      *reinterpret_cast<float2*>(at) = make_float2(s0, s1);
+    }
+  };
+  auto get_scores = [&](int i, int j) -> float2 {
+    const float* at = SROW(i) + j * ATT_CHUNK;
+    if (half_scores) {
+      const long idx = at - p.scores;
+      const unsigned int u = __ldcg(reinterpret_cast<const unsigned int*>(reinterpret_cast<const bf16*>(p.scores) + idx));
+      return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+    }
+    return __ldcg(reinterpret_cast<const float2*>(at));
+  };
 
   // a 64-row chunk = 1024 16-byte pieces, 4 per thread: rows r0 + 16k, same 16-byte column; offsets computed once
   const int r0 = tid >> 4, ch0 = tid & 15;
@@ -833,7 +855,7 @@ __device__ __forceinline__ void attn_stream_item(const AttnArgs& p, AttnFusedSme
           float s0 = c[mb][eh * 2], s1 = c[mb][eh * 2 + 1];
           s0 = p.eager ? rbf(att_div(rbf(s0), inv_div, r_div)) : s0 * p.scale;
           s1 = p.eager ? rbf(att_div(rbf(s1), inv_div, r_div)) : s1 * p.scale;
-          *reinterpret_cast<float2*>(SROW(qi) + j * ATT_CHUNK) = make_float2(s0, s1);
+          put_scores(qi, j, s0, s1);
           const float mx = fmaxf(s0, s1);
           if (mx > rm[qi]) {                                       // rm == -inf: rl == 0 and exp(-inf) == 0
             rl[qi] *= __expf(rm[qi] - mx);
@@ -855,7 +877,7 @@ __device__ __forceinline__ void attn_stream_item(const AttnArgs& p, AttnFusedSme
           s1 = p.eager ? rbf(att_div(rbf(s1), inv_div, r_div)) : s1 * p.scale;
           if (!((vis >> kofs) & 1ull)) s0 = -INFINITY;
           if (!((vis >> (kofs + 1)) & 1ull)) s1 = -INFINITY;
-          *reinterpret_cast<float2*>(SROW(qi) + j * ATT_CHUNK) = make_float2(s0, s1);
+          put_scores(qi, j, s0, s1);
           const float mn = fmaxf(rm[qi], fmaxf(s0, s1));
           if (mn != -INFINITY) {
             float l = rl[qi] * __expf(rm[qi] - mn);
@@ -876,7 +898,7 @@ __device__ __forceinline__ void attn_stream_item(const AttnArgs& p, AttnFusedSme
   cp_async_commit();
   float2 snext[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) snext[i] = nck > 0 ? __ldcg(reinterpret_cast<const float2*>(SROW(i))) : make_float2(-INFINITY, -INFINITY);
+  for (int i = 0; i < 4; ++i) snext[i] = nck > 0 ? get_scores(i, 0) : make_float2(-INFINITY, -INFINITY);
 
   // ---- split statistics: lanes of a row quad, then the warps in fixed order
 #pragma unroll
@@ -915,7 +937,7 @@ __device__ __forceinline__ void attn_stream_item(const AttnArgs& p, AttnFusedSme
     for (int i = 0; i < 4; ++i) cur[i] = snext[i];
     if (j + 1 < nck) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) snext[i] = __ldcg(reinterpret_cast<const float2*>(SROW(i) + (j + 1) * ATT_CHUNK));
+      for (int i = 0; i < 4; ++i) snext[i] = get_scores(i, j + 1);
     }
     // P in the reference's rounding into half jj of the Q/P tile: row q, key column 64*jj + kofs (+1)
 #pragma unroll
