@@ -46,7 +46,7 @@ def _pack_layers(cfg, w):
     return out
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, variant="llama"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -56,6 +56,9 @@ def _worker(rank, world, port, q):
     from oracle import vispec_oracle as vo
     from vispec_b200 import tp_prefill
     cfg = synth.TINY_T
+    if variant == "qwen":      # GQA (8 q heads on 4 kv heads), q/k/v biases, SDPA attention semantics; 1-D positions
+        cfg = vo.TargetCfg(hidden=1024, inter=640, layers=2, heads=8, kv_heads=4, vocab=1000, max_pos=512, qkv_bias=True,
+                           attn_impl="sdpa", rope_theta=1e6)
     w = synth.make_target_weights(cfg, 11)
     ids, emb, mask = synth.make_prompt(cfg, w, 5, 4, 24, 9)
     ref = vo.TargetOracle(cfg, w)
@@ -65,7 +68,7 @@ def _worker(rank, world, port, q):
     pos = torch.arange(Lq)
     cos, sin = ref.cos[pos][None, None], ref.sin[pos][None, None]
     h = tp_prefill.prefill_layers(emb[0], _pack_layers(cfg, w), kv, heads=cfg.heads, kv_heads=cfg.kv_heads, inter=cfg.inter,
-                                  eps=cfg.eps, cos=cos, sin=sin, past=0, sdpa=False, rank=rank, world=world)
+                                  eps=cfg.eps, cos=cos, sin=sin, past=0, sdpa=cfg.attn_impl == "sdpa", rank=rank, world=world)
     hidden = tp_prefill._rms(h, w["model.norm.weight"], cfg.eps)
     # second segment appended behind the first (past > 0): the mask and the KV rows of the other ranks must be in place
     emb2 = emb[:, :7] * 0.5
@@ -73,7 +76,7 @@ def _worker(rank, world, port, q):
     pos2 = torch.arange(Lq, Lq + 7)
     h2 = tp_prefill.prefill_layers(emb2[0], _pack_layers(cfg, w), kv, heads=cfg.heads, kv_heads=cfg.kv_heads,
                                    inter=cfg.inter, eps=cfg.eps, cos=ref.cos[pos2][None, None], sin=ref.sin[pos2][None, None],
-                                   past=Lq, sdpa=False, rank=rank, world=world)
+                                   past=Lq, sdpa=cfg.attn_impl == "sdpa", rank=rank, world=world)
     hidden2 = tp_prefill._rms(h2, w["model.norm.weight"], cfg.eps)
     gathered = [torch.empty_like(hidden) for _ in range(world)]
     dist.all_gather(gathered, hidden.contiguous())
@@ -89,16 +92,13 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_tp_prefill_matches_oracle_gloo(world):
+@pytest.mark.parametrize("world,variant", [(2, "llama"), (2, "qwen"), (4, "qwen")])
+def test_tp_prefill_matches_oracle_gloo(world, variant):
     import torch.multiprocessing as mp
-    from oracle import synth
-    if synth.TINY_T.kv_heads % world or synth.TINY_T.heads % world:
-        pytest.skip("tiny config not divisible")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 23500 + (os.getpid() * 7 + world) % 3000
-    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 23500 + (os.getpid() * 7 + world * 13 + len(variant)) % 3000
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q, variant)) for r in range(world)]
     [p.start() for p in ps]
     res = [q.get(timeout=240) for _ in ps]
     [p.join(timeout=60) for p in ps]
