@@ -492,7 +492,36 @@ def evaluate_posterior_greedy(logits, candidates):
     return best, accept_length, logits[best, accept_length]
 
 
-def evaluate_posterior_sampling(logits, candidates, temperature: float, uni):
+def warp_logits(logits, temperature: float, top_p: float = 0.0, top_k: int = 0):
+    """The logits processors `prepare_logits_processor` assembles for T > 0 (utils.py:39-55), applied in its order:
+    temperature (only when != 1), nucleus filter for 1e-8 <= top_p < 1, top-k filter for top_k > 0.  The warpers are
+    third-party code (transformers.generation.logits_process, pinned 4.49.0 in requirements.txt:219; 5.5 installed here),
+    restated from their published algorithms:
+      * TemperatureLogitsWarper: logits / temperature;
+      * TopPLogitsWarper: sort ascending, softmax, running sum; drop every token whose running sum is <= 1 - top_p, but
+        never the most probable one (min_tokens_to_keep = 1);
+      * TopKLogitsWarper: drop every token whose logit is below the k-th largest.
+    Dropped tokens get -inf.  `logits` [rows, V] fp32; returns a new tensor.  (The repetition penalty sits between the
+    temperature and the nucleus filter in the reference; no evaluation script sets it and it is not restated.)
+    Pinned against the reference's own processor list in tests/test_oracle_golden.py (tests/golden/warpers_sampling.pt)."""
+    x = logits.clone()
+    if temperature > 1e-5 and temperature != 1.0:
+        x = x / temperature
+    if 1e-8 <= top_p < 1.0:
+        asc, idx = torch.sort(x, dim=-1)                       # ascending
+        running = torch.cumsum(torch.softmax(asc, dim=-1), dim=-1)
+        drop_sorted = running <= (1.0 - top_p)
+        drop_sorted[..., -1] = False
+        drop = torch.zeros_like(drop_sorted).scatter(-1, idx, drop_sorted)
+        x = x.masked_fill(drop, float("-inf"))
+    if top_k > 0:
+        k = min(int(top_k), x.shape[-1])
+        kth = torch.topk(x, k, dim=-1).values[..., -1:]
+        x = x.masked_fill(x < kth, float("-inf"))
+    return x
+
+
+def evaluate_posterior_sampling(logits, candidates, temperature: float, uni, top_p: float = 0.0, top_k: int = 0):
     """utils.py:453-493 (T > 0): SpecInfer-style acceptance along the tree with residual renormalisation.
 
     logits [n_leaves, depth, V] fp32 (tree logits gathered along every root->leaf path, utils.py:411);
@@ -500,7 +529,11 @@ def evaluate_posterior_sampling(logits, candidates, temperature: float, uni):
     torch.rand_like (:456) -- passed in so that the decisions can be reproduced.  The logits processor is the
     TemperatureLogitsWarper of prepare_logits_processor (:39-55): logits / temperature.
     Returns (best_candidate, accept_length, sample_p [V]) like the reference (accept_length already minus one)."""
-    logits_p = torch.softmax(logits / temperature, dim=-1)
+    if top_p or top_k:                                 # the processor list works on [rows, V] (utils.py:454)
+        V = logits.shape[-1]
+        logits_p = torch.softmax(warp_logits(logits.reshape(-1, V), temperature, top_p, top_k), dim=-1).view_as(logits)
+    else:
+        logits_p = torch.softmax(logits / temperature, dim=-1)
     accept_length = 1
     accept_cand = candidates[0].clone()
     best_candidate = 0

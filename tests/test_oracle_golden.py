@@ -110,3 +110,18 @@ def test_qwen_target_oracle_matches_reference_golden():
     t.cur_len = L
     _, hid3 = t.forward(input_ids=g["tree_ids"][:, :1], position_ids=torch.tensor([L + g["rope_delta"]]))
     assert torch.equal(hid3, g["one_hidden"])
+
+
+def test_warp_logits_matches_reference_processor_list():
+    """oracle.warp_logits (temperature, nucleus, top-k) against the reference's prepare_logits_processor output on seeded
+    logits incl. a run of exact ties (tests/golden/make_golden_warpers.py).  The same fixture records that the reference's
+    nucleus filter raises on the 3-D tree logits of evaluate_posterior, which is why only the temperature warper is on the
+    product path."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warpers_sampling.pt"), weights_only=False)
+    assert len(g["cases"]) >= 7
+    for c in g["cases"]:
+        kw = c["kw"]
+        got = vo.warp_logits(g["x"], kw["temperature"], kw.get("top_p", 0.0), kw.get("top_k", 0))
+        assert torch.equal(got, c["out"]), kw
+    assert g["observations"]["top_k_3d"] == "ok" and g["observations"]["top_p_3d"].startswith("RuntimeError")
