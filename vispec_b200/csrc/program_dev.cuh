@@ -89,8 +89,16 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
 #define CLK(i)
 #endif
 
-constexpr int EPI_TPI = 8;     // tokens per item
-constexpr int EPI_TPT = 4;     // tokens per thread
+// Tokens per thread of an epilogue item (item = 2 * EPI_TPT token rows).  4 -> groups of 8 rows: 30 tree tokens are 4
+// groups, and the gate|up epilogue of a 7B layer has 172 x 4 = 688 items for 592 teams (two rounds on 96 teams).
+// -DVS_EPI_TPT=5 -> groups of 10 rows, 3 groups, 516 items, one round (untested alternative for the next A/B; the default
+// build is bit-for-bit the validated one).
+#ifndef VS_EPI_TPT
+#define VS_EPI_TPT 4
+#endif
+constexpr int EPI_TPT = VS_EPI_TPT;     // tokens per thread
+constexpr int EPI_TPI = 2 * EPI_TPT;    // tokens per item
+static_assert(EPI_TPT >= 4 && EPI_TPT <= 8 && (VS_TOK + EPI_TPI - 1) / EPI_TPI <= 4, "1..4 token groups per tile");
 constexpr int EPI_BATCH = 4;   // contributors whose partial tiles are loaded together (32 loads in flight per thread)
 
 // q = k / d for k * d < 2^32, with magic = floor(2^32 / d) + 1 precomputed on the host (d == 1: magic == 0 -> q = k)
@@ -175,11 +183,20 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
 #pragma unroll
       for (int c = 0; c < EPI_BATCH; ++c) {
         const int ci = min(c0 + c, n_c - 1);                                   // clamped: always a valid tile
+#if VS_EPI_TPT == 4
         const float* base = partials + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS + ts * PG_BM + col;
 #pragma unroll
         for (int i = 0; i < EPI_TPT; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + i * PG_BM + 64 * j);   // rows >= T hold stale finite data
+#else
+        // the last group may reach past the 32 rows of a partial tile: clamp the row
+        const float* base = partials + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS + col;
+#pragma unroll
+        for (int i = 0; i < EPI_TPT; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + min(ts + i, VS_TOK - 1) * PG_BM + 64 * j);
+#endif
       }
 #pragma unroll
       for (int c = 0; c < EPI_BATCH; ++c) {
@@ -265,7 +282,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       if (ssq) {
         sync();
         if (tt < EPI_TPI) {                                            // token tt of the group: warps 2*h, 2*h+1 hold its half
-          const int h = tt >> 2, i = tt & 3;
+          const int h = tt / EPI_TPT, i = tt % EPI_TPT;
           const int t = grp * EPI_TPI + tt;
           if (t < T) ssq[tile * VS_TOK + t] = red[(2 * h) * EPI_TPT + i] + red[(2 * h + 1) * EPI_TPT + i];
         }
@@ -284,13 +301,14 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
         sync();
         const int n_tiles = ph.n_tiles;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {                                  // warp w: tokens 2w, 2w+1 of the group
-          const int t = grp * EPI_TPI + 2 * warp + q;
+        for (int q = 0; q < (EPI_TPI + 3) / 4; ++q) {                  // warp w: tokens 2w, 2w+1 of the group (3w.. for 10)
+          const int tg = warp * ((EPI_TPI + 3) / 4) + q;
+          const int t = grp * EPI_TPI + tg;
           float ss = 0.f;
-          if (t < T)
+          if (tg < EPI_TPI && t < T)
             for (int i = lane; i < n_tiles; i += 32) ss += __ldcg(ssq + i * VS_TOK + t);
           ss = warp_sum(ss);
-          if (lane == 0) red[32 + 2 * warp + q] = 1.0f / sqrtf(ss / (float)ph.H + ph.eps);
+          if (lane == 0 && tg < EPI_TPI) red[32 + tg] = 1.0f / sqrtf(ss / (float)ph.H + ph.eps);
         }
         sync();
         bf16* X = ph.dst;
