@@ -18,7 +18,9 @@ checkpoints offline).  One "step" = one generation of 256 tokens.
                  attention phases inside the kernel (per-phase %globaltimer trace of the same kernel).
   cpu_baseline : the oracle (CPU restatement of the reference) timed on this box's host cores on a bounded sample.
 
-`--impl reference` times the reference algorithm's CPU implementation (oracle port) on the host cores.
+`--impl reference` times the reference's CPU implementation on the host cores (the unmodified vispec.model modules
+vendored under baseline/_ref; the oracle port only if that copy is missing); `--impl reference-gpu` and the
+`gpu_eager_baseline` object time the same modules with `.cuda()` on this B200 (the north star's denominator).
 `--gpus N` (under torchrun): N independent replicas, one prompt stream each, no data-path collective (weak scaling).
 """
 from __future__ import annotations
@@ -254,15 +256,11 @@ def hbm_peak():
 # ------------------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port) -- the only place bench.py executes oracle/
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_cycles: int, warm: int, threads: int, layers: int = 32):
-    """Time `n_cycles` draft+verify cycles of the oracle on the host cores at the BASELINE config-2 shapes.
-    To stay bounded (a CPU prefill of 704 tokens through 7B weights alone takes minutes) the KV state is
-    synthetic: target KV rows [0,704) hold random bf16 values and the draft is prefilled from random hidden
-    states; the per-cycle work (13.2 GB of target weights, 3.2 GB of draft weights, the attention over S~734 keys,
-    tree build / accept / splice) is exactly that of a real cycle.  Returns (tokens, seconds, accept lengths)."""
+def _cpu_7b_weights(layers: int):
+    """Random bf16 weights at the BASELINE config-2 shapes on the host.  One layer is drawn and cloned per layer
+    (distinct memory, same values: timing-equivalent, and 32 x fewer random numbers to draw on the CPU)."""
     from oracle import vispec_oracle as vo
 
-    torch.set_num_threads(threads)
     tcfg, dcfg = vo.TargetCfg(layers=layers, max_pos=2048), vo.DraftCfg()
     g = torch.Generator().manual_seed(0)
     H, I, V = tcfg.hidden, tcfg.inter, tcfg.vocab
@@ -278,7 +276,7 @@ def cpu_reference_sample(n_cycles: int, warm: int, threads: int, layers: int = 3
              "post_attention_layernorm.weight": torch.ones(H, dtype=torch.bfloat16)}
     tw = {"model.embed_tokens.weight": rn(V, H, std=1.0), "model.norm.weight": torch.ones(H, dtype=torch.bfloat16),
           "lm_head.weight": rn(V, H, std=4.0 * H ** -0.5)}
-    for li in range(tcfg.layers):                       # distinct memory per layer (clone), same values: timing-equivalent
+    for li in range(tcfg.layers):
         for k, v in proto.items():
             tw[f"model.layers.{li}.{k}"] = v.clone() if li else v
     dw = {"embed_tokens.weight": tw["model.embed_tokens.weight"]}
@@ -291,19 +289,52 @@ def cpu_reference_sample(n_cycles: int, warm: int, threads: int, layers: int = 3
     dw["imadpt.q"] = rn(dcfg.num_q, dcfg.heads, 128, std=128 ** -0.5)
     for n in ("k_proj", "v_proj", "o_proj"):
         dw[f"imadpt.{n}.weight"] = rn(H, H, std=H ** -0.5)
-    target, draft = vo.TargetOracle(tcfg, tw, kv_max=1024), vo.DraftOracle(dcfg, dw)
     L = N_PRE + N_IMG + N_POST
-    target.kv[..., :L, :] = rn(2 * tcfg.layers, 1, tcfg.kv_heads, L, 128, std=1.0)
-    target.cur_len = L
-    ids = torch.randint(1, V - 64, (1, L + 1), generator=g)
+    ids = torch.randint(1, V - 64, (1, L), generator=g)
     mask = torch.zeros(1, L, dtype=torch.bool)
     mask[0, N_PRE:N_PRE + N_IMG] = True
-    emb = torch.nn.functional.embedding(ids[:, :L], tw["model.embed_tokens.weight"])
+    emb = torch.nn.functional.embedding(ids, tw["model.embed_tokens.weight"])
+    return tcfg, dcfg, tw, dw, ids, emb, mask, g
+
+
+def cpu_reference_sample(n_cycles: int, warm: int, threads: int, layers: int = 32):
+    """Time `n_cycles` draft+verify cycles of the reference's CPU path on the host cores at the BASELINE config-2 shapes,
+    after `warm` untimed cycles.  Preferred: the UNMODIFIED reference modules vendored under baseline/_ref
+    (baseline/ref_harness.py, kind "reference"); fallback: the oracle restatement (kind "port").
+    Decode only: a CPU prefill of 704 tokens through 7B weights takes minutes, so the KV state is synthetic -- target KV
+    rows [0,704) hold random bf16 values and the draft is prefilled from random hidden states; the per-cycle work
+    (13.2 GB of target weights, 3.2 GB of draft weights, the attention over S~734 keys, tree build / accept / splice) is
+    exactly that of a real cycle.  Returns (tokens, seconds, accept lengths, kind, what)."""
+    torch.set_num_threads(threads)
+    tcfg, dcfg, tw, dw, ids, emb, mask, g = _cpu_7b_weights(layers)
+    from baseline import ref_harness as rh
+
+    why = rh.available()
+    if why is None:
+        model = rh.RefSpecStandIn(rh.build_target(tcfg, tw, "cpu", assign=True), rh.build_draft(dcfg, dw, "cpu", assign=True))
+        kv = rh.make_kv(model, tcfg, "cpu")
+        if warm > 0:
+            rh.generate(model, kv, ids, emb, mask, max_new_tokens=10 ** 9, max_cycles=warm, synthetic_prefill=True)
+        r = rh.generate(model, kv, ids, emb, mask, max_new_tokens=10 ** 9, max_cycles=n_cycles, synthetic_prefill=True)
+        return r["new_token"], r["decode_s"], r["accept"], "reference", \
+            "unmodified vispec.model modules (baseline/_ref) driven by baseline/ref_harness.py"
+    from oracle import vispec_oracle as vo
+
+    H = tcfg.hidden
+
+    def rn(*s, std):
+        return (torch.randn(*s, generator=g) * std).to(torch.bfloat16)
+
+    target, draft = vo.TargetOracle(tcfg, tw, kv_max=1024), vo.DraftOracle(dcfg, dw)
+    L = ids.shape[1]
+    target.kv[..., :L, :] = rn(2 * tcfg.layers, 1, tcfg.kv_heads, L, 128, std=1.0)
+    target.cur_len = L
+    ids1 = torch.cat((ids, torch.randint(1, tcfg.vocab - 64, (1, 1), generator=g)), dim=1)
     hidden = rn(1, L, H, std=1.0)
     head_w = tw["lm_head.weight"]
     with torch.no_grad():
-        tree = draft.topk_generate(hidden, ids, head_w, inputs_embeds=emb, image_mask=mask)
-        input_ids = ids[:, :L]
+        tree = draft.topk_generate(hidden, ids1, head_w, inputs_embeds=emb, image_mask=mask)
+        input_ids = ids
         pad = torch.full((1, 1), -1, dtype=torch.long)
         tokens, acc, t0 = 0, [], None
         for c in range(warm + n_cycles):
@@ -326,8 +357,48 @@ def cpu_reference_sample(n_cycles: int, warm: int, threads: int, layers: int = 3
             if c >= warm:
                 acc.append(a)
         dt = time.perf_counter() - t0
-    return tokens, dt, acc
+    return tokens, dt, acc, "port", f"oracle/vispec_oracle.py (vendored reference unavailable: {why})"
 
+
+def gpu_reference_run(device, steps: int, warmup: int, seed: int, layers: int = 32, count_launches: bool = True):
+    """The north star's denominator: the reference's own HF/PyTorch eager path on this B200 -- the unmodified
+    vispec.model modules (baseline/_ref) with `.cuda()`, same synthetic 7B weights, same 576 + 128 prompt, 256-token
+    greedy generation, prompt pass included in each generation but excluded from the timed region exactly like the
+    reference's `return_decode_time` (spec_model_ours.py:480-482,575-578; torch.cuda.synchronize on both sides).
+    Returns None when the vendored reference is unavailable."""
+    from baseline import ref_harness as rh
+    from vispec_b200.engine import DraftConfig, TargetConfig
+
+    why = rh.available()
+    if why is not None:
+        return {"unavailable": why}
+    tcfg, dcfg = TargetConfig(layers=layers), DraftConfig()
+    tw = synth_target_weights(tcfg, seed, device)
+    dw = synth_draft_weights(dcfg, seed + 1, device)
+    model = rh.RefSpecStandIn(rh.build_target(tcfg, tw, device, assign=True), rh.build_draft(dcfg, dw, device, assign=True))
+    ids, emb, mask = synth_prompt(tcfg, tw["model.embed_tokens.weight"], seed + 7, device)
+    kv = rh.make_kv(model, tcfg, device)
+    launches = None
+    for i in range(max(1, warmup)):
+        r = rh.generate(model, kv, ids, emb, mask, max_new_tokens=GEN_TOKENS - 1, count_launches=count_launches and i == 0)
+        launches = r["launches_per_cycle"] if r["launches_per_cycle"] is not None else launches
+    gi = torch.device(device).index or 0
+    clocks = ClockSampler(gi)
+    clocks.start()
+    tokens, dec_s, pre_s, acc, out = 0, 0.0, 0.0, [], None
+    for _ in range(steps):
+        r = rh.generate(model, kv, ids, emb, mask, max_new_tokens=GEN_TOKENS - 1)
+        tokens += r["new_token"]; dec_s += r["decode_s"]; pre_s += r["prefill_s"]; acc += r["accept"]
+        out = r["output_ids"]
+    clk = clocks.stop()
+    res = {"value": tokens / dec_s, "unit": "tokens/s", "kind": "reference",
+           "what": "unmodified vispec.model modules (baseline/_ref) on cuda, eager PyTorch " + torch.__version__,
+           "steps": steps, "warmup": max(1, warmup), "tokens": tokens, "decode_s": dec_s, "ms_per_cycle": dec_s / max(1, len(acc)) * 1e3,
+           "prefill_ms": pre_s / steps * 1e3, "accept_len_mean": sum(acc) / max(1, len(acc)),
+           "kernel_launches_per_cycle": launches, "clocks": clk, "output_ids": out[0].tolist()}
+    del model, kv, tw, dw
+    torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -378,23 +449,46 @@ def dist_setup(n_gpus):
 
 
 def run_reference(args):
-    rank, world, _ = dist_setup(args.gpus)
+    """`--impl reference`: the reference's CPU implementation on the host cores (the tier's reference arm).
+    `--impl reference-gpu`: the reference's own eager PyTorch path on the B200 (the north star's denominator)."""
+    rank, world, local = dist_setup(args.gpus)
     if rank != 0:
+        return
+    t_all0 = time.perf_counter()
+    cfg = {"workload": WORKLOAD, "tree": "total_token=30 depth=3 top_k=8 num_q=2", "weights": "random-init"}
+    if args.impl == "reference-gpu":
+        device = f"cuda:{local}"
+        torch.cuda.set_device(local)
+        r = gpu_reference_run(device, args.steps, max(args.warmup, 1), seed=0, layers=args.layers)
+        if "unavailable" in r:
+            print(json.dumps({"impl": "reference-gpu", "unavailable": r["unavailable"]}), flush=True)
+            return
+        r.pop("output_ids", None)
+        line = {"metric": "decode_tokens_per_sec", "value": r["value"], "unit": "tokens/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": r["warmup"], "ms_per_step": r["decode_s"] / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference-gpu",
+                "config": dict(cfg, path="reference eager PyTorch on 1xB200, decode region of spec_model_ours.py:480-482"),
+                "accept_len_mean": r["accept_len_mean"], "gpu_eager_baseline": r, "clocks": r["clocks"],
+                "e2e": {"value": r["tokens"] / (r["decode_s"] + r["prefill_ms"] * 1e-3 * args.steps), "unit": "tokens/s",
+                        "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s": time.perf_counter() - t_all0}
+        print(json.dumps(line), flush=True)
         return
     threads = os.cpu_count() or 1
     per_step = max(1, args.ref_cycles)
-    vals, accs = [], []
-    t_all0 = time.perf_counter()
-    tokens, dt, acc = cpu_reference_sample(per_step * args.steps, warm=min(args.warmup, 1), threads=threads)
+    warm = min(max(args.warmup, 0), 2) * per_step            # warm-up CYCLES actually run (bounded: ~0.3 s each)
+    tokens, dt, acc, kind, what = cpu_reference_sample(per_step * args.steps, warm=warm, threads=threads)
     tps = tokens / dt
     line = {"metric": "decode_tokens_per_sec", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm // per_step, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "tree": "total_token=30 depth=3 top_k=8 num_q=2", "weights": "random-init"},
+            "config": dict(cfg, region="decode only (synthetic KV state, CPU prompt pass skipped)",
+                           sample=f"{per_step} draft+verify cycle(s) per step"),
             "accept_len_mean": sum(acc) / max(1, len(acc)),
-            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                             "sample": f"{per_step} draft+verify cycle(s) per step at S=704+ with synthetic KV state "
-                                       f"(CPU prefill skipped), oracle/vispec_oracle.py, torch {torch.__version__} CPU bf16"},
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": kind,
+                             "sample": f"{per_step} draft+verify cycle(s) per step after {warm} warm-up cycle(s) at S=704+ with "
+                                       f"synthetic KV state (decode only; CPU prompt pass skipped); {what}; torch "
+                                       f"{torch.__version__} CPU bf16"},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0}
     print(json.dumps(line), flush=True)
@@ -415,8 +509,11 @@ def run_ours(args):
     eng = model.base_model_engine
     gen_kw = dict(temperature=0.0, log=True, return_acceptance_len=True, max_new_tokens=GEN_TOKENS - 1)
 
+    last_out = {}
+
     def decode_step():
         out, new_token, idx, acc = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, **gen_kw)
+        last_out["ids"] = out
         return new_token, acc, model.last_decode_ms
 
     # pinned host copies for the e2e leg
@@ -572,13 +669,27 @@ def run_ours(args):
         return
     value = tokens_all / (dec_ms_max * 1e-3)
     e2e_v = e2e_tokens_all / e2e_s_max
+    # the north star's denominator (rank 0, N=1): the reference's own eager PyTorch path on this B200
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_baseline:
+        gpu_ref = gpu_reference_run(device, steps=max(1, min(2, args.steps)), warmup=1, seed=rank, layers=args.layers)
+        if "unavailable" not in gpu_ref:
+            ref_ids = gpu_ref.pop("output_ids")
+            mine = last_out["ids"][0].tolist()
+            n_cmp = min(len(mine), len(ref_ids))
+            same = 0
+            while same < n_cmp and mine[same] == ref_ids[same]:
+                same += 1
+            gpu_ref["tokens_identical_to_ours"] = {"compared": n_cmp - ids.shape[1], "common_prefix": same - ids.shape[1]}
+            gpu_ref["speedup_decode"] = value / gpu_ref["value"]
+            gpu_ref["target_1p5x_met"] = bool(value >= 1.5 * gpu_ref["value"])
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        ctok, cdt, cacc = cpu_reference_sample(args.ref_cycles, warm=1, threads=threads)
-        cpu = {"value": ctok / cdt, "unit": "tokens/s", "cores": threads, "kind": "port",
-               "sample": f"{args.ref_cycles} draft+verify cycle(s) after 1 warm-up at S=704+ with synthetic KV state, "
-                         f"oracle/vispec_oracle.py on CPU bf16"}
+        ctok, cdt, cacc, ckind, cwhat = cpu_reference_sample(args.ref_cycles, warm=1, threads=threads)
+        cpu = {"value": ctok / cdt, "unit": "tokens/s", "cores": threads, "kind": ckind,
+               "sample": f"{args.ref_cycles} draft+verify cycle(s) after 1 warm-up cycle at S=704+ with synthetic KV state "
+                         f"(decode only); {cwhat}; CPU bf16"}
     line = {"metric": "decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dec_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -590,7 +701,7 @@ def run_ours(args):
             "e2e": {"value": e2e_v, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clk, "roofline": roof, "roofline_attention": roof_attn,
             "phases_us_per_cycle": phases, "accept_fixture": fixture, "qwen2_5_vl_7b": qwen,
-            "attention_long_context": attn_long, "cpu_baseline": cpu}
+            "attention_long_context": attn_long, "gpu_eager_baseline": gpu_ref, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()
@@ -601,13 +712,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--ref-cycles", type=int, default=3, help="CPU cycles per bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU (eager PyTorch) leg")
     ap.add_argument("--no-fixture", action="store_true", help="skip the accept-length (bigram fixture) leg")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-gpu"):
         run_reference(args)
     else:
         run_ours(args)

@@ -395,7 +395,8 @@ class DraftOracle:
             out, past = self.forward(hidden, input_ids=input_ids)
         self.stable_kv = past
         last_hidden = out[:, -1]
-        last_p = F.log_softmax(F.linear(last_hidden, head_weight), dim=-1)   # bf16, :1111-1113
+        root_logits = F.linear(last_hidden, head_weight)
+        last_p = F.log_softmax(root_logits, dim=-1)                          # bf16, :1111-1113
         top = torch.topk(last_p, top_k, dim=-1)
         scores = top.values[0]
         scores_list = [scores[None]]
@@ -409,6 +410,7 @@ class DraftOracle:
         if trace is not None:
             trace["stable_out"] = last_hidden.clone()
             trace["levels"] = []
+            trace["logit_absmax"] = [float(root_logits.float().abs().max())]   # noise unit of the margin rule (tests/parity.py)
         for i in range(depth):                                            # :1126-1165
             self.tree_mask = tree_mask
             pos = len_posi + torch.zeros(top_k, dtype=torch.long, device=self.device)
@@ -416,7 +418,8 @@ class DraftOracle:
             len_posi += 1
             bias = 1 + top_k ** 2 * max(0, i - 1) + (top_k if i > 0 else 0)
             parents_list.append(cs_index + bias)
-            last_p = F.log_softmax(F.linear(out[0], head_weight), dim=-1)
+            level_logits = F.linear(out[0], head_weight)
+            last_p = F.log_softmax(level_logits, dim=-1)
             top = torch.topk(last_p, top_k, dim=-1)
             cu_scores = top.values + scores[:, None]
             cs = torch.topk(cu_scores.view(-1), top_k, dim=-1)
@@ -430,6 +433,7 @@ class DraftOracle:
             if trace is not None:
                 trace["levels"].append(dict(logp=last_p.clone(), topk_idx=top.indices.clone(),
                                             cu_scores=cu_scores.clone(), cs_index=cs_index.clone()))
+                trace["logit_absmax"].append(float(level_logits.float().abs().max()))
         self.tree_mask = None
         scores_flat = torch.cat(scores_list, dim=0).view(-1)
         tokens_flat = torch.cat(ss_token, dim=0).view(-1)
@@ -582,6 +586,7 @@ def kv_splice(kv, select_indices, prev_len: int):
 @dataclass
 class SpecTrace:
     cycles: List[dict] = field(default_factory=list)
+    draft: List[dict] = field(default_factory=list)   # per topk_generate call (prefill first): scores / margins of the tree
 
 
 @torch.no_grad()
@@ -603,8 +608,11 @@ def spec_generate(target: TargetOracle, draft: DraftOracle, input_ids, inputs_em
         logits, hidden = target.forward(inputs_embeds=inputs_embeds)
     token = torch.argmax(logits[:, -1])[None, None]
     input_ids = torch.cat((input_ids, token), dim=1)
+    dt = {} if trace is not None else None
     draft_tokens, retrieve, tree_mask, tree_pos = draft.topk_generate(
-        hidden, input_ids, head_w, inputs_embeds=inputs_embeds, image_mask=image_mask)
+        hidden, input_ids, head_w, inputs_embeds=inputs_embeds, image_mask=image_mask, trace=dt)
+    if trace is not None:
+        trace.draft.append(dt)
     input_ids = input_ids[:, :-1]     # initialize_tree's cat is local (utils.py:292); caller keeps the prompt
     new_token, accept_lens, idx = 0, [], 0
     pad = torch.full((1, 1), -1, dtype=torch.long, device=input_ids.device)
@@ -625,8 +633,11 @@ def spec_generate(target: TargetOracle, draft: DraftOracle, input_ids, inputs_em
             trace.cycles.append(dict(draft_tokens=draft_tokens.clone(), retrieve=retrieve.clone(),
                                      tree_mask=tree_mask.clone(), tree_pos=tree_pos.clone(),
                                      best=best, accept=a, token=int(token), logits_root=t_logits[0, 0].clone()))
+        dt = {} if trace is not None else None
         draft_tokens, retrieve, tree_mask, tree_pos = draft.topk_generate(
-            acc_hidden, torch.cat((input_ids, token), dim=1), head_w)
+            acc_hidden, torch.cat((input_ids, token), dim=1), head_w, trace=dt)
+        if trace is not None:
+            trace.draft.append(dt)
         new_token += a + 1
         if eos_token_id is not None and eos_token_id in input_ids[0, input_len:].tolist():
             break

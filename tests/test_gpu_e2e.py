@@ -6,9 +6,11 @@ Exactness policy:
   * accepted token ids at T=0 depend only on the target's arg-max -> compared exactly with the reference's
     output AND with plain greedy decoding (the speculative-decoding invariant);
   * draft-tree contents depend on bf16 log-prob top-k, where 1-ulp GEMM differences and exact ties (torch's tie
-    order is implementation-defined) can change which candidates enter the tree; trees and accept lengths are
-    therefore compared exactly only up to the first cycle where the reference's own top-k margins are below one
-    bf16 ulp; structural invariants are asserted for every cycle.
+    order is implementation-defined) can change which candidates enter the tree.  Trees are compared exactly with the
+    reference's; the FIRST cycle whose tree differs must be one where the reference's own selection margins (from the
+    oracle's trace of the same cycle; the oracle is pinned bit-exactly to these goldens) are within two noise units --
+    tests/parity.py -- otherwise the test fails.  After such a cycle the two runs hold different drafts and only
+    the accepted tokens (which do not depend on the draft) and the structural invariants are compared.
 """
 import glob
 import os
@@ -20,6 +22,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import synth  # noqa: E402  (checker only)
 from oracle import vispec_oracle as vo  # noqa: E402
+from parity import assert_ulps, record, tree_mismatch_is_excusable  # noqa: E402
 from vispec_b200 import _lib as L  # noqa: E402
 from vispec_b200.engine import DraftConfig, TargetConfig  # noqa: E402
 from vispec_b200.model import utils as vu  # noqa: E402
@@ -91,13 +94,17 @@ def test_reference_api_cycle_matches_golden(name):
     (draft_tokens, retrieve, tree_mask, tree_pos, logits, hidden, sample_token) = \
         vu.initialize_tree(ids_d, model, pkv, None, emb_d, None, image_mask=mask_d)
     first = g["first"]
-    # prefill: logits within bf16 tolerance of the reference's, same first token
-    torch.testing.assert_close(logits[0, -1].cpu(), first["prefill_last_logits"], rtol=2 ** -6, atol=0.15)
+    # the oracle's per-cycle score traces give the margins of every tree the reference built (CPU, seconds)
+    otrace = vo.SpecTrace()
+    vo.spec_generate(vo.TargetOracle(tcfg, tw), vo.DraftOracle(dcfg, dw), ids, emb, mask, max_new_tokens=10 ** 9,
+                     max_cycles=g["meta"]["n_cycles"], trace=otrace)
+    # prefill: logits as a bf16 ulp histogram against the reference's, same first token
+    assert_ulps(f"e2e/{name}/prefill_last_logits", logits[0, -1], first["prefill_last_logits"], exact=0.5, le2=0.97, le4=0.995)
     assert int(sample_token) == int(first["sample_token"])
     assert model.spec_layer.stable_kv[0][0].shape[2] == first["draft_kv_len"]
     assert model.spec_layer.stable_kv[0][2] == first["draft_real_len"]
-    torch.testing.assert_close(model.spec_layer.last_img_hidden.float().cpu(), first["last_img_hidden"].float(),
-                               rtol=2 ** -6, atol=2e-2)
+    assert_ulps(f"e2e/{name}/last_img_hidden", model.spec_layer.last_img_hidden, first["last_img_hidden"], exact=0.7,
+                le2=0.99, le4=0.995)
     input_ids = ids_d
     new_token = 0
     pad = torch.full((1, 1), -1, dtype=torch.long, device=DEV)
@@ -109,11 +116,17 @@ def test_reference_api_cycle_matches_golden(name):
         gt = golden_trees[ci]
         same_tree = (torch.equal(draft_tokens.cpu(), gt["draft_tokens"]) and torch.equal(retrieve, gt["retrieve_indices"])
                      and torch.equal(tree_mask, gt["tree_mask"]) and torch.equal(tree_pos.cpu(), gt["tree_position_ids"]))
+        if trees_exact and not same_tree:
+            # first divergent tree: tolerated only where the reference's own margins are small
+            ok, margins = tree_mismatch_is_excusable(otrace.draft[ci], dcfg.top_k, dcfg.total_tokens - 1)
+            record(f"e2e/{name}/first_divergent_tree", {"cycle": ci, "excusable": bool(ok),
+                                                        "min_margin_units": min(m for _, m in margins)})
+            assert ok, f"cycle {ci}: tree differs from the reference's although every selection margin is large: {margins}"
         trees_exact = trees_exact and same_tree
         model.base_model.model.tree_mask = tree_mask
         logits, hidden_new, _ = vu.tree_decoding(model, draft_tokens, pkv, tree_pos, input_ids, retrieve)
         if trees_exact:
-            torch.testing.assert_close(logits[0, 0].cpu(), ref["tree_logits_root"], rtol=2 ** -6, atol=0.15)
+            assert_ulps(f"e2e/{name}/tree_logits_root/{ci}", logits[0, 0], ref["tree_logits_root"], exact=0.5, le2=0.97, le4=0.995)
         cand = torch.cat((draft_tokens, pad), dim=1)[0, retrieve.to(DEV)]
         best, a, sample_p = vu.evaluate_posterior(logits, cand, None)
         if trees_exact:
@@ -136,6 +149,7 @@ def test_reference_api_cycle_matches_golden(name):
         assert new_token == g["new_token"]
         kv_sum = pkv_data[0][..., :int(cur_len[0]), :].float().sum(dim=(1, 2, 3, 4)).cpu()
         torch.testing.assert_close(kv_sum, g["kv_checksum"], rtol=1e-2, atol=2.0)
+    record(f"e2e/{name}/trees_identical_every_cycle", {"value": bool(trees_exact)})
     print(f"[{name}] trees identical to the reference in every cycle: {trees_exact}")
 
 

@@ -1,5 +1,5 @@
 // extern "C" boundary of libvispec_b200.so (declared in include/vispec_b200.h) and the composite steps that
-// chain the kernels of gemm_skinny.cu / attention.cu / rowops.cu / tree.cu on one stream.
+// chain the kernels of gemm_tc.cu / gemm_wide.cu / attention.cu / rowops.cu / tree.cu on one stream.
 #include <math.h>
 #include <stdio.h>
 

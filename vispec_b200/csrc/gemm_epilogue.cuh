@@ -1,4 +1,4 @@
-// Fused epilogues of the weight-streaming GEMM, shared by the kernels in gemm_skinny.cu / gemm_tc.cu.
+// Fused epilogues of the weight-streaming GEMM, shared by the kernels in gemm_tc.cu / gemm_wide.cu.
 // Input: one fp32 accumulator tile ct[32 tokens][EPI_CT_LD] (128 weight rows) in shared memory.
 #pragma once
 #include "kernels.h"

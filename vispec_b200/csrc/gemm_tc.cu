@@ -1,6 +1,6 @@
 // Weight-streaming GEMM on the 5th-generation tensor cores:  Y[T<=32 per block, N] = X[T,K] * W[N,K]^T.
 //
-// Same contract and epilogues as gemm_skinny.cu (the mma.sync bring-up kernel); this is the production path.
+// (The mma.sync bring-up kernel this replaced was removed in round 2.)
 // ncu on the mma.sync version showed the legacy tensor pipe 25 % busy at only 31 % of HBM bandwidth and a
 // 1.3-wave grid, i.e. it could never reach the HBM roofline.  Here:
 //   * persistent kernel, one CTA per SM, work units (128-row tile x k-split x token block) dealt round-robin
@@ -25,7 +25,6 @@
 
 namespace vs {
 
-cudaError_t launch_gemm_legacy(const GemmArgs& a, cudaStream_t st);
 
 namespace {
 
@@ -353,15 +352,6 @@ cudaError_t launch_t(const GemmArgs& a, cudaStream_t st) {
   return e;
 }
 
-bool use_legacy() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VS_GEMM_LEGACY");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 bool use_wide() {
   static int v = -1;
   if (v < 0) {
@@ -417,7 +407,6 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st) {
   if (a.K % BK != 0 || a.ldw % 8 != 0 || a.ldx % 8 != 0) return cudaErrorInvalidValue;
   if (a.splits > 1 && (!a.partials || !a.counters)) return cudaErrorInvalidValue;
   if (a.splits > a.K / BK) return cudaErrorInvalidValue;
-  if (use_legacy()) return launch_gemm_legacy(a, st);
   if (a.T > GEMM_WIDE_MIN_ROWS && use_wide()) return launch_gemm_wide(a, st);   // prompt passes: 256-token MMA tiles
   switch (a.epi) {
     case EPI_STORE: return launch_t<EPI_STORE>(a, st);

@@ -179,6 +179,19 @@ class ScratchBuffers:
                            L.ptr(self.opart), self.pv_splits, L.ptr(self.attn_counters))
 
 
+def run_linear(lib, sc: ScratchBuffers, x, ldx, w, bias, T, N, K, y, ldy, epi=L.EPI_STORE):
+    """y[T,N] = x[T,K] @ w[N,K]^T (+ bias) through vs_linear with the caller's scratch."""
+    a = L.LinearArgs()
+    a.X, a.ldx, a.W, a.ldw, a.bias = L.ptr(x), ldx, L.ptr(w), K, L.ptr(bias)
+    a.T, a.N, a.K = T, N, K
+    a.splits = lib.vs_linear_splits(N, K, T)
+    while a.splits > 1 and lib.vs_linear_partials_floats(N, T, a.splits) > sc.partials.numel():
+        a.splits -= 1
+    a.partials, a.counters, a.epi = L.ptr(sc.partials), L.ptr(sc.counters), epi
+    a.Y, a.ldy = L.ptr(y), ldy
+    L.check(lib.vs_linear(C.byref(a), _stream()), "vs_linear")
+
+
 def _dims(hidden, inter, heads, kv_heads, vocab, layers, eps) -> L.Dims:
     return L.Dims(hidden, inter, heads, kv_heads, vocab, layers, eps)
 
@@ -439,7 +452,10 @@ class TargetEngine:
         hidden = torch.empty(Lq, cfg.hidden, dtype=self.dtype, device=self.device)
         L.check(self.lib.vs_rmsnorm(L.ptr(big.h), cfg.hidden, L.ptr(self.norm), L.ptr(hidden), cfg.hidden, Lq, cfg.hidden,
                                     cfg.eps, st), "vs_rmsnorm")
-        logits_last = torch.nn.functional.linear(hidden[-1], self.lm_head).float()
+        # LM head on the one row the caller consumes (modeling_llama_kv.py:1196-1197 computes all rows)
+        run_linear(self.lib, self.scratch, hidden[Lq - 1:], cfg.hidden, self.lm_head, None, 1, cfg.vocab, cfg.hidden,
+                   self.logits, cfg.vocab)
+        logits_last = self.logits[0].float()
         self.set_len(S)
         return logits_last, hidden[None]
 
@@ -479,7 +495,7 @@ class DraftEngine:
     fc / img_fc, ImgAdaptor, dynamic draft tree.  `weights` uses the reference state-dict keys."""
 
     def __init__(self, cfg: DraftConfig, weights: Dict[str, torch.Tensor], lm_head: torch.Tensor, device="cuda",
-                 cache_rows: int = 4096):
+                 cache_rows: int = 4096, max_positions: int = 8192 + 64):
         _require_cuda(device)
         if cfg.head_dim != 128:
             raise NotImplementedError("head_dim must be 128")
@@ -516,7 +532,11 @@ class DraftEngine:
         if use_programs() and use_tiled():
             for w in (self.w_qkv, self.w_o, self.w_gateup, self.w_down, self.w_fc, self.w_img_fc):
                 self.tiled.append((w, pack_weight_tiles(w)))
-        self.cos, self.sin = rope_tables(128, cfg.max_pos, cfg.rope_theta, self.dtype, dev)
+        # Draft positions follow the UNCOMPRESSED sequence index (image tokens keep their original positions,
+        # cnets_ours.py:932-937), so they run up to the target's KV length, not the draft's max_position_embeddings: the
+        # tables cover both (rows < cfg.max_pos equal the reference's; it raises an index error beyond them)
+        self.rope_rows = max(cfg.max_pos, int(max_positions))
+        self.cos, self.sin = rope_tables(128, self.rope_rows, cfg.rope_theta, self.dtype, dev)
         self.cache_rows = cache_rows
         self.k_cache = torch.zeros(nh, cache_rows, 128, dtype=self.dtype, device=dev)
         self.v_cache = torch.zeros(nh, cache_rows, 128, dtype=self.dtype, device=dev)
@@ -637,6 +657,8 @@ class DraftEngine:
         n_c = n_text + n_c_img
         if n_c + 8 * (cfg.depth + 1) + 8 > self.cache_rows:
             raise ValueError("draft KV cache too small for this prompt")
+        if Lq + cfg.depth + 2 > self.rope_rows:
+            raise ValueError("prompt positions exceed the draft's rotary table")
         rows = _ceil(max(n_c, 1), 32)
         big = ScratchBuffers(H, cfg.inter, nh, cfg.vocab, rows, rows, dev)
         x1 = torch.zeros(rows, 2 * H, dtype=self.dtype, device=dev)
@@ -662,6 +684,7 @@ class DraftEngine:
         else:
             big.h[:n_c] = fused[:n_c]
             pos[:n_c] = pos_all
+        self.prefill_packed = big.h[:n_c].clone()                           # packed rows before the layer (parity tests)
         layer = self._layer_struct()
         rope = L.Rope(L.ptr(self.cos), L.ptr(self.sin))
         L.check(lib.vs_decoder_layer(C.byref(self.dims), C.byref(layer), C.byref(big.c), C.byref(rope), n_c, L.ptr(pos),
@@ -688,15 +711,7 @@ class DraftEngine:
                                     None, int(sample_token), st), "vs_draft_levels")
 
     def _linear(self, sc: ScratchBuffers, x, ldx, w, bias, T, N, K, y, ldy, epi=L.EPI_STORE):
-        a = L.LinearArgs()
-        a.X, a.ldx, a.W, a.ldw, a.bias = L.ptr(x), ldx, L.ptr(w), K, L.ptr(bias)
-        a.T, a.N, a.K = T, N, K
-        a.splits = self.lib.vs_linear_splits(N, K, T)
-        while a.splits > 1 and self.lib.vs_linear_partials_floats(N, T, a.splits) > sc.partials.numel():
-            a.splits -= 1
-        a.partials, a.counters, a.epi = L.ptr(sc.partials), L.ptr(sc.counters), epi
-        a.Y, a.ldy = L.ptr(y), ldy
-        L.check(self.lib.vs_linear(C.byref(a), _stream()), "vs_linear")
+        run_linear(self.lib, sc, x, ldx, w, bias, T, N, K, y, ldy, epi)
 
     # -- later calls (cnets_ours.py:1090-1092 + tree) ------------------------------------------------------
     def tree_from_accepted(self, hidden_rows: torch.Tensor, ids: torch.Tensor, sample_token: int):

@@ -16,9 +16,10 @@ from ..engine import DraftConfig, DraftEngine
 
 class Model:
     def __init__(self, config: DraftConfig, weights, lm_head_weight: torch.Tensor, device="cuda",
-                 cache_rows: int = 4096):
+                 cache_rows: int = 4096, max_positions: int = 8192 + 64):
         self.config = config
-        self.engine = DraftEngine(config, weights, lm_head_weight, device=device, cache_rows=cache_rows)
+        self.engine = DraftEngine(config, weights, lm_head_weight, device=device, cache_rows=cache_rows,
+                                  max_positions=max_positions)
         self.total_tokens = config.total_tokens - 1       # cnets_ours.py:733
         self.depth = config.depth
         self.top_k = config.top_k

@@ -58,6 +58,9 @@ class TargetLM:
         self.current_length_data = None        # set by initialize_past_key_values' caller (SpecModel)
 
     rope_deltas = 0
+    # Prompt-pass logits: "last" returns [1, 1, V] (the row `initialize_tree` and the baseline loops consume through
+    # `logits[:, -1]`); "all" computes the reference's [1, L, V] -- 185 GFLOP and 90 MB at 704 rows for one used row.
+    prompt_logits = "last"
 
     def get_input_embeddings(self):
         return self.engine.embed_tokens
@@ -87,8 +90,11 @@ class TargetLM:
                 p3 = position_ids.reshape(3, -1)
                 self.rope_deltas = int(p3.max()) + 1 - p3.shape[1]
                 eng.set_rope_delta(self.rope_deltas)
-            _, hidden = eng.prefill(emb, past=cur, position_ids=position_ids)
-            logits = torch.nn.functional.linear(hidden, eng.lm_head).float()
+            logits_last, hidden = eng.prefill(emb, past=cur, position_ids=position_ids)
+            if self.prompt_logits == "all":    # the reference's [1, L, V] (modeling_llama_kv.py:1196-1197)
+                logits = torch.nn.functional.linear(hidden, eng.lm_head).float()
+            else:                              # every caller on the path reads logits[:, -1] only (utils.py:284-290)
+                logits = logits_last.reshape(1, 1, -1)
         else:
             ids = input_ids.to(eng.device, torch.int32).flatten().contiguous()
             if position_ids is None:       # modeling_qwen2_5_vl_kv.py:2166-2175: cache position + rope_deltas (0 for Llama)
@@ -191,7 +197,8 @@ class SpecModel:
         checkpoints offline)."""
         eng = TargetEngine(target_cfg, target_weights, device=device, kv_max=kv_max)
         lm = TargetLM(eng, image_token_index=image_token_index)
-        draft = Model(draft_cfg, draft_weights, eng.lm_head, device=device, cache_rows=draft_cache_rows)
+        draft = Model(draft_cfg, draft_weights, eng.lm_head, device=device, cache_rows=draft_cache_rows,
+                      max_positions=eng.kv_max + 64)
         return cls(lm, draft, tokenizer=tokenizer, eos_token_id=eos_token_id, vision=vision)
 
     @classmethod
@@ -384,12 +391,23 @@ class SpecModel:
         margin = 2 * (T + L.VS_MAX_ACCEPT)
         idx = 0
         launched = 0
+
+        def fits_now():
+            # rows a cycle (and the one launched ahead of its record) may append: target slab, draft cache, and the
+            # draft's rotary table (draft positions follow the uncompressed sequence index = cur_len)
+            return (cur_len + margin + T < eng_t.kv_max and
+                    d_rows + margin + 8 * (self.spec_layer.depth + 2) < eng_d.cache_rows and
+                    cur_len + margin + self.spec_layer.depth + 2 < eng_d.rope_rows)
+
         self._dec_evt[0].record()
         if max_length > 0:
+            if not fits_now():       # the reference raises in KVCache.cat (kv_cache.py:52-66); never launch past the slab
+                raise ValueError(f"prompt of {input_len} tokens leaves no room for a draft tree in the KV slab "
+                                 f"({eng_t.kv_max} rows) / draft cache ({eng_d.cache_rows} rows)")
             launch(0)
             launched = 1
         for idx in range(max_length):
-            fits = (cur_len + margin + T < eng_t.kv_max) and (d_rows + margin + 8 * (self.spec_layer.depth + 2) < eng_d.cache_rows)
+            fits = fits_now()
             if launched == idx + 1 and idx + 1 < max_length and fits:
                 launch((idx + 1) % 2)
                 launched += 1
