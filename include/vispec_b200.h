@@ -287,7 +287,9 @@ const char* vs_program_last_error(void);
  * vs_attention_fused_capacity(n_heads, scratch pv_splits, scratch max_chunks) keys (n_ctx + n_new) = what the scratch was
  * sized for (max_chunks * 64; score_ld must cover it); the kernel traps beyond it. */
 int vs_attention_fused_capacity(int n_heads, int pv_splits_cap, int max_chunks);
-/* options: "pf_ahead" (L2 prefetch distance in 16 KB weight chunks per SM, default 0 = off),
+/* options: "pf_ahead" / "inflight" (accepted and ignored since round 2: the L2 prefetcher warp is gone), "x3d" (default 1:
+ * the activations of a slab stage arrive through one 3-D tensor-map load instead of one 2-D load per k-chunk),
+ * formerly: "pf_ahead" (L2 prefetch distance in 16 KB weight chunks per SM, default 0 = off),
  * "trace" (1: record a %globaltimer stamp per phase), "grid" (CTAs; default = SM count; before adding phases),
  * "attn_fused" (see above; before adding phases), "fuse_epilogue" (default 1: an epilogue waits on per-tile arrival
  * counters instead of a grid barrier), "fuse_norm" (default 1; before adding phases: an RMSNorm that follows the
@@ -310,6 +312,22 @@ int vs_program_read_trace_cta(const vs_program* pg, unsigned long long* out_ns, 
  * it.  Every linear added AFTER the registration whose W pointer matches (and ldw == K) streams the tiled copy with
  * contiguous 16 KB bulk copies and is prefetched into L2 ahead of use ("pf_ahead"); results are bit-identical. */
 int vs_program_register_tiled(vs_program* pg, const void* w_row_major, const void* w_tiled);
+/* Slab weights (round 2; vispec_b200/csrc/slab.h has the byte-level layout): the rows of W[N][K] are dealt over the `grid`
+ * CTAs of the persistent kernel so that every CTA owns COMPLETE output rows, streams their whole K range as one
+ * contiguous byte range and finishes them from TMEM -- no split-K partial tiles, no separate epilogue phase (the
+ * reference computes each of these projections as one `F.linear`, e.g. modeling_llama_kv.py:563-565, 648, 421;
+ * cnets_ours.py:363-365, 445, 508, 982-988).  `epi` selects the row pairing: VS_EPI_SWIGLU / VS_EPI_HEADS keep the two
+ * members of a gate|up resp. rotate-half pair in the same accumulator lane.  vs_slab_bytes returns 0 for shapes the
+ * layout does not cover.  A linear added after vs_program_register_slab whose W, epilogue class and grid match runs on
+ * the slab path; anything else keeps the stream-K path above.  grid <= 0: the SM count of the current device. */
+int vs_device_sms(void);
+size_t vs_slab_bytes(int N, int K, int epi, int grid);
+/* the plan behind a slab image, for tools and tests: out[0..13] = pair, packed, elements, tiles per pass, passes,
+ * rows per block, block bytes (HBM), block stride in shared memory, k-chunks, k-chunks per stage, activation offset in a
+ * slot, elements per unit, units with one more, grid.  Returns the number of values written (0: unsupported shape). */
+int vs_slab_plan(int N, int K, int epi, int grid, int32_t* out, int cap);
+int vs_slab_pack(const void* W, int64_t ldw, int N, int K, int epi, int grid, void* dst_128B_aligned, void* stream);
+int vs_program_register_slab(vs_program* pg, const void* w_row_major, const void* w_slab, int epi, int grid);
 int vs_program_add_linear(vs_program* pg, const vs_linear_args* a);
 int vs_program_add_rmsnorm(vs_program* pg, const void* x, int64_t ldx, const void* weight, void* y, int64_t ldy, int T,
                            int H, float eps);

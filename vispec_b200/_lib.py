@@ -19,9 +19,9 @@ VS_MAX_ACCEPT = 8
 ST_SLOTS = 16
 EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_HEADS = range(4)
 (PH_NOP, PH_GEMM, PH_EPI, PH_NORM, PH_ROWS, PH_ATTN_S, PH_ATTN_PV, PH_ARGMAX, PH_LSM_STATS, PH_TREE, PH_SPLICE,
- PH_LSM_CAND, PH_ATTN_FUSED) = range(13)
+ PH_LSM_CAND, PH_ATTN_FUSED, PH_GEMM2) = range(14)
 PHASE_NAMES = ("nop", "gemm", "epilogue", "rmsnorm", "rows", "attn_scores", "attn_pv", "argmax", "lsm_stats", "tree",
-               "kv_splice", "lsm_candidates", "attn_fused")
+               "kv_splice", "lsm_candidates", "attn_fused", "slab_gemm")
 
 
 class LinearArgs(C.Structure):
@@ -129,6 +129,11 @@ _SIGS = {
     "vs_program_read_trace": (C.c_int, [c_vp, c_vp, C.c_int]),
     "vs_program_read_trace_cta": (C.c_int, [c_vp, c_vp, C.c_int]),
     "vs_program_register_tiled": (C.c_int, [c_vp, c_vp, c_vp]),
+    "vs_device_sms": (C.c_int, []),
+    "vs_slab_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vs_slab_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_int]),
+    "vs_slab_pack": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "vs_program_register_slab": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int]),
     "vs_attention_fused_capacity": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "vs_program_add_linear": (C.c_int, [c_vp, C.POINTER(LinearArgs)]),
     "vs_program_add_rmsnorm": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_f32]),

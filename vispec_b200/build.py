@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvispec_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_wide.cu", "attention.cu", "rowops.cu", "tree.cu", "profile.cu", "program.cu", "program_api.cu", "api.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_wide.cu", "attention.cu", "rowops.cu", "tree.cu", "profile.cu", "slab.cu", "program.cu", "program_api.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

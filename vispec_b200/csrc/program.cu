@@ -9,7 +9,7 @@
 //     6-stage / 96 KB ring full (cp.async.bulk of contiguous 16 KB blocks of the tiled weight copy, or TMA tensor loads of
 //     row-major weights).  Weights never depend on activations, so it runs ahead across phase boundaries: the HBM stream
 //     continues while the rest of the CTA is in an epilogue, an attention phase or a grid barrier.  (Deeper rings and an
-//     L2 prefetcher on warp 3 -- option "pf_ahead", off -- were measured and lost: DESIGN.md section 6);
+//     L2 prefetcher on warp 3 were measured and lost in round 1; the prefetcher is gone);
 //   * warp 2 (one lane) is the ACTIVATION producer: the [32 x 64] token tile of each stage is loaded once the phase
 //     that produces it has completed on every CTA (it polls the grid-barrier counter);
 //   * warp 1 (one lane) issues tcgen05.mma (M=128 weight rows, N=32 tokens, K=16; fp32 accumulators double-buffered in
@@ -36,19 +36,24 @@
 #include "attn_dev.cuh"
 #include "profile.h"
 #include "program_dev.cuh"
+#include "slab.h"
 #include "sm100.cuh"
 
 namespace vs {
 
 namespace {
 
+// Ring of the role warps: NS slots of 32 KB (slab.h).  A slab stage (PH_GEMM2) fills a slot with kc k-chunks of this
+// CTA's weight rows + the matching activation blocks; a stream-K stage (PH_GEMM, row-major / tiled weights) uses the
+// first 20 KB of a slot (one 128 x 64 weight chunk + one 32 x 64 activation block).
 #ifndef VS_PG_STAGES
-#define VS_PG_STAGES 6          // weight/activation ring depth per SM (run-ahead buffer); 8 measured slower, 3-4 see DESIGN.md
+#define VS_PG_STAGES 4
 #endif
 constexpr int BM = PG_BM, BK = PG_BK, NS = VS_PG_STAGES;
 constexpr int W_STAGE = BM * BK * 2;             // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;         // 4096
-constexpr int STAGE_BYTES = W_STAGE + X_STAGE;   // 20480 (multiple of 1024)
+constexpr int STAGE_BYTES = SLAB_SLOT_BYTES;     // 32768
+static_assert(W_STAGE + X_STAGE <= STAGE_BYTES, "stream-K stage larger than a ring slot");
 constexpr int BIG_SMEM = 44032;                  // scratch of one attention team (AttnSmem); both together also stage the
                                                  // tree ops and the top-k merge on CTA 0
 constexpr int TEAM_SMEM = 1024;                  // reduction scratch of one small team
@@ -60,7 +65,7 @@ constexpr int BAR_OFF = PHBUF_OFF + 2 * PHASE_SLOT;
 constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
 static_assert(PHASE_WORDS <= PG_WORKERS, "phase descriptor larger than one word per worker thread");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-constexpr int TMEM_COLS = 64;
+constexpr int TMEM_COLS = 128;               // two accumulator sets x two tiles x 32 token columns
 static_assert(sizeof(AttnSmem) <= BIG_SMEM, "team scratch too small for attention");
 static_assert(sizeof(AttnFusedSmem) <= BIG_SMEM, "team scratch too small for fused attention");
 static_assert(sizeof(TreeSmem) <= BIG_SMEM, "team scratch too small for the tree ops");
@@ -133,35 +138,6 @@ __device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team
                             ph.out_rec, *reinterpret_cast<SampleSmem*>(team_base), wtid, PG_WORKERS, WorkerSync());
 }
 
-struct GemmCursor {            // walks the GEMM phases of the program and this CTA's chunk range in each
-  const Phase* phases;
-  const int* tables;
-  int n_phases;
-  int p;                       // current phase index (a PH_GEMM phase) or n_phases
-  int c, hi;                   // next chunk, end of this CTA's range
-  int nk;
-  __device__ __forceinline__ void init(const ProgramHeader& h) {
-    phases = h.phases;
-    tables = h.tables;
-    n_phases = h.n_phases;
-    p = -1;
-    c = hi = 0;
-    nk = 1;
-  }
-  // advance to the next phase in which this CTA has work; false when the program is exhausted
-  __device__ __forceinline__ bool next_phase(int b, int G) {
-    for (++p; p < n_phases; ++p) {
-      if (phases[p].type != PH_GEMM) continue;
-      const int2 r = *reinterpret_cast<const int2*>(tables + phases[p].range_off + 2 * b);
-      c = r.x;
-      hi = r.y;
-      nk = phases[p].nk;
-      if (c < hi) return true;
-    }
-    return false;
-  }
-};
-
 __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHeader hdr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -172,7 +148,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
   uint64_t* tfull = empty + NS;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  volatile int* w_issued = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, b = blockIdx.x;
@@ -187,7 +162,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], PG_WORKERS / 32);
     }
-    *w_issued = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -202,110 +176,177 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
 
   if (warp == 0) {
     // ===================== weight producer =====================
+    // Walks every GEMM phase of the program in order.  Weights never depend on activations, so this thread runs ahead of
+    // the rest of the CTA across phase boundaries: the ring (NS x 32 KB) is the run-ahead buffer.
     if (lane == 0) {
-      GemmCursor cur;
-      cur.init(hdr);
-      int stage = 0, par = 0, issued = 0;
-      // `inflight`: at most this many stages issued but not yet landed.  The ring (NS stages) is the run-ahead buffer;
-      // the in-flight limit only bounds the depth of the memory-system queues, so that the latency-critical loads of
-      // the non-GEMM phases do not wait behind a whole ring of weight tiles.
-      const int inflight = hdr.inflight > 0 && hdr.inflight < NS ? hdr.inflight : NS;
-      int landed = 0;
-      while (cur.next_phase(b, G)) {
-        const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmW;
-        const bf16* wt = hdr.phases[cur.p].Wt;            // tiled layout: chunk c is the 16 KB block c of the matrix
-        int tile = (int)(cur.c / cur.nk), kc = (int)(cur.c % cur.nk);
-        for (int c = cur.c; c < cur.hi; ++c) {
-          while (issued - landed >= inflight) {
-            if (mbar_try_wait(&full_w[landed % NS], (landed / NS) & 1)) ++landed;
+      int stage = 0, par = 0;
+      for (int p = 0; p < hdr.n_phases; ++p) {
+        const Phase& ph = hdr.phases[p];
+        if (ph.type == PH_GEMM2) {
+          const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
+          const uint32_t blk = (uint32_t)ph.s_blk_bytes, blk_smem = (uint32_t)ph.s_blk_smem;
+          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(ph.Wt);
+          for (int ps = 0; ps < passes; ++ps) {
+            const int u = b * passes + ps;
+            if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
+            const uint8_t* src = wbase + (long)u * ph.s_unit_stride;
+            for (int j0 = 0; j0 < nk; j0 += kc) {
+              const uint32_t nblk = (uint32_t)(min(kc, nk - j0) * nt);
+              mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+              mbar_expect_tx(&full_w[stage], nblk * blk);
+              uint8_t* dst = smem + stage * STAGE_BYTES;
+              if (blk == blk_smem) {
+                bulk_load(dst, src, nblk * blk, &full_w[stage], HINT_EVICT_FIRST);     // the whole stage: one copy
+              } else {
+                for (uint32_t i = 0; i < nblk; ++i)
+                  bulk_load(dst + i * blk_smem, src + i * blk, blk, &full_w[stage], HINT_EVICT_FIRST);
+              }
+              src += nblk * blk;
+              if (++stage == NS) { stage = 0; par ^= 1; }
+            }
           }
-          mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
-          mbar_expect_tx(&full_w[stage], W_STAGE);
-          if (wt) bulk_load(smem + stage * STAGE_BYTES, wt + (long)c * (BM * BK), W_STAGE, &full_w[stage], HINT_EVICT_FIRST);
-          else tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES, kc * BK, tile * BM, HINT_EVICT_FIRST);
-          *w_issued = ++issued;
-          if (++stage == NS) { stage = 0; par ^= 1; }
-          if (++kc == cur.nk) { kc = 0; ++tile; }
+        } else if (ph.type == PH_GEMM) {
+          const int2 r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
+          const int nk = ph.nk;
+          const CUtensorMap* tm = hdr.maps + ph.tmW;
+          const bf16* wt = ph.Wt;                            // tiled layout: chunk c is the 16 KB block c of the matrix
+          int tile = r.x / nk, kc = r.x % nk;
+          for (int c = r.x; c < r.y; ++c) {
+            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+            mbar_expect_tx(&full_w[stage], W_STAGE);
+            if (wt) bulk_load(smem + stage * STAGE_BYTES, wt + (long)c * (BM * BK), W_STAGE, &full_w[stage], HINT_EVICT_FIRST);
+            else tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES, kc * BK, tile * BM, HINT_EVICT_FIRST);
+            if (++stage == NS) { stage = 0; par ^= 1; }
+            if (++kc == nk) { kc = 0; ++tile; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      GemmCursor cur;
-      cur.init(hdr);
       int stage = 0, par = 0, acc = 0, acc_par = 0;
-      while (cur.next_phase(b, G)) {
-        int c = cur.c;
-        int tile = c / cur.nk;
-        while (c < cur.hi) {
-          const int seg_end = min(cur.hi, (tile + 1) * cur.nk);
-          mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * 32;
-          bool first = true;
-          for (; c < seg_end; ++c) {
-            mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
-            mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
+      for (int p = 0; p < hdr.n_phases; ++p) {
+        const Phase& ph = hdr.phases[p];
+        if (ph.type == PH_GEMM2) {
+          const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
+          const uint32_t blk_smem = (uint32_t)ph.s_blk_smem, x_off = (uint32_t)ph.s_xoff;
+          for (int ps = 0; ps < passes; ++ps) {
+            const int u = b * passes + ps;
+            if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
+            mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
             tc_fence_after();
-            const uint64_t da = make_desc(smem + stage * STAGE_BYTES);
-            const uint64_t db = make_desc(smem + stage * STAGE_BYTES + W_STAGE);
+            const uint32_t d_tmem = tmem_base + acc * 64;
+            for (int j0 = 0; j0 < nk; j0 += kc) {
+              const int nj = min(kc, nk - j0);
+              mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
+              mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
+              tc_fence_after();
+              const uint8_t* base = smem + stage * STAGE_BYTES;
+              for (int jj = 0; jj < nj; ++jj) {
+                const uint64_t db = make_desc(base + x_off + jj * X_STAGE);
+                for (int t = 0; t < nt; ++t) {
+                  const uint64_t da = make_desc(base + (uint32_t)(jj * nt + t) * blk_smem);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) tc_mma(d_tmem, da + 2 * k, db + 2 * k, (!first || k > 0) ? 1u : 0u);
-            tc_commit(&empty[stage]);
-            first = false;
-            if (++stage == NS) { stage = 0; par ^= 1; }
+                  for (int k = 0; k < BK / 16; ++k)
+                    tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (j0 | jj | k) ? 1u : 0u);
+                }
+              }
+              tc_commit(&empty[stage]);
+              if (++stage == NS) { stage = 0; par ^= 1; }
+            }
+            tc_commit(&tfull[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_par ^= 1;
           }
-          tc_commit(&tfull[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_par ^= 1;
-          ++tile;
+        } else if (ph.type == PH_GEMM) {
+          const int2 r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
+          const int nk = ph.nk;
+          int c = r.x;
+          int tile = c / nk;
+          while (c < r.y) {
+            const int seg_end = min(r.y, (tile + 1) * nk);
+            mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 64;
+            bool first = true;
+            for (; c < seg_end; ++c) {
+              mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
+              mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
+              tc_fence_after();
+              const uint64_t da = make_desc(smem + stage * STAGE_BYTES);
+              const uint64_t db = make_desc(smem + stage * STAGE_BYTES + W_STAGE);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) tc_mma(d_tmem, da + 2 * k, db + 2 * k, (!first || k > 0) ? 1u : 0u);
+              tc_commit(&empty[stage]);
+              first = false;
+              if (++stage == NS) { stage = 0; par ^= 1; }
+            }
+            tc_commit(&tfull[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_par ^= 1;
+            ++tile;
+          }
         }
       }
     }
   } else if (warp == 2) {
     // ===================== activation producer =====================
     if (lane == 0) {
-      GemmCursor cur;
-      cur.init(hdr);
       int stage = 0, par = 0;
-      while (cur.next_phase(b, G)) {
+      for (int p = 0; p < hdr.n_phases; ++p) {
+        const Phase& ph = hdr.phases[p];
+        if (ph.type != PH_GEMM2 && ph.type != PH_GEMM) continue;
+        int n_stages;                                        // stages of this CTA in the phase
+        int2 r = make_int2(0, 0);
+        if (ph.type == PH_GEMM2) {
+          int units = 0;
+          for (int ps = 0; ps < ph.s_passes; ++ps) {
+            const int u = b * ph.s_passes + ps;
+            units += ph.s_eper + (u < ph.s_erem ? 1 : 0) > 0 ? 1 : 0;
+          }
+          n_stages = units * ((ph.nk + ph.s_kc - 1) / ph.s_kc);
+        } else {
+          r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
+          n_stages = r.y - r.x;
+        }
+        if (n_stages <= 0) continue;
         // the token tile is produced by earlier phases of this launch: wait until all of them completed everywhere
-        const unsigned int need = (unsigned int)hdr.phases[cur.p].bars_before * (unsigned int)G;
-        // relaxed polling (no L1 invalidation storm); the tile itself is read by the TMA unit from L2, ordered behind the
-        // observed counter value by the proxy fence
+        // (relaxed polling, no L1 invalidation storm; the tile itself is read by the TMA unit from L2, ordered behind the
+        // observed counter value by the proxy fence)
+        const unsigned int need = (unsigned int)ph.bars_before * (unsigned int)G;
         while (ld_relaxed_u32(hdr.counters) < need) __nanosleep(64);
         fence_proxy_async();
-        const CUtensorMap* tm = hdr.maps + hdr.phases[cur.p].tmX;
-        int kc = (int)(cur.c % cur.nk);
-        for (int c = cur.c; c < cur.hi; ++c) {
-          mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
-          mbar_expect_tx(&full_x[stage], X_STAGE);
-          tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kc * BK, 0, HINT_EVICT_LAST);
-          if (++stage == NS) { stage = 0; par ^= 1; }
-          if (++kc == cur.nk) kc = 0;
-        }
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== L2 prefetcher =====================
-    // Tiled weights only: this CTA's chunk range of a GEMM phase is ONE contiguous byte range, prefetched into L2 in
-    // 64 KB pieces up to `pf_ahead` chunks ahead of the weight producer -- across phase boundaries, so HBM keeps
-    // streaming while the CTA sits in an epilogue / attention phase or a grid barrier with a full shared-memory ring.
-    if (lane == 0 && hdr.pf_ahead > 0) {
-      GemmCursor cur;
-      cur.init(hdr);
-      int idx = 0;                                       // chunks prefetched so far (program order)
-      constexpr int PIECE = 4;                           // chunks per prefetch instruction
-      while (cur.next_phase(b, G)) {
-        const bf16* wt = hdr.phases[cur.p].Wt;
-        const int n = cur.hi - cur.c;
-        if (!wt) { idx += n; continue; }
-        for (int c = cur.c; c < cur.hi; c += PIECE) {
-          const int m = min(PIECE, cur.hi - c);
-          while (idx >= *w_issued + hdr.pf_ahead) __nanosleep(200);
-          if (idx >= *w_issued + NS) bulk_prefetch_l2(wt + (long)c * (BM * BK), (uint32_t)m * W_STAGE);
-          idx += m;
+        if (ph.type == PH_GEMM2) {
+          const int kc = ph.s_kc, nk = ph.nk;
+          const uint32_t x_off = (uint32_t)ph.s_xoff;
+          const CUtensorMap* tm3 = ph.tmX3 >= 0 ? hdr.maps + ph.tmX3 : nullptr;
+          const CUtensorMap* tm = hdr.maps + ph.tmX;
+          const int spp = (nk + kc - 1) / kc;                // stages per pass: every pass walks the same k-chunks
+          for (int s = 0; s < n_stages; ++s) {
+            const int j0 = (s % spp) * kc;
+            const int nj = min(kc, nk - j0);
+            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+            mbar_expect_tx(&full_x[stage], nj * X_STAGE);
+            uint8_t* dst = smem + stage * STAGE_BYTES + x_off;
+            if (tm3 && nj == kc) {
+              tma_load_3d(tm3, &full_x[stage], dst, 0, 0, j0, HINT_EVICT_LAST);      // {64, 32, kc} box: kc blocks at once
+            } else {
+              for (int jj = 0; jj < nj; ++jj)
+                tma_load_2d(tm, &full_x[stage], dst + jj * X_STAGE, (j0 + jj) * BK, 0, HINT_EVICT_LAST);
+            }
+            if (++stage == NS) { stage = 0; par ^= 1; }
+          }
+        } else {
+          const CUtensorMap* tm = hdr.maps + ph.tmX;
+          int kc = r.x % ph.nk;
+          for (int c = r.x; c < r.y; ++c) {
+            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+            mbar_expect_tx(&full_x[stage], X_STAGE);
+            tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kc * BK, 0, HINT_EVICT_LAST);
+            if (++stage == NS) { stage = 0; par ^= 1; }
+            if (++kc == ph.nk) kc = 0;
+          }
         }
       }
     }
@@ -349,7 +390,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
               mbar_wait(&tfull[acc], acc_par);
               tc_fence_after();
               float v[8];
-              tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 32 + cg * 8, v);
+              tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 64 + cg * 8, v);
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -366,6 +407,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
             }
           }
         } break;
+        case PH_GEMM2:
+          slab_epilogue(ph, epoch, b, G, wtid, tmem_base, acc, acc_par, tfull, tempty, *reinterpret_cast<SlabRed*>(team_base));
+          break;
         case PH_EPI: epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
@@ -427,7 +471,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
 // =================================================================================================================
 struct vs_program {
   std::vector<vs::Phase> phases;
-  struct MapReq { const void* ptr; long ld; int rows, cols, box_rows; };
+  struct MapReq { const void* ptr; long ld; int rows, cols, box_rows, box_depth; };   // box_depth > 0: 3-D {64, rows, depth}
+  struct SlabReg { const void* w; const void* slab; int pair, grid, packed; };
+  std::vector<SlabReg> slabs; // row-major weight pointer -> slab image (vs_program_register_slab)
+  int last_ssq_rows = 0;      // rows of [.][32] partial sums the last residual epilogue left in the ssq workspace
+  bool x3d = true;            // activations of a slab GEMM through ONE 3-D tensor-map load per stage
   std::vector<MapReq> maps;
   std::vector<int> tables;    // chunk ranges per CTA + contributor info per tile of every GEMM phase
   std::vector<std::pair<const void*, const void*>> tiled;   // row-major weight pointer -> tiled copy
@@ -462,23 +510,25 @@ int pfail(int code, const char* where, const std::string& what) {
   return code;
 }
 
-int device_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        sms <= 0)
-      sms = 148;
+int device_sms() {     // of the CURRENT device (one process may drive several GPUs)
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    cache[dev] = sms;
   }
-  return sms;
+  return cache[dev];
 }
 
-int add_map(vs_program* pg, const void* ptr, long ld, int rows, int cols, int box_rows) {
+int add_map(vs_program* pg, const void* ptr, long ld, int rows, int cols, int box_rows, int box_depth = 0) {
   for (size_t i = 0; i < pg->maps.size(); ++i) {
     const auto& m = pg->maps[i];
-    if (m.ptr == ptr && m.ld == ld && m.rows == rows && m.cols == cols && m.box_rows == box_rows) return (int)i;
+    if (m.ptr == ptr && m.ld == ld && m.rows == rows && m.cols == cols && m.box_rows == box_rows && m.box_depth == box_depth)
+      return (int)i;
   }
-  pg->maps.push_back({ptr, ld, rows, cols, box_rows});
+  pg->maps.push_back({ptr, ld, rows, cols, box_rows, box_depth});
   return (int)pg->maps.size() - 1;
 }
 
@@ -531,6 +581,42 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
     return pfail(VS_ERR_INVALID, "vs_program_add_linear", "SWIGLU / HEADS need N % 128 == 0");
   const int G = pg->grid ? pg->grid : device_sms();
   pg->grid = G;
+  // ---- slab path (slab.h): a registered slab image of these weights for this grid -> whole rows per CTA, epilogue from
+  // TMEM inside the same phase
+  {
+    const int pair = (a.epi == EPI_SWIGLU || a.epi == EPI_HEADS) ? 1 : 0;
+    const vs_program::SlabReg* reg = nullptr;
+    if (a.ldw == a.K)
+      for (const auto& r : pg->slabs)
+        if (r.w == a.W && r.pair == pair && r.grid == G) reg = &r;
+    SlabPlan sp;
+    if (reg && slab_plan(a.N, a.K, pair, G, reg->packed, &sp)) {
+      Phase g = blank(PH_GEMM2, a.T);
+      g.N = a.N;
+      g.nk = sp.nk;
+      g.Wt = static_cast<const bf16*>(reg->slab);
+      g.s_pair = sp.pair; g.s_ntiles = sp.n_tiles; g.s_passes = sp.passes; g.s_rows_alloc = sp.rows_alloc;
+      g.s_blk_bytes = sp.blk_bytes; g.s_blk_smem = sp.blk_smem; g.s_kc = sp.kc; g.s_xoff = sp.x_off;
+      g.s_eper = sp.e_per; g.s_erem = sp.e_rem; g.s_unit_stride = sp.unit_stride;
+      g.tmX = add_map(pg, a.X, a.ldx, a.T, a.K, VS_TOK);
+      g.tmX3 = (pg->x3d && sp.kc > 1) ? add_map(pg, a.X, a.ldx, a.T, a.K, VS_TOK, sp.kc) : -1;
+      g.epi = a.epi;
+      g.bias = a.bias;
+      g.Y = a.Y; g.ldy = a.ldy; g.R = a.R; g.ldr = a.ldr;
+      g.ssq = ssq;
+      if (ssq == PROG_WS_SSQ) {
+        if ((size_t)G * VS_TOK > pg->ssq_floats) pg->ssq_floats = (size_t)G * VS_TOK;
+        pg->last_ssq_rows = G;
+      }
+      g.n_q_tiles = a.n_q_tiles; g.n_k_tiles = a.n_k_tiles; g.rope = a.rope;
+      g.cos = a.cos; g.sin = a.sin; g.pos_ids = a.pos_ids;
+      g.Qout = a.Qout; g.q_head_stride = a.q_head_stride;
+      g.Kout = a.Kout; g.Vout = a.Vout; g.kv_head_stride = a.kv_head_stride;
+      g.kv_row_base = a.kv_row_base; g.kv_row_off = a.kv_row_off;
+      pg->phases.push_back(g);
+      return VS_OK;
+    }
+  }
   Phase g = blank(PH_GEMM, a.T);
   g.n_tiles = (a.N + BM - 1) / BM;
   g.nk = a.K / BK;
@@ -574,7 +660,10 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
   e.bias = a.bias;
   e.Y = a.Y; e.ldy = a.ldy; e.R = a.R; e.ldr = a.ldr;
   e.ssq = ssq;
-  if (ssq == PROG_WS_SSQ && (size_t)g.n_tiles * VS_TOK > pg->ssq_floats) pg->ssq_floats = (size_t)g.n_tiles * VS_TOK;
+  if (ssq == PROG_WS_SSQ) {
+    if ((size_t)g.n_tiles * VS_TOK > pg->ssq_floats) pg->ssq_floats = (size_t)g.n_tiles * VS_TOK;
+    pg->last_ssq_rows = g.n_tiles;
+  }
   e.n_q_tiles = a.n_q_tiles; e.n_k_tiles = a.n_k_tiles; e.rope = a.rope;
   e.cos = a.cos; e.sin = a.sin; e.pos_ids = a.pos_ids;
   e.Qout = a.Qout; e.q_head_stride = a.q_head_stride;
@@ -592,6 +681,17 @@ int prog_add_norm(vs_program* pg, const bf16* x, long ldx, const bf16* w, bf16* 
   // into that epilogue.  Each (tile, 8-token group) item publishes its sums of squares, waits on the group's arrival
   // counter for the other tiles and normalises the values it still holds in registers -- one phase, one grid barrier
   // and one read of the rows less.  All items of a group wait for each other, so every item needs its own team.
+  if (ssq_in == PROG_WS_SSQ && pg->last_ssq_rows > 0) ssq_tiles = pg->last_ssq_rows;
+  if (pg->fuse_norm && ssq_in && !pg->phases.empty()) {
+    Phase& e = pg->phases.back();
+    if (e.type == PH_GEMM2 && e.epi == EPI_RESID && e.ssq == ssq_in && e.Y == x && e.ldy == ldx && e.T == T && e.N == H &&
+        e.s_passes == 1 && !e.w) {
+      e.w = w; e.dst = y; e.ldd = ldy; e.H = H; e.eps = eps;
+      e.norm_cnt = reinterpret_cast<unsigned int*>(uintptr_t(pg->tile_cnt_count + 1));
+      pg->tile_cnt_count += 1;
+      return VS_OK;
+    }
+  }
   if (pg->fuse_norm && pg->fuse_epilogue && ssq_in && !pg->phases.empty()) {
     Phase& e = pg->phases.back();
     const int G = pg->grid ? pg->grid : device_sms();
@@ -609,6 +709,13 @@ int prog_add_norm(vs_program* pg, const bf16* x, long ldx, const bf16* w, bf16* 
   ph.ssq_in = ssq_in; ph.ssq_tiles = ssq_tiles;
   pg->phases.push_back(ph);
   return VS_OK;
+}
+
+bool prog_last_is_residual_of(const vs_program* pg, const bf16* x, long ldx, int T, int H) {
+  if (!pg || pg->phases.empty()) return false;
+  const Phase& e = pg->phases.back();
+  return (e.type == PH_EPI || e.type == PH_GEMM2) && e.epi == EPI_RESID && e.ssq == PROG_WS_SSQ && e.Y == x && e.ldy == ldx &&
+         e.T == T && e.N == H;
 }
 
 int prog_add_rows(vs_program* pg, const bf16* src, long lds, const int* idx, int n_src_rows, int broadcast, bf16* dst,
@@ -798,6 +905,8 @@ int vs_program_create(vs_program** out) {
   if (e) (*out)->fuse_norm = atoi(e) != 0;
   e = getenv("VS_SPIN_NS");
   if (e) (*out)->spin_ns = atoi(e);
+  e = getenv("VS_X3D");
+  if (e) (*out)->x3d = atoi(e) != 0;
   return VS_OK;
 }
 
@@ -824,6 +933,7 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
     pg->fuse_norm = value != 0;
   }
   else if (!strcmp(name, "spin_ns")) pg->spin_ns = value;
+  else if (!strcmp(name, "x3d")) pg->x3d = value != 0;
 
   else if (!strcmp(name, "grid")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "grid must be set before adding phases");
@@ -844,6 +954,17 @@ int vs_program_register_tiled(vs_program* pg, const void* w_row_major, const voi
   if (!pg || !w_row_major || !w_tiled) return vs::pfail(VS_ERR_INVALID, "vs_program_register_tiled", "null argument");
   if (reinterpret_cast<uintptr_t>(w_tiled) % 1024) return vs::pfail(VS_ERR_INVALID, "vs_program_register_tiled", "tiled weights must be 1024-byte aligned");
   pg->tiled.emplace_back(w_row_major, w_tiled);
+  return VS_OK;
+}
+
+int vs_device_sms(void) { return vs::device_sms(); }
+
+int vs_program_register_slab(vs_program* pg, const void* w_row_major, const void* w_slab, int epi, int grid) {
+  if (!pg || !w_row_major || !w_slab) return vs::pfail(VS_ERR_INVALID, "vs_program_register_slab", "null argument");
+  if (reinterpret_cast<uintptr_t>(w_slab) % 128) return vs::pfail(VS_ERR_INVALID, "vs_program_register_slab", "slab image must be 128-byte aligned");
+  if (grid <= 0) grid = vs::device_sms();
+  const int pair = (epi == vs::EPI_SWIGLU || epi == vs::EPI_HEADS) ? 1 : 0;
+  pg->slabs.push_back({w_row_major, w_slab, pair, grid, vs::slab_default_packed() ? 1 : 0});
   return VS_OK;
 }
 
@@ -868,14 +989,35 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
   for (size_t i = 0; i < pg->maps.size(); ++i) {
     const auto& m = pg->maps[i];
     CUtensorMap tm;
-    cuuint64_t dims[2] = {(cuuint64_t)m.cols, (cuuint64_t)m.rows};
-    cuuint64_t strides[1] = {(cuuint64_t)m.ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)m.box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(m.ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return pfail(VS_ERR_CUDA, "vs_program_commit", "cuTensorMapEncodeTiled failed");
+    CUresult r;
+    if (m.box_depth > 0) {
+      // [rows][cols] viewed as {64 columns, rows, cols / 64 chunks}: one box = box_depth consecutive [rows x 64] blocks,
+      // each landing as its own 128-byte-swizzled 4 KB tile (the activation side of a slab stage)
+      cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)m.rows, (cuuint64_t)(m.cols / BK)};
+      cuuint64_t strides[2] = {(cuuint64_t)m.ld * 2, (cuuint64_t)BK * 2};
+      cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)m.box_rows, (cuuint32_t)m.box_depth};
+      cuuint32_t estr[3] = {1, 1, 1};
+      r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(m.ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t dims[2] = {(cuuint64_t)m.cols, (cuuint64_t)m.rows};
+      cuuint64_t strides[1] = {(cuuint64_t)m.ld * 2};
+      cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)m.box_rows};
+      cuuint32_t estr[2] = {1, 1};
+      r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(m.ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+      if (m.box_depth > 0) {   // the driver refused the 3-D view: fall back to kc 2-D loads per stage
+        for (auto& ph : pg->phases)
+          if (ph.type == PH_GEMM2 && ph.tmX3 == (int)i) ph.tmX3 = -1;
+        memset(&tm, 0, sizeof(tm));
+      } else {
+        return pfail(VS_ERR_CUDA, "vs_program_commit", "cuTensorMapEncodeTiled failed");
+      }
+    }
     memcpy(host.data() + pg->off_maps + i * sizeof(CUtensorMap), &tm, sizeof(tm));
   }
   memcpy(host.data() + pg->off_tables, pg->tables.data(), pg->tables.size() * sizeof(int));
@@ -890,6 +1032,7 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
     if (ph.norm_cnt)
       ph.norm_cnt = reinterpret_cast<unsigned int*>(pg->ws + pg->off_tilecnt) + (reinterpret_cast<uintptr_t>(ph.norm_cnt) - 1);
     if (ph.type == PH_GEMM || ph.type == PH_EPI) ph.partials = partials;
+    if (ph.type == PH_GEMM2 && ph.tmX3 < 0) ph.tmX3 = -1;
     if (ph.ssq == PROG_WS_SSQ) ph.ssq = reinterpret_cast<float*>(pg->ws + pg->off_ssq);
     if (ph.ssq_in == PROG_WS_SSQ) ph.ssq_in = reinterpret_cast<float*>(pg->ws + pg->off_ssq);
     if (ph.keys == PROG_WS_KEYS) ph.keys = reinterpret_cast<unsigned long long*>(pg->ws + pg->off_keys);
@@ -900,11 +1043,15 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
   if (cudaMemcpyAsync(pg->ws, host.data(), host.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess)
     return pfail(VS_ERR_CUDA, "vs_program_commit", cudaGetErrorString(cudaGetLastError()));
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return pfail(VS_ERR_CUDA, "vs_program_commit", cudaGetErrorString(e));
-    attr_set = true;
+  {
+    static bool attr_set[64] = {false};      // a function attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e != cudaSuccess) return pfail(VS_ERR_CUDA, "vs_program_commit", cudaGetErrorString(e));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   pg->committed = true;
   return VS_OK;

@@ -24,7 +24,9 @@ enum PhaseType : int {
   PH_TREE = 9,      // integer tree bookkeeping (level0 / expand / build / accept / commit / merges) on CTA 0
   PH_SPLICE = 10,   // KV-cache splice
   PH_LSM_CAND = 11, // log-softmax + top-k, step 2: k best log-probs per (row, slice); merged by the next tree phase
-  PH_ATTN_FUSED = 12 // both attention passes in one phase (every (head, split) item resident; per-head arrival counters)
+  PH_ATTN_FUSED = 12, // both attention passes in one phase (every (head, split) item resident; per-head arrival counters)
+  PH_GEMM2 = 13      // slab GEMM (slab.h): every CTA streams whole output rows over the full K range and runs the fused
+                     // epilogue (and, optionally, the following RMSNorm) straight from TMEM -- no partial tiles, no PH_EPI
 };
 
 enum TreeOp : int {
@@ -56,6 +58,12 @@ struct Phase {
   const bf16* R; long ldr;
   float* ssq;                 // residual epilogue: [n_tiles][32] sums of squares of the new rows (or null)
   unsigned int* norm_cnt;     // PH_EPI with a folded-in RMSNorm (`w` != null): [4] arrivals per group of 8 token rows, monotonic
+                              // (PH_GEMM2: [1] arrivals of all CTAs)
+  // ---- PH_GEMM2 (slab layout, slab.h); Wt = the slab image, nk / N / T / tmX3 / the epilogue fields as above
+  int s_pair, s_ntiles, s_passes, s_rows_alloc, s_blk_bytes, s_blk_smem, s_kc, s_xoff, s_eper, s_erem;
+  long s_unit_stride;
+  int tmX3;                   // 3-D tensor map of the activations: box {64 columns, 32 rows, kc chunks} (-1: kc 2-D loads)
+                              // (`ssq` of a PH_GEMM2 residual epilogue is [grid][32]: one row of partial sums per CTA)
   int n_q_tiles, n_k_tiles, rope;
   const bf16* cos; const bf16* sin; const int* pos_ids;
   bf16* Qout; long q_head_stride;
@@ -107,6 +115,9 @@ namespace vs {
 int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq);
 int prog_add_norm(vs_program* pg, const bf16* x, long ldx, const bf16* w, bf16* y, long ldy, int T, int H, float eps,
                   const float* ssq_in, int ssq_tiles);
+// true when the last phase of the program is a residual epilogue that wrote exactly the rows x[T][H] and left their sums
+// of squares in the program's ssq workspace
+bool prog_last_is_residual_of(const vs_program* pg, const bf16* x, long ldx, int T, int H);
 int prog_add_rows(vs_program* pg, const bf16* src, long lds, const int* idx, int n_src_rows, int broadcast, bf16* dst,
                   long ldd, int T, int H);
 int prog_add_attention(vs_program* pg, const AttnArgs& a);

@@ -160,12 +160,15 @@ extern "C" {
 
 int vs_program_add_linear(vs_program* pg, const vs_linear_args* a) {
   REQUIRE(pg && a && a->X && a->W, "null operand");
-  return vs::prog_add_linear(pg, to_gemm(a), nullptr);
+  // a residual epilogue leaves the sums of squares of its new rows in the program's workspace: an RMSNorm of exactly
+  // those rows added right behind it (the usual next step) starts from them / is folded into the epilogue
+  return vs::prog_add_linear(pg, to_gemm(a), a->epi == vs::EPI_RESID && a->N % 128 == 0 ? PROG_WS_SSQ : nullptr);
 }
 int vs_program_add_rmsnorm(vs_program* pg, const void* x, int64_t ldx, const void* weight, void* y, int64_t ldy, int T,
                            int H, float eps) {
   REQUIRE(pg && x && weight && y, "null operand");
-  return vs::prog_add_norm(pg, B(x), ldx, B(weight), B(y), ldy, T, H, eps, nullptr, 0);
+  const bool after_resid = vs::prog_last_is_residual_of(pg, B(x), ldx, T, H);
+  return vs::prog_add_norm(pg, B(x), ldx, B(weight), B(y), ldy, T, H, eps, after_resid ? PROG_WS_SSQ : nullptr, H / 128);
 }
 int vs_program_add_gather_rows(vs_program* pg, const void* src, int64_t lds, const int32_t* idx, void* dst, int64_t ldd,
                                int T, int H) {

@@ -329,6 +329,205 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// PH_GEMM2 epilogue (slab.h): the 16 worker warps finish this CTA's output rows straight from TMEM -- nothing is
+// exchanged with other CTAs except, for a residual epilogue, one row of sums of squares for the RMSNorm that follows.
+// warp = (lane quarter q of the accumulators: tile rows 32q .. 32q+31, token group cg: columns 8cg .. 8cg+7);
+// thread = (tile row 32q + lane, 8 tokens) of both accumulators of the pass: the two members of a gate|up or rotate-half
+// pair sit in the same lane of accumulator 0 and 1.
+// ---------------------------------------------------------------------------------------------------------------
+struct SlabRed {
+  float part[4][VS_TOK];     // per lane quarter: sums of squares of its rows, per token
+  float rstd[VS_TOK];
+};
+
+__device__ __noinline__ void slab_epilogue(const Phase& ph, unsigned int epoch, int b, int G, int wtid, uint32_t tmem_base,
+                                           int& acc, int& acc_par, uint64_t* tfull, uint64_t* tempty, SlabRed& red) {
+  const int wwarp = wtid >> 5, lane = wtid & 31, quarter = wwarp & 3, cg = wwarp >> 2;
+  const int T = ph.T, epi = ph.epi;
+  const int passes = ph.s_passes, n_tiles = ph.s_ntiles, rows_alloc = ph.s_rows_alloc, pair = ph.s_pair;
+  const int e_per = ph.s_eper, e_rem = ph.s_erem;
+  const int row = quarter * 32 + lane;                 // accumulator lane = row of the tile
+  const int t0 = cg * 8;                               // first token of this thread
+  const bool resid = epi == EPI_RESID, heads = epi == EPI_HEADS;
+  float* ssq = ph.ssq;
+  const bf16* nw = ph.w;                               // folded-in RMSNorm (prog_add_norm) or null; then passes == 1
+  float ssq_acc = 0.f;                                 // threads wtid < 32: token wtid, summed over the passes
+  float yv[2][8];                                      // the new rows of the (single) pass, for the folded norm
+  int n_keep[2] = {-1, -1};
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yv[j][i] = 0.f;
+
+#pragma unroll 1
+  for (int ps = 0; ps < passes; ++ps) {
+    const int u = b * passes + ps;
+    const int e_lo = u * e_per + min(u, e_rem), cnt = e_per + (u < e_rem ? 1 : 0);
+    if (cnt == 0) continue;                            // (uniform over the CTA: no stages were streamed either)
+    // output feature of this thread in accumulator 0 / 1, -1 = this lane holds no row
+    int n[2] = {-1, -1};
+    if (pair) {
+      if (row < cnt) {
+        const int e = e_lo + row;
+        n[0] = (e >> 6) * 128 + (e & 63);
+        n[1] = n[0] + 64;
+      }
+    } else if (row < rows_alloc) {
+      if (row < cnt) n[0] = e_lo + row;
+      if (n_tiles == 2 && rows_alloc + row < cnt) n[1] = e_lo + rows_alloc + row;
+    }
+    // ---- operand loads that do not depend on the accumulators: in flight while the weight stream finishes
+    float bias[2] = {0.f, 0.f};
+    if (ph.bias) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bias[j] = bf2f(ph.bias[max(n[j], 0)]);
+    }
+    unsigned short rraw[2][8];
+    if (resid) {
+      const bf16* R = ph.R;
+      const long ldr = ph.ldr;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rraw[j][i] = __ldcg(reinterpret_cast<const unsigned short*>(R + (long)min(t0 + i, T - 1) * ldr + max(n[j], 0)));
+    }
+    const int e_me = e_lo + min(row, cnt - 1);         // pair element of this lane (clamped)
+    const int hh = e_me >> 6, d = e_me & 63;           // HEADS: head (over q | k | v) and dim < 64
+    const bool is_q = hh < ph.n_q_tiles, is_k = !is_q && hh < ph.n_q_tiles + ph.n_k_tiles;
+    const bool rope = heads && ph.rope && (is_q || is_k);
+    bf16 cs[4][8];
+    if (heads && ph.rope) {                             // (uniform branch; lanes of v heads load and ignore)
+      int pos[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pos[i] = __ldcg(ph.pos_ids + min(t0 + i, T - 1));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        cs[0][i] = ph.cos[(long)pos[i] * 128 + d];      cs[1][i] = ph.sin[(long)pos[i] * 128 + d];
+        cs[2][i] = ph.cos[(long)pos[i] * 128 + 64 + d]; cs[3][i] = ph.sin[(long)pos[i] * 128 + 64 + d];
+      }
+    }
+    // ---- the accumulators of this pass
+    mbar_wait(&tfull[acc], acc_par);
+    tc_fence_after();
+    float a[2][8];
+    tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 64 + t0, a[0]);
+    if (n_tiles == 2) tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 64 + 32 + t0, a[1]);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[1][i] = 0.f;
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[acc]);
+    acc ^= 1;
+    if (acc == 0) acc_par ^= 1;
+
+    if (epi == EPI_SWIGLU) {
+      if (n[0] >= 0) {
+        bf16* Y = ph.Y + (e_lo + row);                  // feature index = pair element
+        const long ldy = ph.ldy;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (t0 + i < T) {
+            const float g = rbf(pg_silu(rbf(a[0][i])));               // act_fn(gate) rounds, then * up rounds
+            Y[(long)(t0 + i) * ldy] = f2bf(g * rbf(a[1][i]));
+          }
+      }
+    } else if (heads) {
+      if (n[0] >= 0) {
+        const int row_base = (ph.kv_row_base ? __ldcg(ph.kv_row_base) : 0) + ph.kv_row_off;
+        const int head = is_q ? hh : (is_k ? hh - ph.n_q_tiles : hh - ph.n_q_tiles - ph.n_k_tiles);
+        bf16* dst = is_q ? ph.Qout + (long)head * ph.q_head_stride
+                         : (is_k ? ph.Kout : ph.Vout) + (long)head * ph.kv_head_stride + (long)row_base * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (t0 + i < T) {
+            const float x1 = rbf(a[0][i] + bias[0]), x2 = rbf(a[1][i] + bias[1]);
+            float o1 = x1, o2 = x2;
+            if (rope) {   // rotate-half RoPE with three bf16 roundings (cnets_ours.py:117-118)
+              o1 = rbf(x1 * bf2f(cs[0][i])) + rbf(-x2 * bf2f(cs[1][i]));
+              o2 = rbf(x2 * bf2f(cs[2][i])) + rbf(x1 * bf2f(cs[3][i]));
+            }
+            dst[(long)(t0 + i) * 128 + d] = f2bf(o1);
+            dst[(long)(t0 + i) * 128 + 64 + d] = f2bf(o2);
+          }
+      }
+    } else {
+      // STORE / RESID (+ this CTA's sums of squares of the new rows for the RMSNorm that follows)
+      bf16* Y = ph.Y;
+      const long ldy = ph.ldy;
+      float q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (n[j] < 0) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = a[j][i] + bias[j];
+          if (resid) v = bf_bits(rraw[j][i]) + rbf(v);                // Linear output rounds to bf16, then the add rounds again
+          const bf16 y = f2bf(v);
+          yv[j][i] = bf2f(y);
+          if (t0 + i < T) {
+            Y[(long)(t0 + i) * ldy + n[j]] = y;
+            q[i] += bf2f(y) * bf2f(y);
+          }
+        }
+      }
+      if (ssq) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float s = warp_sum(q[i]);
+          if (lane == 0) red.part[quarter][t0 + i] = s;
+        }
+        named_bar_sync(1, PG_WORKERS);
+        if (wtid < VS_TOK) ssq_acc += (red.part[0][wtid] + red.part[1][wtid]) + (red.part[2][wtid] + red.part[3][wtid]);
+        named_bar_sync(1, PG_WORKERS);                                 // `part` is free for the next pass
+      }
+      n_keep[0] = n[0];
+      n_keep[1] = n[1];
+    }
+  }
+  if (ssq) {
+    if (wtid < VS_TOK) ssq[b * VS_TOK + wtid] = ssq_acc;              // [grid][32]; tokens >= T hold 0
+  }
+  if (nw) {
+    // LlamaRMSNorm of the finished rows: publish this CTA's sums of squares, wait until every CTA of the grid has, then
+    // normalise the values still held in registers (y = weight * bf16(x * rstd): two bf16 roundings, cnets_ours.py:523-527)
+    float wj[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) wj[j] = bf2f(nw[max(n_keep[j], 0)]);   // in flight during the exchange
+    named_bar_sync(1, PG_WORKERS);
+    if (wtid == 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ph.norm_cnt) : "memory");
+      const unsigned int want = (epoch + 1u) * (unsigned int)G;
+      while (ld_relaxed_u32(ph.norm_cnt) < want) {
+      }
+    }
+    named_bar_sync(1, PG_WORKERS);
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq) {                                   // warp w: tokens 2w, 2w+1
+      const int t = 2 * wwarp + qq;
+      float ss = 0.f;
+      for (int bb = lane; bb < G; bb += 32) ss += __ldcg(ssq + bb * VS_TOK + t);   // fixed order
+      ss = warp_sum(ss);
+      if (lane == 0) red.rstd[t] = 1.0f / sqrtf(ss / (float)ph.H + ph.eps);
+    }
+    named_bar_sync(1, PG_WORKERS);
+    bf16* X = ph.dst;
+    const long ldd = ph.ldd;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (n_keep[j] < 0) continue;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (t0 + i < T) X[(long)(t0 + i) * ldd + n_keep[j]] = f2bf(wj[j] * rbf(yv[j][i] * red.rstd[t0 + i]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // PH_NORM: item = (token row, quarter of the row).  y = weight * bf16(x * rsqrt(mean(x^2) + eps)).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void norm_phase(const Phase& ph, int gteam, int n_teams, int tt, float* red, TeamSync sync) {

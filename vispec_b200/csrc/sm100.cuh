@@ -45,6 +45,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -61,10 +69,14 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
       "l"(desc_a), "l"(desc_b), "r"(IDESC), "r"(accumulate)
       : "memory");
 }
-// K-major operand tile [rows][64 bf16] with 128-byte swizzle: SBO = 1024 B between 8-row groups, version 1
+// K-major operand tile [rows][64 bf16] with 128-byte swizzle: SBO = 1024 B between 8-row groups, version 1.
+// A tile that does not start on a 1024-byte boundary of the swizzle pattern (the packed blocks of slab.h start every
+// rows * 128 bytes) carries base_offset = (start address >> 7) & 7 in bits [49, 52), as the PTX ISA prescribes; for an
+// aligned tile the field is 0.
 __device__ __forceinline__ uint64_t make_desc(const void* smem_tile) {
   uint64_t addr = smem_u32(smem_tile);
-  return ((addr & 0x3FFFFull) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  return ((addr & 0x3FFFFull) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (((addr >> 7) & 7ull) << 49) |
+         (2ull << 61);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];

@@ -29,6 +29,18 @@ def use_tiled() -> bool:
     return os.environ.get("VS_TILED", "1") != "0"
 
 
+def weight_layout() -> str:
+    """HBM layout of the decode weights streamed by the program kernel: "slab" (default, round 2: whole output rows per
+    CTA, epilogue from TMEM -- csrc/slab.h), "tiled" (round 1: 16 KB tiles, stream-K + partial-tile epilogues) or
+    "rowmajor" (tensor maps over the row-major copy).  VS_LAYOUT / VS_TILED=0 select the older ones for A/B runs."""
+    if not use_tiled():
+        return "rowmajor"
+    v = os.environ.get("VS_LAYOUT", "slab")
+    if v not in ("slab", "tiled", "rowmajor"):
+        raise ValueError(f"VS_LAYOUT={v!r}: expected slab, tiled or rowmajor")
+    return v
+
+
 def use_programs() -> bool:
     """The persistent program kernel (one launch per step) is the product path; VS_MULTI_KERNEL=1 selects the
     one-launch-per-op path (same kernels' arithmetic, kept for A/B measurements and as a cross-check)."""
@@ -124,6 +136,39 @@ def pack_weight_tiles(w: torch.Tensor) -> torch.Tensor:
     packed.copy_(out.view(-1))
     packed._vs_storage = buf
     return packed
+
+
+def pack_weight_slab(w: torch.Tensor, epi: int) -> torch.Tensor:
+    """Row-major [N,K] bf16 -> the slab image of include/vispec_b200.h (vs_slab_pack) for this device's SM count; `epi`
+    picks the row pairing (L.EPI_SWIGLU / L.EPI_HEADS keep the two members of a pair in one accumulator lane).
+    Returns None for shapes the layout does not cover (the linear then keeps the stream-K path)."""
+    lib = L.load()
+    n, k = w.shape
+    with torch.cuda.device(w.device):
+        nbytes = lib.vs_slab_bytes(n, k, epi, 0)
+        if nbytes == 0:
+            return None
+        buf = torch.empty(nbytes // 2 + 64, dtype=w.dtype, device=w.device)
+        off = ((-buf.data_ptr()) % 128) // 2
+        slab = buf[off:off + nbytes // 2]
+        L.pcheck(lib.vs_slab_pack(w.data_ptr(), w.stride(0), n, k, epi, 0, slab.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream), "vs_slab_pack")
+    slab._vs_storage = buf
+    slab._vs_epi = epi
+    return slab
+
+
+def pack_decode_weight(w: torch.Tensor, epi: int):
+    """(row-major weight, streamed copy, epi) in the configured layout, or None when the row-major copy is streamed."""
+    lay = weight_layout()
+    if lay == "slab":
+        s = pack_weight_slab(w, epi)
+        if s is not None:
+            return (w, s, epi)
+        lay = "tiled"
+    if lay == "tiled":
+        return (w, pack_weight_tiles(w), -1)
+    return None
 
 
 def _stream() -> int:
@@ -242,11 +287,13 @@ class TargetEngine:
         self._layer_arr = arr
         # tiled copies for the persistent program kernel (the row-major copies stay for the prefill / per-op path)
         self.tiled = []
-        if use_programs() and use_tiled():
+        if use_programs():
+            epis = (("w_qkv", L.EPI_HEADS), ("w_o", L.EPI_RESID), ("w_gateup", L.EPI_SWIGLU), ("w_down", L.EPI_RESID))
             for t in self.layers_t:
-                for k in ("w_qkv", "w_o", "w_gateup", "w_down"):
-                    self.tiled.append((t[k], pack_weight_tiles(t[k])))
-            self.tiled.append((self.lm_head, pack_weight_tiles(self.lm_head)))
+                for k, epi in epis:
+                    self.tiled.append(pack_decode_weight(t[k], epi))
+            self.tiled.append(pack_decode_weight(self.lm_head, L.EPI_STORE))
+            self.tiled = [p for p in self.tiled if p is not None]
         self.dims = _dims(cfg.hidden, cfg.inter, cfg.heads, cfg.kv_heads, cfg.vocab, cfg.layers, cfg.eps)
         if cfg.attn_impl not in ("eager", "sdpa"):
             raise NotImplementedError(f"attention implementation {cfg.attn_impl!r}")
@@ -529,9 +576,11 @@ class DraftEngine:
         self.adpt_q[:, :cfg.num_q] = g("imadpt.q").view(cfg.num_q, nh, 128).transpose(0, 1)
         self.lm_head = lm_head
         self.tiled = []                                   # the target engine's lm_head pair is added by bind_tiled
-        if use_programs() and use_tiled():
-            for w in (self.w_qkv, self.w_o, self.w_gateup, self.w_down, self.w_fc, self.w_img_fc):
-                self.tiled.append((w, pack_weight_tiles(w)))
+        if use_programs():
+            for w, epi in ((self.w_qkv, L.EPI_HEADS), (self.w_o, L.EPI_RESID), (self.w_gateup, L.EPI_SWIGLU),
+                           (self.w_down, L.EPI_RESID), (self.w_fc, L.EPI_STORE), (self.w_img_fc, L.EPI_STORE)):
+                self.tiled.append(pack_decode_weight(w, epi))
+            self.tiled = [p for p in self.tiled if p is not None]
         # Draft positions follow the UNCOMPRESSED sequence index (image tokens keep their original positions,
         # cnets_ours.py:932-937), so they run up to the target's KV length, not the draft's max_position_embeddings: the
         # tables cover both (rows < cfg.max_pos equal the reference's; it raises an index error beyond them)

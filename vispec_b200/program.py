@@ -40,17 +40,28 @@ class Program:
         L.pcheck(self.lib.vs_program_set_option(self.h, name.encode(), int(value)), "vs_program_set_option")
 
     def register_tiled(self, pairs):
-        """pairs of (row-major weight tensor, tiled copy from engine.pack_weight_tiles): linears added afterwards that
-        use one of these weights stream the tiled copy (contiguous 16 KB blocks, L2 prefetch)."""
+        """Streamed copies of decode weights.  Items are (row-major weight, copy[, epi]): epi >= 0 -> `copy` is the slab
+        image of engine.pack_weight_slab for that epilogue class (whole rows per CTA, epilogue from TMEM); epi < 0 or
+        absent -> the tiled copy of engine.pack_weight_tiles (16 KB tiles, stream-K).  Linears added afterwards that use
+        one of these weights stream the copy instead of the row-major matrix."""
         self._tiled_refs = getattr(self, "_tiled_refs", []) + list(pairs)
-        for w, wt in pairs:
-            L.pcheck(self.lib.vs_program_register_tiled(self.h, w.data_ptr(), wt.data_ptr()), "vs_program_register_tiled")
+        with torch.cuda.device(self.device):
+            for item in pairs:
+                w, wt = item[0], item[1]
+                epi = item[2] if len(item) > 2 else -1
+                if epi >= 0:
+                    L.pcheck(self.lib.vs_program_register_slab(self.h, w.data_ptr(), wt.data_ptr(), epi, 0),
+                             "vs_program_register_slab")
+                else:
+                    L.pcheck(self.lib.vs_program_register_tiled(self.h, w.data_ptr(), wt.data_ptr()),
+                             "vs_program_register_tiled")
         return self
 
     def add(self, fn_name: str, *args):
         """Call `vs_program_add_<fn_name>(program, *args)`."""
         fn = getattr(self.lib, "vs_program_add_" + fn_name)
-        L.pcheck(fn(self.h, *args), "vs_program_add_" + fn_name)
+        with torch.cuda.device(self.device):          # the grid size is the SM count of the program's device
+            L.pcheck(fn(self.h, *args), "vs_program_add_" + fn_name)
         return self
 
     @property
@@ -75,7 +86,11 @@ class Program:
 
     def run(self, stream: Optional[int] = None):
         if stream is None:
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        if torch.cuda.current_device() != self.device.index and self.device.index is not None:
+            with torch.cuda.device(self.device):
+                L.pcheck(self.lib.vs_program_run(self.h, stream), "vs_program_run")
+            return
         L.pcheck(self.lib.vs_program_run(self.h, stream), "vs_program_run")
 
     def read_trace_us(self) -> List[float]:
