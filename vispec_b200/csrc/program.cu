@@ -350,8 +350,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         }
       }
     }
-  } else {
-    // ===================== workers (two teams of 128 threads) =====================
+  } else if (warp >= 4) {        // (warp 3 is idle: it was the L2 prefetcher of round 1)
+    // ===================== workers (16 warps: four teams of 128 threads / two attention teams of 256) =====================
     const int wtid = threadIdx.x - 4 * 32;          // 0..511
     const int team = wtid >> 7, tt = wtid & 127;    // small team
     const int bteam = wtid >> 8, btt = wtid & 255;  // attention team
