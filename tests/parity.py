@@ -68,7 +68,7 @@ def lowest_index_topk():
 
     def topk(input, k, dim=-1, largest=True, sorted=True):
         v, i = torch.sort(input.float(), dim=dim, descending=largest, stable=True)
-        return SimpleNamespace(values=v.narrow(dim, 0, k).to(input.dtype), indices=i.narrow(dim, 0, k))
+        return SimpleNamespace(values=v.narrow(dim, 0, k).to(input.dtype).contiguous(), indices=i.narrow(dim, 0, k).contiguous())
 
     torch.topk = topk
     try:

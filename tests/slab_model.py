@@ -53,7 +53,7 @@ def pack(p, W: np.ndarray) -> np.ndarray:
                         continue
                     o = (jj * p["n_tiles"] + t) * p["blk_smem"] + r * 128     # offset of the row inside its stage
                     for c in range(8):
-                        cs = c ^ ((o >> 7) & 7)
+                        cs = c ^ ((r & 7) if p["packed"] == 2 else ((o >> 7) & 7))
                         dst = (base + r * 128 + cs * 16) // 2
                         out[dst:dst + 8] = W[n, j * 64 + c * 8:j * 64 + c * 8 + 8]
     return out
@@ -92,8 +92,9 @@ def emulate_gemm(p, slab: np.ndarray, X: np.ndarray, N: int) -> np.ndarray:
                         for r in range(p["rows_alloc"]):            # (lanes beyond hold garbage and are never read)
                             row = np.empty(64, dtype=np.uint16)
                             addr = a + r * 128
-                            for c in range(8):
-                                phys = addr + ((c ^ ((addr >> 7) & 7)) << 4)
+                            for c in range(8):     # packed == 2: pattern relative to the block (descriptor base offset)
+                                phase = (r & 7) if p["packed"] == 2 else ((addr >> 7) & 7)
+                                phys = addr + ((c ^ phase) << 4)
                                 row[c * 8:c * 8 + 8] = slot[phys // 2: phys // 2 + 8]
                             wf = (row.astype(np.uint32) << 16).view(np.float32)
                             acc[t, r] += xk @ wf

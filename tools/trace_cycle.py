@@ -54,18 +54,34 @@ for k, (n, d) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:16s} n={n:4d} total={d:9.1f} us  avg={d / n:7.2f} us  share={100 * d / total:5.1f}%")
 if args.brief:
     sys.exit(0)
-# one target layer in the middle of the verify step
-per_layer = 14 if args.two_phase_attention else 13
-start = 2 + 5 * per_layer if len(types) > 2 + 6 * per_layer else 0
+# one target layer in the middle of the verify step: from the GEMM in front of the 6th attention phase to the one in
+# front of the 7th (works for the slab program -- 5 phases per layer -- and the round-1 stream-K program -- 13)
+attn = [i for i, t in enumerate(types) if t in (L.PH_ATTN_FUSED, L.PH_ATTN_S)]
+gemm_types = (L.PH_GEMM, L.PH_GEMM2)
+
+
+def layer_start(ai):
+    i = ai - 1
+    while i > 0 and types[i] not in gemm_types:
+        i -= 1
+    while i > 0 and types[i - 1] in (L.PH_GEMM, L.PH_EPI) and types[i] == L.PH_EPI:
+        i -= 1
+    return i
+
+
+start, stop = (layer_start(attn[5]), layer_start(attn[6])) if len(attn) > 7 else (0, min(len(types), 16))
 print("phases of one target layer:")
-for i in range(start, min(start + per_layer, len(types))):
+for i in range(start, stop):
     print(f"  [{i}] {L.PHASE_NAMES[types[i]]:16s} {us[i]:8.2f} us")
 end, done = prog.read_trace_detail()
 print("per phase of that layer: work = slowest CTA's items-done minus previous barrier; sync = barrier end minus that")
-for i in range(start, min(start + per_layer, len(types))):
+for i in range(start, stop):
     t0 = end[i - 1]
     d = sorted(x - t0 for x in done[i])
     print(f"  [{i}] {L.PHASE_NAMES[types[i]]:16s} work: min {d[0] / 1e3:6.2f} median {d[len(d) // 2] / 1e3:6.2f} "
           f"max {d[-1] / 1e3:6.2f} us   sync {(end[i] - t0 - d[-1]) / 1e3:5.2f} us")
+# the tail of the cycle: LM head, accept, splice, the four draft forwards
+tail0 = layer_start(attn[tcfg_layers - 1]) if (tcfg_layers := model.base_model_engine.cfg.layers) <= len(attn) else 0
+print("after the last target layer (phase: us):", " ".join(f"{L.PHASE_NAMES[types[i]][:9]}:{us[i]:.1f}" for i in range(tail0, len(types))))
 if args.json:
     json.dump({"types": types, "us": us, "cycle_ms": ms, "end_ns": end, "done_ns": done}, open(args.json, "w"))

@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         if (ph.type == PH_GEMM2) {
           const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
           const uint32_t blk_smem = (uint32_t)ph.s_blk_smem, x_off = (uint32_t)ph.s_xoff;
+          const uint32_t idesc = ph.s_m64 ? IDESC_M64 : IDESC;
+          const bool rel = ph.s_packed == 2;
           for (int ps = 0; ps < passes; ++ps) {
             const int u = b * passes + ps;
             if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
@@ -246,10 +248,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
               for (int jj = 0; jj < nj; ++jj) {
                 const uint64_t db = make_desc(base + x_off + jj * X_STAGE);
                 for (int t = 0; t < nt; ++t) {
-                  const uint64_t da = make_desc(base + (uint32_t)(jj * nt + t) * blk_smem);
+                  const uint8_t* blk = base + (uint32_t)(jj * nt + t) * blk_smem;
+                  const uint64_t da = rel ? make_desc_rel(blk) : make_desc(blk);
 #pragma unroll
                   for (int k = 0; k < BK / 16; ++k)
-                    tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (j0 | jj | k) ? 1u : 0u);
+                    tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (j0 | jj | k) ? 1u : 0u, idesc);
                 }
               }
               tc_commit(&empty[stage]);
@@ -598,6 +601,7 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
       g.s_pair = sp.pair; g.s_ntiles = sp.n_tiles; g.s_passes = sp.passes; g.s_rows_alloc = sp.rows_alloc;
       g.s_blk_bytes = sp.blk_bytes; g.s_blk_smem = sp.blk_smem; g.s_kc = sp.kc; g.s_xoff = sp.x_off;
       g.s_eper = sp.e_per; g.s_erem = sp.e_rem; g.s_unit_stride = sp.unit_stride;
+      g.s_packed = sp.packed; g.s_m64 = sp.m64;
       g.tmX = add_map(pg, a.X, a.ldx, a.T, a.K, VS_TOK);
       g.tmX3 = (pg->x3d && sp.kc > 1) ? add_map(pg, a.X, a.ldx, a.T, a.K, VS_TOK, sp.kc) : -1;
       g.epi = a.epi;
@@ -964,7 +968,7 @@ int vs_program_register_slab(vs_program* pg, const void* w_row_major, const void
   if (reinterpret_cast<uintptr_t>(w_slab) % 128) return vs::pfail(VS_ERR_INVALID, "vs_program_register_slab", "slab image must be 128-byte aligned");
   if (grid <= 0) grid = vs::device_sms();
   const int pair = (epi == vs::EPI_SWIGLU || epi == vs::EPI_HEADS) ? 1 : 0;
-  pg->slabs.push_back({w_row_major, w_slab, pair, grid, vs::slab_default_packed() ? 1 : 0});
+  pg->slabs.push_back({w_row_major, w_slab, pair, grid, vs::slab_default_packed()});
   return VS_OK;
 }
 

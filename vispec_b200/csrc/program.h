@@ -61,6 +61,7 @@ struct Phase {
                               // (PH_GEMM2: [1] arrivals of all CTAs)
   // ---- PH_GEMM2 (slab layout, slab.h); Wt = the slab image, nk / N / T / tmX3 / the epilogue fields as above
   int s_pair, s_ntiles, s_passes, s_rows_alloc, s_blk_bytes, s_blk_smem, s_kc, s_xoff, s_eper, s_erem;
+  int s_packed, s_m64;        // SlabPlan::packed / m64
   long s_unit_stride;
   int tmX3;                   // 3-D tensor map of the activations: box {64 columns, 32 rows, kc chunks} (-1: kc 2-D loads)
                               // (`ssq` of a PH_GEMM2 residual epilogue is [grid][32]: one row of partial sums per CTA)

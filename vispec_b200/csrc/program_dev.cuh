@@ -346,7 +346,8 @@ __device__ __noinline__ void slab_epilogue(const Phase& ph, unsigned int epoch, 
   const int T = ph.T, epi = ph.epi;
   const int passes = ph.s_passes, n_tiles = ph.s_ntiles, rows_alloc = ph.s_rows_alloc, pair = ph.s_pair;
   const int e_per = ph.s_eper, e_rem = ph.s_erem;
-  const int row = quarter * 32 + lane;                 // accumulator lane = row of the tile
+  // accumulator lane -> row of the tile: M = 128 keeps row r in lane r; M = 64 keeps it in lane (r & 15) + 32 * (r >> 4)
+  const int row = ph.s_m64 ? (lane < 16 ? quarter * 16 + lane : 1 << 20) : quarter * 32 + lane;
   const int t0 = cg * 8;                               // first token of this thread
   const bool resid = epi == EPI_RESID, heads = epi == EPI_HEADS;
   float* ssq = ph.ssq;

@@ -10,9 +10,10 @@
 
 namespace vs {
 
-bool slab_default_packed() {
+int slab_default_packed() {
   const char* e = getenv("VS_SLAB_PACKED");
-  return !(e && e[0] == '0');
+  if (e && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
+  return 1;
 }
 
 bool slab_plan(int N, int K, int pair, int grid, int packed, SlabPlan* out) {
@@ -20,7 +21,7 @@ bool slab_plan(int N, int K, int pair, int grid, int packed, SlabPlan* out) {
   if (pair && N % 128 != 0) return false;
   SlabPlan p;
   p.pair = pair ? 1 : 0;
-  p.packed = packed ? 1 : 0;
+  p.packed = packed;
   p.E = pair ? N / 2 : N;
   p.nk = K / 64;
   p.grid = grid;
@@ -49,6 +50,10 @@ bool slab_plan(int N, int K, int pair, int grid, int packed, SlabPlan* out) {
     if (w + kc * SLAB_X_BYTES <= SLAB_SLOT_BYTES) p.kc = kc;
   }
   p.x_off = (p.kc * p.n_tiles * p.blk_smem + 1023) / 1024 * 1024;
+  {
+    const char* e = getenv("VS_SLAB_M64");
+    p.m64 = (p.rows_alloc <= 64 && !(e && e[0] == '0')) ? 1 : 0;
+  }
   p.unit_stride = (long)p.nk * p.n_tiles * p.blk_bytes;
   p.total_bytes = units * p.unit_stride;
   *out = p;
@@ -80,7 +85,7 @@ __global__ void slab_pack_kernel(const bf16* __restrict__ W, long ldw, int N, Sl
     if (n >= 0 && n < N) v = *reinterpret_cast<const uint4*>(W + (long)n * ldw + (long)j * 64 + c * 8);
     // shared-memory offset of the row inside its stage decides the swizzle phase (slab.h)
     const int o = (jj * p.n_tiles + t) * p.blk_smem + r * 128;
-    const int cs = c ^ ((o >> 7) & 7);
+    const int cs = c ^ (p.packed == 2 ? (r & 7) : ((o >> 7) & 7));
     *reinterpret_cast<uint4*>(ublk + (long)t * p.blk_bytes + r * 128 + cs * 16) = v;
   }
 }

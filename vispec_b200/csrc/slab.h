@@ -23,9 +23,9 @@
 //             back to back (rows_alloc need not be a multiple of 8), so a block may start in the middle of a 1024-byte
 //             swizzle atom: the 16-byte chunk c of the row at byte offset `o` of the stage is stored at chunk position
 //             c ^ ((o >> 7) & 7) -- the 128-byte swizzle is a function of the shared-memory ADDRESS (the slot base is
-//             1024-byte aligned) -- and the MMA descriptor of the block carries base_offset = (o >> 7) & 7.
-//             (`packed` = 0 selects the conservative variant: blocks padded to whole atoms in shared memory, one bulk
-//             copy per block.)
+//             1024-byte aligned; descriptor base offset 0).  `packed` = 0 selects the conservative variant (blocks padded
+//             to whole atoms in shared memory, one bulk copy per block: TMA-issue-bound, measured 130 vs 186 tokens/s),
+//             `packed` = 2 the other reading of the ISA's base-offset field (pattern relative to the block).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -38,7 +38,10 @@ constexpr int SLAB_MAX_ROWS = 112;       // rows per tile: 2 x 112 x 128 B + 4 K
 
 struct SlabPlan {
   int pair;          // 1: elements are row pairs (SWIGLU / HEADS)
-  int packed;        // 1: blocks back to back in shared memory (one bulk copy per stage)
+  int packed;        // 0: blocks padded to whole 1024-byte atoms in shared memory, one bulk copy per block;
+                     // 1: blocks back to back (one bulk copy per stage), image swizzled by shared-memory address;
+                     // 2: back to back, image swizzled relative to each block + descriptor base offset
+  int m64;           // 1: rows_alloc <= 64 -> MMAs with M = 64 (half the shared-memory reads of the weight operand)
   int E;             // elements
   int n_tiles;       // accumulators per pass
   int passes;        // units per CTA
@@ -55,6 +58,6 @@ struct SlabPlan {
 
 // false: the shape cannot use the slab path (the caller falls back to the tiled / row-major stream-K path)
 bool slab_plan(int N, int K, int pair, int grid, int packed, SlabPlan* out);
-bool slab_default_packed();              // VS_SLAB_PACKED (default 1)
+int slab_default_packed();               // VS_SLAB_PACKED (default 1)
 
 }  // namespace vs

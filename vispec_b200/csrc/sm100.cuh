@@ -12,6 +12,8 @@ constexpr uint64_t HINT_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=32, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+// the same with M=64: accumulator row r sits in TMEM lane (r & 15) + 32 * (r >> 4) (16 lanes of every 32-lane quarter)
+constexpr uint32_t IDESC_M64 = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((64u >> 4) << 24);
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -59,24 +61,30 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate,
+                                       uint32_t idesc = IDESC) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(IDESC), "r"(accumulate)
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // K-major operand tile [rows][64 bf16] with 128-byte swizzle: SBO = 1024 B between 8-row groups, version 1.
-// A tile that does not start on a 1024-byte boundary of the swizzle pattern (the packed blocks of slab.h start every
-// rows * 128 bytes) carries base_offset = (start address >> 7) & 7 in bits [49, 52), as the PTX ISA prescribes; for an
-// aligned tile the field is 0.
+// base_offset (bits [49, 52)) = 0: the swizzle pattern repeats from 1024-byte boundaries of the shared-memory ADDRESS, so a
+// tile may start at any multiple of 128 bytes as long as its image was swizzled by address (slab.h, packed blocks).
 __device__ __forceinline__ uint64_t make_desc(const void* smem_tile) {
   uint64_t addr = smem_u32(smem_tile);
-  return ((addr & 0x3FFFFull) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (((addr >> 7) & 7ull) << 49) |
-         (2ull << 61);
+  return ((addr & 0x3FFFFull) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// The other reading of the PTX ISA's "matrix base offset": the pattern starts at the TILE (row r of the tile uses phase
+// r & 7) and the descriptor carries base_offset = (start address >> 7) & 7.  Selectable for the packed slab blocks
+// (VS_SLAB_PACKED=2) so that both can be checked on hardware.
+__device__ __forceinline__ uint64_t make_desc_rel(const void* smem_tile) {
+  uint64_t addr = smem_u32(smem_tile);
+  return make_desc(smem_tile) | (((addr >> 7) & 7ull) << 49);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];

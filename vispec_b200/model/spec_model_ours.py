@@ -231,7 +231,7 @@ class SpecModel:
                         sd["model." + k[len(pre):]] = v
                 if k in ("language_model.lm_head.weight", "lm_head.weight"):
                     sd["lm_head.weight"] = v
-            vision = _HFLlavaVision(hf.to(device))
+            vision = _HFLlavaVision(hf, device)
         elif arch == "Qwen2_5_VLForConditionalGeneration":
             # spec_model_ours.py:137-140,380-449.  Needs a checkpoint on disk: not exercised offline (the Qwen target
             # itself is, at synthetic weights: tests/test_gpu_qwen.py).
@@ -452,24 +452,56 @@ EaModel = SpecModel
 
 
 class _HFLlavaVision:
-    """Host-side vision front-end (spec_model_ours.py:311-378): HF vision tower + projector + feature packing.
-    Out of the decode path; requires a real checkpoint."""
+    """Host-side vision front-end (spec_model_ours.py:311-378): HF vision tower + projector + feature packing
+    (spatial unpad + image_newline for LLaVA-Next).  Out of the decode path.  Only the vision tower, the projector, the
+    newline row and the token embedding are kept on the device: the language model lives in the B200 engine."""
 
-    def __init__(self, hf_model):
+    def __init__(self, hf_model, device=None):
         self.m = hf_model
+        self.cfg = hf_model.config
+        inner = getattr(hf_model, "model", hf_model)
+        lm = getattr(inner, "language_model", None)
+        # free the HF language model's layers (a third copy of the LM weights); the embedding table stays
+        self.embed = hf_model.get_input_embeddings()
+        if lm is not None and hasattr(lm, "layers"):
+            lm.layers = torch.nn.ModuleList()
+        if hasattr(hf_model, "lm_head"):
+            hf_model.lm_head = torch.nn.Identity()
+        if device is not None:
+            hf_model.to(device)
+
+    def image_features(self, pixel_values, image_sizes):
+        """[n_image_tokens, H] in the order of the image placeholders.  transformers 4.x returns per-image patch features
+        and leaves the packing to the caller (`pack_image_features`, spec_model_ours.py:342-355); 5.x returns the packed
+        rows in `pooler_output`.  Both are handled; keyword arguments only (the positional order changed)."""
+        m, cfg = self.m, self.cfg
+        kw = dict(vision_feature_layer=getattr(cfg, "vision_feature_layer", -2),
+                  vision_feature_select_strategy=getattr(cfg, "vision_feature_select_strategy", "default"))
+        if image_sizes is not None:
+            out = m.get_image_features(pixel_values=pixel_values, image_sizes=image_sizes, **kw)
+        else:                                         # LlavaForConditionalGeneration: no any-resolution packing
+            out = m.get_image_features(pixel_values=pixel_values, **kw)
+        feats = getattr(out, "pooler_output", out)
+        if isinstance(feats, (list, tuple)):
+            if feats and feats[0].dim() == 3 and image_sizes is not None:      # unpacked [patches, tokens, H] per image
+                inner = getattr(m, "model", m)
+                packer = m.pack_image_features if hasattr(m, "pack_image_features") else inner.pack_image_features
+                feats, _ = packer(list(feats), image_sizes, vision_feature_select_strategy=kw["vision_feature_select_strategy"],
+                                  image_newline=getattr(inner, "image_newline", getattr(m, "image_newline", None)))
+            if isinstance(feats, (list, tuple)):
+                feats = torch.cat([f.reshape(-1, f.shape[-1]) for f in feats], dim=0)
+        return feats.reshape(-1, feats.shape[-1])
 
     @torch.no_grad()
     def __call__(self, input_ids, pixel_values=None, image_sizes=None, **kw):
-        m = self.m
-        inputs_embeds = m.get_input_embeddings()(input_ids)
-        feats = m.get_image_features(pixel_values, image_sizes)
-        feats = torch.cat(list(feats), dim=0) if isinstance(feats, (list, tuple)) else feats
-        mask = input_ids == m.config.image_token_index
+        inputs_embeds = self.embed(input_ids)
+        feats = self.image_features(pixel_values.to(inputs_embeds.device), image_sizes)
+        mask = input_ids == self.cfg.image_token_index
         if int(mask.sum()) != feats.shape[0]:
             raise ValueError(f"Image features and image tokens do not match: tokens: {int(mask.sum())}, "
                              f"features {feats.shape[0]}")
         inputs_embeds = inputs_embeds.masked_scatter(mask.unsqueeze(-1).expand_as(inputs_embeds),
-                                                     feats.to(inputs_embeds.dtype))
+                                                     feats.to(inputs_embeds.device, inputs_embeds.dtype))
         return inputs_embeds, mask
 
 
