@@ -116,7 +116,7 @@ def synth_prompt(cfg, embed, seed, device, n_post=None):
     return ids.to(device), emb, mask.to(device)
 
 
-def make_bigram(tw, dw, tcfg, dcfg):
+def make_bigram(tw, dw, tcfg, dcfg, fc_noise=0.0, seed=0):
     """The tau > 0 fixture of SURVEY.md 7.2 at full size (oracle/synth.py:make_bigram_fixture is the CPU original):
     every target layer's o_proj / down_proj is zero, so next = argmax(lm_head(norm(embed[tok]))), and the draft
     (same embedding, fc = [I | 0], zero o_proj / down_proj) predicts it: accept length = depth + 1."""
@@ -128,6 +128,9 @@ def make_bigram(tw, dw, tcfg, dcfg):
     H = dcfg.hidden
     fc = torch.zeros(H, 2 * H, dtype=torch.bfloat16, device=dw["fc.weight"].device)
     fc[:, :H] = torch.eye(H, dtype=torch.bfloat16, device=fc.device)
+    if fc_noise > 0:        # an imperfect draft: intermediate accept lengths (oracle/synth.py:make_bigram_fixture)
+        g = torch.Generator(device=fc.device).manual_seed(seed + 2)
+        fc = (fc.float() + fc_noise * torch.randn(H, 2 * H, generator=g, device=fc.device) / math.sqrt(2 * H)).to(torch.bfloat16)
     dw["fc.weight"] = fc
     if "fc.bias" in dw:
         dw["fc.bias"].zero_()
@@ -135,7 +138,7 @@ def make_bigram(tw, dw, tcfg, dcfg):
     dw["layers.0.mlp.down_proj.weight"].zero_()
 
 
-def build_llava7b(device="cuda", seed=0, layers=32, fixture="random"):
+def build_llava7b(device="cuda", seed=0, layers=32, fixture="random", fc_noise=0.0, n_post=None):
     """(model, input_ids, inputs_embeds, image_mask) for the BASELINE config-2 workload.  fixture="bigram": the same
     shapes with weights under which the draft is always right (accept length 4), to exercise accept / splice / the
     accepted-rows draft forward at full size."""
@@ -147,9 +150,9 @@ def build_llava7b(device="cuda", seed=0, layers=32, fixture="random"):
     tw = synth_target_weights(tcfg, seed, device)
     dw = synth_draft_weights(dcfg, seed + 1, device)
     if fixture == "bigram":
-        make_bigram(tw, dw, tcfg, dcfg)
+        make_bigram(tw, dw, tcfg, dcfg, fc_noise=fc_noise, seed=seed)
     model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=device, eos_token_id=None)
-    ids, emb, mask = synth_prompt(tcfg, model.base_model_engine.embed, seed + 7, device)
+    ids, emb, mask = synth_prompt(tcfg, model.base_model_engine.embed, seed + 7, device, n_post=n_post)
     del tw, dw
     torch.cuda.empty_cache()
     return model, ids, emb, mask
@@ -707,6 +710,199 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: eight independent batch-1 streams with mixed prompt lengths (576 image + 64..512 text tokens)
+# ------------------------------------------------------------------------------------------------------------
+MIXED_TEXT = (64, 128, 256, 512, 96, 192, 384, 448)       # text tokens of stream i (drawn once from {64 ... 512})
+MIXED_NOISE = (0.0, 0.6, 0.3, 0.9, 0.45, 0.15, 0.75, 1.2)  # draft quality of stream i -> accept length varies
+
+
+def run_mixed(args):
+    """`--workload mixed`: the reference's multi-GPU scheme (prompt sharding over replicas, no data-path collective,
+    gen_spec_answer_coco_caption.py:53-83) on BASELINE config 5.  Stream i = 576 image rows + MIXED_TEXT[i] text tokens
+    on the LLaVA-7B bigram fixture with draft noise MIXED_NOISE[i]; rank r of N runs streams r, r + N, ...; 256 tokens
+    per stream at T = 0.  value = all generated tokens / the slowest rank's decode time."""
+    from collections import Counter
+
+    from vispec_b200 import _lib as L
+    from vispec_b200 import replicas
+
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    lib = L.load()
+    mine = list(replicas.shard_prompts(len(MIXED_TEXT), rank, world))
+    gen_kw = dict(temperature=0.0, log=True, return_acceptance_len=True, max_new_tokens=GEN_TOKENS - 1)
+    records, launches = [], 0
+    clocks = ClockSampler(local)
+    for si in mine:
+        model, ids, emb, mask = build_llava7b(device=device, seed=100 + si, layers=args.layers, fixture="bigram",
+                                              fc_noise=MIXED_NOISE[si], n_post=MIXED_TEXT[si] - 5)
+        for _ in range(max(args.warmup, 1)):
+            model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, **gen_kw)
+        torch.cuda.synchronize()
+        if si == mine[0]:
+            clocks.start()
+        lib.vs_launch_count(1)
+        tok, ms, acc, wall = 0, 0.0, [], 0.0
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            _, n, _, a = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, **gen_kw)
+            torch.cuda.synchronize()
+            wall += time.perf_counter() - t0
+            tok += n; ms += model.last_decode_ms; acc += a
+        launches += lib.vs_launch_count(1)
+        records.append({"question_id": si, "text_tokens": MIXED_TEXT[si], "prompt_tokens": int(ids.shape[1]),
+                        "fc_noise": MIXED_NOISE[si], "new_tokens": [tok], "wall_time": [wall], "decode_ms": ms,
+                        "acceptance_length": acc, "tokens_per_s": tok / (ms * 1e-3), "rank": rank})
+        del model
+        torch.cuda.empty_cache()
+    clk = clocks.stop()
+    t = torch.tensor([sum(r["decode_ms"] for r in records)], dtype=torch.float64, device=device)
+    cnt = torch.tensor([sum(r["new_tokens"][0] for r in records), launches], dtype=torch.float64, device=device)
+    if use_dist:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    allrec = replicas.gather_results(records)
+    if rank == 0:
+        hist = Counter(a for r in allrec for a in r["acceptance_length"])
+        agg = replicas.aggregate_throughput(allrec)
+        wall_by_rank = {}
+        for r in allrec:
+            wall_by_rank[r["rank"]] = wall_by_rank.get(r["rank"], 0.0) + sum(r["wall_time"])
+        wall_max = max(wall_by_rank.values())
+        line = {"metric": "decode_tokens_per_sec", "value": cnt[0].item() / (t.item() * 1e-3), "unit": "tokens/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": t.item() / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "BASELINE config 5: 8 independent batch-1 streams, LLaVA-1.6-7B shapes + ViSpec head, 576 "
+                                       "image + 64..512 text tokens, T=0, 256-token gen, bigram fixture with per-stream draft noise",
+                           "parallelism": f"replicas x{world} (prompt sharding, no data-path collective)",
+                           "l2": "inputs larger than L2 (16.4 GB of weights streamed per cycle)"},
+                "streams": [{k: r[k] for k in ("question_id", "rank", "text_tokens", "prompt_tokens", "fc_noise", "tokens_per_s")}
+                            | {"accept_len_mean": sum(r["acceptance_length"]) / max(1, len(r["acceptance_length"]))}
+                            for r in allrec],
+                "accept_len_hist": {str(k): hist[k] for k in sorted(hist)}, "accept_len_mean": agg["mean_accept_len"],
+                "mean_stream_tokens_per_s": agg["mean_tokens_per_s"], "gpu_launches": int(cnt[1].item()), "clocks": clk,
+                "e2e": {"value": sum(r["new_tokens"][0] for r in allrec) / wall_max,
+                        "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "wall clock around specgenerate incl. the prompt pass; inputs resident"}}
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE config 4: LLaVA-1.6-13B shapes, tensor-parallel target prompt pass over the N GPUs, replicated decode
+# ------------------------------------------------------------------------------------------------------------
+def run_tp13b(args):
+    """`--workload llava13b_tp`: 13B target (H=5120, 40 heads, I=13824, 40 layers) + ViSpec head.  The prompt pass is
+    sharded tensor-parallel over the N ranks (vispec_b200/tp_prefill.py: column-parallel q|k|v / gate|up, row-parallel
+    o / down with one all-reduce each, KV all-gathered); the draft head and the draft-and-verify decode are replicated
+    (one persistent kernel per GPU, every rank produces the same tokens).  Reports the prompt pass at 704 and 2885 rows
+    (TP vs the single-GPU native pass on rank 0) and decode tokens/s; value = ONE stream's decode tokens/s (the ranks
+    decode in lockstep: replicas of the same stream, not additional throughput)."""
+    from vispec_b200.engine import DraftConfig, TargetConfig
+    from vispec_b200.model.spec_model_ours import SpecModel
+
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    layers = args.layers if args.layers != 32 else 40
+    tcfg = TargetConfig(hidden=5120, inter=13824, layers=layers, heads=40, kv_heads=40, vocab=32064)
+    dcfg = DraftConfig(hidden=5120, inter=13824, heads=40, vocab=32064)
+    tw = synth_target_weights(tcfg, 5, device)          # same seed on every rank: identical replicas
+    dw = synth_draft_weights(dcfg, 6, device)
+    model = SpecModel.from_state_dicts(tcfg, tw, dcfg, dw, device=device, kv_max=4096, eos_token_id=None)
+    del tw, dw
+    torch.cuda.empty_cache()
+    eng = model.base_model_engine
+    gen_kw = dict(temperature=0.0, log=True, return_acceptance_len=True, max_new_tokens=GEN_TOKENS - 1)
+    out = {}
+    prefill = []
+    for n_post in (123, 2304):                              # 704 rows; 5 + 576 + 2304 = 2885 rows
+        ids, emb, mask = synth_prompt(tcfg, eng.embed, 12, device, n_post=n_post)
+        rows = ids.shape[1]
+        res = {"rows": rows}
+        for mode in (("native_1gpu", "tp") if use_dist else ("native_1gpu",)):
+            eng._tp = None
+            if mode == "tp":
+                model.enable_tensor_parallel_prefill()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            times = []
+            for it in range(2 + max(1, args.steps)):
+                eng.set_len(0)
+                if use_dist:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                ev0.record()
+                lg, _ = eng.prefill(emb)
+                ev1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    times.append(ev0.elapsed_time(ev1))
+            tm = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=device)
+            if use_dist:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            res[mode + "_ms"] = tm.item()
+            res[mode + "_next_token"] = int(torch.argmax(lg))
+        if use_dist:
+            res["speedup_tp_over_native"] = res["native_1gpu_ms"] / res["tp_ms"]
+            res["next_token_equal"] = res["native_1gpu_next_token"] == res["tp_next_token"]
+        prefill.append(res)
+    # decode on the 704-row prompt (TP prompt pass when N > 1), all ranks in lockstep
+    ids, emb, mask = synth_prompt(tcfg, eng.embed, 12, device)
+    for _ in range(max(args.warmup, 1)):
+        model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, **gen_kw)
+    if use_dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    tok, ms, acc, last = 0, 0.0, [], None
+    for _ in range(args.steps):
+        o, n, _, a = model.specgenerate(ids, inputs_embeds=emb, image_mask=mask, **gen_kw)
+        tok += n; ms += model.last_decode_ms; acc += a; last = o
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    same = torch.ones(1, dtype=torch.int64, device=device)
+    if use_dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ref = last.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([int(ref.shape == last.shape and bool(torch.equal(ref, last)))], dtype=torch.int64, device=device)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        by = cycle_algorithmic_bytes(tcfg, dcfg, ids.shape[1] + GEN_TOKENS / 2 + 30, 130 + GEN_TOKENS / 2)
+        cyc_ms = t.item() / max(1, len(acc))
+        line = {"metric": "decode_tokens_per_sec", "value": tok / (t.item() * 1e-3), "unit": "tokens/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": t.item() / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"BASELINE config 4: LLaVA-1.6-13B shapes ({layers} layers) + ViSpec head, T=0, 576 img + 128 "
+                                       "text tokens, 256-token gen; tensor-parallel target prompt pass, replicated decode",
+                           "parallelism": f"tp{world} prompt pass (NCCL all-reduce on the row-parallel boundaries) + replicated decode",
+                           "l2": "inputs larger than L2 (26 GB of weights streamed per cycle)"},
+                "accept_len_mean": sum(acc) / max(1, len(acc)), "ms_per_cycle": cyc_ms,
+                "roofline": {"bound": "hbm", "achieved": by["total"] / (cyc_ms * 1e-3) / 1e9, "peak": hbm_peak()[0], "unit": "GB/s",
+                             "frac": by["total"] / (cyc_ms * 1e-3) / 1e9 / hbm_peak()[0], "traffic": None,
+                             "algorithmic_bytes_per_launch": by["total"]},
+                "prompt_pass": prefill, "tokens_identical_on_all_ranks": bool(same.item()), "clocks": clk,
+                "e2e": {"value": tok / (t.item() * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "decode region only (inputs resident); the prompt pass is reported separately"}}
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -718,9 +914,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU (eager PyTorch) leg")
     ap.add_argument("--no-fixture", action="store_true", help="skip the accept-length (bigram fixture) leg")
+    ap.add_argument("--workload", default="llava7b", choices=["llava7b", "mixed", "llava13b_tp"],
+                    help="llava7b = BASELINE config 2 (the headline line); mixed = config 5 (8 streams, 64..512 text tokens, "
+                         "prompt sharding over the GPUs); llava13b_tp = config 4 (13B shapes, tensor-parallel prompt pass)")
     args = ap.parse_args()
     if args.impl in ("reference", "reference-gpu"):
         run_reference(args)
+    elif args.workload == "mixed":
+        run_mixed(args)
+    elif args.workload == "llava13b_tp":
+        run_tp13b(args)
     else:
         run_ours(args)
 

@@ -99,12 +99,13 @@ def test_reference_api_cycle_matches_golden(name):
     vo.spec_generate(vo.TargetOracle(tcfg, tw), vo.DraftOracle(dcfg, dw), ids, emb, mask, max_new_tokens=10 ** 9,
                      max_cycles=g["meta"]["n_cycles"], trace=otrace)
     # prefill: logits as a bf16 ulp histogram against the reference's, same first token
-    assert_ulps(f"e2e/{name}/prefill_last_logits", logits[0, -1], first["prefill_last_logits"], exact=0.5, le2=0.97, le4=0.995)
+    assert_ulps(f"e2e/{name}/prefill_last_logits", logits[0, -1], first["prefill_last_logits"], exact=0.35, le2=0.93, le4=0.985,
+                max_ulps=24)
     assert int(sample_token) == int(first["sample_token"])
     assert model.spec_layer.stable_kv[0][0].shape[2] == first["draft_kv_len"]
     assert model.spec_layer.stable_kv[0][2] == first["draft_real_len"]
-    assert_ulps(f"e2e/{name}/last_img_hidden", model.spec_layer.last_img_hidden, first["last_img_hidden"], exact=0.45,
-                le2=0.88, le4=0.96, max_ulps=24)
+    assert_ulps(f"e2e/{name}/last_img_hidden", model.spec_layer.last_img_hidden, first["last_img_hidden"], exact=0.35,
+                le2=0.93, le4=0.985, max_ulps=24)
     input_ids = ids_d
     new_token = 0
     pad = torch.full((1, 1), -1, dtype=torch.long, device=DEV)
@@ -126,7 +127,8 @@ def test_reference_api_cycle_matches_golden(name):
         model.base_model.model.tree_mask = tree_mask
         logits, hidden_new, _ = vu.tree_decoding(model, draft_tokens, pkv, tree_pos, input_ids, retrieve)
         if trees_exact:
-            assert_ulps(f"e2e/{name}/tree_logits_root/{ci}", logits[0, 0], ref["tree_logits_root"], exact=0.5, le2=0.97, le4=0.995)
+            assert_ulps(f"e2e/{name}/tree_logits_root/{ci}", logits[0, 0], ref["tree_logits_root"], exact=0.35, le2=0.93,
+                        le4=0.985, max_ulps=24)
         cand = torch.cat((draft_tokens, pad), dim=1)[0, retrieve.to(DEV)]
         best, a, sample_p = vu.evaluate_posterior(logits, cand, None)
         if trees_exact:

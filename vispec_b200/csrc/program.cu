@@ -138,6 +138,24 @@ __device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team
                             ph.out_rec, *reinterpret_cast<SampleSmem*>(team_base), wtid, PG_WORKERS, WorkerSync());
 }
 
+// Every CTA of a slab GEMM needs ALL activation blocks of the phase.  Walking the k-chunks in the same order on every CTA
+// makes all 148 SMs ask the L2 for the same 4-16 KB at the same moment, and requests for one line serialise in its L2
+// slice: measured 8-11 GB/s per SM for the activation blocks, which made every GEMM phase activation-bound (35-65 us
+// against 5-28 us of weight streaming, profiles/r2c_trace.txt).  So CTA b starts its k loop at stage b * spp / G and
+// wraps around: at any time the CTAs are spread evenly over the stages.  (The k order of the fp32 accumulation of a row
+// therefore depends on the CTA that owns it -- fixed per row and launch-invariant, like every other order in here.)
+__device__ __forceinline__ int slab_rotation(int b, int G, int spp) {
+#ifdef VS_SLAB_NO_ROTATION
+  return 0;
+#else
+  return (int)(((long)b * spp) / G);
+#endif
+}
+__device__ __forceinline__ int slab_stage(int s, int rot, int spp) {
+  const int v = s + rot;
+  return v >= spp ? v - spp : v;
+}
+
 __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHeader hdr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -186,12 +204,15 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
           const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
           const uint32_t blk = (uint32_t)ph.s_blk_bytes, blk_smem = (uint32_t)ph.s_blk_smem;
           const uint8_t* wbase = reinterpret_cast<const uint8_t*>(ph.Wt);
+          const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
           for (int ps = 0; ps < passes; ++ps) {
             const int u = b * passes + ps;
             if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
-            const uint8_t* src = wbase + (long)u * ph.s_unit_stride;
-            for (int j0 = 0; j0 < nk; j0 += kc) {
+            const uint8_t* ubase = wbase + (long)u * ph.s_unit_stride;
+            for (int s = 0; s < spp; ++s) {
+              const int j0 = slab_stage(s, rot, spp) * kc;          // (rotated k order, see slab_stage)
               const uint32_t nblk = (uint32_t)(min(kc, nk - j0) * nt);
+              const uint8_t* src = ubase + (long)j0 * nt * blk;
               mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
               mbar_expect_tx(&full_w[stage], nblk * blk);
               uint8_t* dst = smem + stage * STAGE_BYTES;
@@ -201,7 +222,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
                 for (uint32_t i = 0; i < nblk; ++i)
                   bulk_load(dst + i * blk_smem, src + i * blk, blk, &full_w[stage], HINT_EVICT_FIRST);
               }
-              src += nblk * blk;
               if (++stage == NS) { stage = 0; par ^= 1; }
             }
           }
@@ -233,13 +253,15 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
           const uint32_t blk_smem = (uint32_t)ph.s_blk_smem, x_off = (uint32_t)ph.s_xoff;
           const uint32_t idesc = ph.s_m64 ? IDESC_M64 : IDESC;
           const bool rel = ph.s_packed == 2;
+          const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
           for (int ps = 0; ps < passes; ++ps) {
             const int u = b * passes + ps;
             if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
             mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 64;
-            for (int j0 = 0; j0 < nk; j0 += kc) {
+            for (int s = 0; s < spp; ++s) {
+              const int j0 = slab_stage(s, rot, spp) * kc;
               const int nj = min(kc, nk - j0);
               mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
               mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
@@ -252,7 +274,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
                   const uint64_t da = rel ? make_desc_rel(blk) : make_desc(blk);
 #pragma unroll
                   for (int k = 0; k < BK / 16; ++k)
-                    tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (j0 | jj | k) ? 1u : 0u, idesc);
+                    tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
                 }
               }
               tc_commit(&empty[stage]);
@@ -326,8 +348,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
           const CUtensorMap* tm3 = ph.tmX3 >= 0 ? hdr.maps + ph.tmX3 : nullptr;
           const CUtensorMap* tm = hdr.maps + ph.tmX;
           const int spp = (nk + kc - 1) / kc;                // stages per pass: every pass walks the same k-chunks
+          const int rot = slab_rotation(b, G, spp);
           for (int s = 0; s < n_stages; ++s) {
-            const int j0 = (s % spp) * kc;
+            const int j0 = slab_stage(s % spp, rot, spp) * kc;
             const int nj = min(kc, nk - j0);
             mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
             mbar_expect_tx(&full_x[stage], nj * X_STAGE);
