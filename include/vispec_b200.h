@@ -244,6 +244,36 @@ typedef struct vs_draft {
   void* logits;                        /* [32][V] */
 } vs_draft;
 
+/* A1: the image/prefill branch of the draft model in ONE call -- `ImgAdaptor.forward` (cnets_ours.py:603-661: K,V =
+ * Linear(image embeds), `num_q` learned queries cross-attend, o_proj) + the prefill packing of `Model.forward`
+ * (cnets_ours.py:879-975: text rows through fc(cat(emb, img_fc(cat(hidden, g)))), the image run compressed to
+ * num_q - 1 tokens at the run's LAST positions, the global feature g = last adaptor row) + the draft decoder layer over
+ * the packed rows (KV rows [0, n_c) of the draft cache).  `hidden` / `emb_shifted`: [L][H] target features and input
+ * embeddings ALREADY shifted by one (cnets_ours.py:1066-1082); the image rows are rows [img_start, img_end) of that
+ * shifted frame (exactly one contiguous run -- the reference fails on more, cnets_ours.py:938-941,1021), or
+ * img_start = -1 for a text-only prompt (g = 0, cnets_ours.py:977-981).  All buffers are the caller's: nothing is
+ * allocated, no host sync.  On return: g_out [H] and the g half of dm->x1, last_row_out [H] = the layer output of the
+ * last packed row, state[VS_ST_D_LEN] = n_c, state[VS_ST_D_POS] = L, state[VS_ST_LAST_ROW] = 0, ws->pos = packed position
+ * ids, scratch->h = the layer output [n_c][H].  Returns n_c (>= 1) or a negative VS_ERR_*. */
+typedef struct vs_adaptor {
+  const void* w_kv; const void* b_kv;  /* [2H][H]: k_proj rows then v_proj rows; bias or NULL */
+  const void* w_o;                     /* [H][H] */
+  const void* q;                       /* [n_heads][32][128]: the learned queries head-major, rows >= num_q zero */
+  int32_t num_q;
+} vs_adaptor;
+typedef struct vs_prefill_ws {
+  int32_t max_rows;                    /* multiple of 32; >= image rows and >= packed rows; <= scratch->max_rows */
+  void* img_k; void* img_v;            /* [n_heads][max_rows][128] */
+  void* x1; void* x2;                  /* [max_rows][2H] */
+  void* fused;                         /* [max_rows][H] */
+  void* adapted; void* attn_out;       /* [32][H] */
+  int32_t* pos;                        /* [max_rows] */
+  void* packed;                        /* [max_rows][H]: copy of the packed rows before the layer, or NULL */
+} vs_prefill_ws;
+int vs_img_adaptor_prefill(const vs_draft* dm, const vs_adaptor* ad, const vs_scratch* s, const vs_prefill_ws* ws,
+                           const void* hidden, const void* emb_shifted, int L, int img_start, int img_end, void* g_out,
+                           void* last_row_out, int32_t* state, void* stream);
+
 /* A2-A5 decode branch (cnets_ours.py:976-1018): rows of x1[:, :H] hold the incoming hidden states. */
 int vs_draft_forward(const vs_draft* dm, const vs_scratch* s, int T, const int32_t* ids, const int32_t* pos_ids,
                      const int32_t* kv_row_base, int kv_row_off, const int32_t* n_ctx, int n_new, int causal,

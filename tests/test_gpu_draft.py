@@ -187,7 +187,7 @@ def test_draft_decode_forward_global_feature_and_tree_match_oracle(name, m):
         k0 = do_zero_g.stable_kv[0][0][:, n_c:n_c + m]
         h0 = ulp_hist(eng.k_cache[:, n_c:n_c + m], k0)
         record(f"decode_k_rows_zero_g_control/{name}/m{m}", h0)
-        assert h0["le4"] < 0.8 and h0["exact"] < 0.3 and h0["max_ulps"] > hk["max_ulps"], \
+        assert h0["le2"] < 0.7 and h0["exact"] < 0.3 and h0["le2"] < hk["le2"] - 0.25, \
             f"the test cannot see a missing global-feature add: {h0}"
 
 

@@ -400,7 +400,7 @@ def test_program_slab_residual_and_folded_norm(T):
     p = slab_program(build, [(w, L.EPI_RESID)])
     assert p.phase_types() == [L.PH_GEMM2]                     # the norm ran inside the GEMM phase
     h_ref = (r[:T].float() + rbf(x.float() @ w.float().T)).to(BF)
-    assert_bf16_close(h[:T], h_ref)
+    assert_bf16_close(h[:T], h_ref, atol=4e-2)      # (one ulp of a residual value in [4, 8) is 0.031)
     hf = h[:T].float()
     xn_ref = nw * (hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(BF)
     assert_bf16_close(xn[:T], xn_ref, frac_exact=0.98)

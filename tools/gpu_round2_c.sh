@@ -12,13 +12,13 @@ VS_SLAB_PACKED=$MODE VS_SLAB_M64=0 slab_tests > gpurun_out/t_slab_m128.log 2>&1;
 export VS_SLAB_PACKED=$MODE; echo "USING VS_SLAB_PACKED=$MODE"
 timeout 900 python -m pytest tests -q -m gpu $T > gpurun_out/t_all.log 2>&1; echo all_rc=$?
 tail -n 12 gpurun_out/t_all.log
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_r2c.json 2> gpurun_out/bench_r2c.err; echo bench_rc=$?
-VS_SLAB_M64=0 timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-fixture > gpurun_out/bench_r2c_m128.json 2> gpurun_out/bench_r2c_m128.err; echo bench_m128_rc=$?
-timeout 300 python tools/trace_cycle.py --json gpurun_out/trace_r2c.json > gpurun_out/trace_r2c.txt 2>&1; echo trace_rc=$?
-cat gpurun_out/trace_r2c.txt | tail -n 40
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_r2d.json 2> gpurun_out/bench_r2d.err; echo bench_rc=$?
+VS_SLAB_M64=0 timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-fixture > gpurun_out/bench_r2d_m128.json 2> gpurun_out/bench_r2d_m128.err; echo bench_m128_rc=$?
+timeout 300 python tools/trace_cycle.py --json gpurun_out/trace_r2d.json > gpurun_out/trace_r2d.txt 2>&1; echo trace_rc=$?
+cat gpurun_out/trace_r2d.txt | tail -n 40
 python - <<'PY'
 import json
-for f in ("bench_r2c","bench_r2c_m128"):
+for f in ("bench_r2d","bench_r2d_m128"):
     try:
         d=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
         print(f, d["value"], d["roofline"]["frac"], {k:v["us"] for k,v in (d.get("phases_us_per_cycle") or {}).items()})

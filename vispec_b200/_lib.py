@@ -86,6 +86,15 @@ class Draft(C.Structure):
                 ("x1", c_vp), ("x2", c_vp), ("logits", c_vp)]
 
 
+class Adaptor(C.Structure):
+    _fields_ = [("w_kv", c_vp), ("b_kv", c_vp), ("w_o", c_vp), ("q", c_vp), ("num_q", c_i32)]
+
+
+class PrefillWs(C.Structure):
+    _fields_ = [("max_rows", c_i32), ("img_k", c_vp), ("img_v", c_vp), ("x1", c_vp), ("x2", c_vp), ("fused", c_vp),
+                ("adapted", c_vp), ("attn_out", c_vp), ("pos", c_vp), ("packed", c_vp)]
+
+
 _SIGS = {
     "vs_last_error": (C.c_char_p, []),
     "vs_abi_version": (C.c_int, []),
@@ -111,6 +120,8 @@ _SIGS = {
                                  c_vp, c_vp]),
     "vs_draft_forward": (C.c_int, [C.POINTER(Draft), C.POINTER(Scratch), C.c_int, c_vp, c_vp, c_vp, C.c_int, c_vp,
                                    C.c_int, C.c_int, c_vp, c_vp]),
+    "vs_img_adaptor_prefill": (C.c_int, [C.POINTER(Draft), C.POINTER(Adaptor), C.POINTER(Scratch), C.POINTER(PrefillWs), c_vp,
+                                         c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "vs_draft_levels": (C.c_int, [C.POINTER(Draft), C.POINTER(Scratch), C.POINTER(TreeBufs), c_vp, C.c_int, c_vp,
                                   C.c_int, c_vp]),
     "vs_draft_tree": (C.c_int, [C.POINTER(Draft), C.POINTER(Scratch), C.POINTER(TreeBufs), c_vp, c_vp]),

@@ -68,6 +68,21 @@ int linear(const vs_scratch* s, const bf16* X, long ldx, const bf16* W, const bf
   return VS_OK;
 }
 
+// packed position ids of the draft prefill (cnets_ours.py:932-948): text before the image run keeps its positions, the
+// num_q - 1 compressed image tokens take the LAST positions of the run, text after the run keeps its positions
+__global__ void prefill_positions_kernel(int32_t* pos, int n_pre, int n_c_img, int img_end, int n_post) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_c = n_pre + n_c_img + n_post;
+  if (i >= n_c) return;
+  pos[i] = i < n_pre ? i : (i < n_pre + n_c_img ? img_end - n_c_img + (i - n_pre) : img_end + (i - n_pre - n_c_img));
+}
+
+// rows [0, n) of src (ld lds) -> dst (ld ldd), `cols` bf16 elements each
+cudaError_t copy_rows(bf16* dst, long ldd, const bf16* src, long lds, int n, int cols, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  return cudaMemcpy2DAsync(dst, ldd * 2, src, lds * 2, (size_t)cols * 2, n, cudaMemcpyDeviceToDevice, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -238,6 +253,84 @@ int vs_draft_forward(const vs_draft* dm, const vs_scratch* s, int T, const int32
   RET(linear(s, B(dm->x2), 2L * H, B(dm->w_fc), B(dm->b_fc), T, H, 2 * H, vs::EPI_STORE, B(s->h), H, nullptr, 0, st));
   return vs_decoder_layer(d, &dm->layer, s, &dm->rope, T, pos_ids, kv_row_base, kv_row_off, n_ctx, 0, n_new, causal, bits,
                           0, stream);
+}
+
+int vs_img_adaptor_prefill(const vs_draft* dm, const vs_adaptor* ad, const vs_scratch* s, const vs_prefill_ws* ws,
+                           const void* hidden, const void* emb_shifted, int L, int img_start, int img_end, void* g_out,
+                           void* last_row_out, int32_t* state, void* stream) {
+  REQUIRE(dm && s && ws && hidden && emb_shifted && g_out && state, "null operand");
+  REQUIRE(L >= 1, "empty prompt");
+  const bool has_img = img_start >= 0;
+  REQUIRE(!has_img || (ad && img_start < img_end && img_end <= L), "image run must satisfy 0 <= start < end <= L");
+  cudaStream_t st = S(stream);
+  const vs_dims* d = &dm->dims;
+  const int H = d->hidden, nh = d->n_heads;
+  const int n_img = has_img ? img_end - img_start : 0;
+  const int n_pre = has_img ? img_start : L, n_post = has_img ? L - img_end : 0;
+  const int n_c_img = has_img ? ad->num_q - 1 : 0;
+  const int n_text = n_pre + n_post, n_c = n_text + n_c_img;
+  REQUIRE(!has_img || (ad->num_q >= 1 && ad->num_q <= VS_TOK_BLOCK), "num_q must be in 1..32");
+  REQUIRE(n_c >= 1 && n_c <= ws->max_rows && n_img <= ws->max_rows && ws->max_rows <= s->max_rows,
+          "prompt exceeds the prefill workspace / scratch rows");
+  const bf16* hid = B(hidden);
+  const bf16* emb = B(emb_shifted);
+  bf16* x1 = B(ws->x1);
+  bf16* x2 = B(ws->x2);
+  bf16* fused = B(ws->fused);
+  bf16* adapted = B(ws->adapted);
+  bf16* h = B(s->h);
+  if (has_img) {
+    // ---- ImgAdaptor.forward (cnets_ours.py:630-661): K,V = Linear(image embeds) head-major, the num_q learned queries
+    // cross-attend over the image rows (no mask), o_proj.  The image rows are one contiguous run of the prompt.
+    const long kvs = (long)ws->max_rows * 128;
+    vs::GemmArgs g;
+    g.X = emb + (long)img_start * H; g.ldx = H; g.W = B(ad->w_kv); g.ldw = H; g.bias = B(ad->b_kv);
+    g.T = n_img; g.N = 2 * H; g.K = H;
+    g.splits = splits_for(s, g.N, g.K, n_img); g.partials = s->partials; g.counters = s->counters;
+    g.epi = vs::EPI_HEADS; g.n_q_tiles = 0; g.n_k_tiles = nh; g.rope = 0;
+    g.Kout = B(ws->img_k); g.Vout = B(ws->img_v); g.kv_head_stride = kvs;
+    CK(vs::launch_gemm(g, st));
+    vs::AttnArgs a;
+    a.Q = B(ad->q); a.q_head_stride = 32L * 128; a.K = B(ws->img_k); a.V = B(ws->img_v); a.kv_head_stride = kvs;
+    a.n_heads = nh; a.n_kv_heads = nh; a.Tq = ad->num_q; a.n_ctx = nullptr; a.n_ctx_host = n_img; a.n_new = 0;
+    a.causal = 0; a.bits = nullptr; a.eager = 0; a.scale = 1.0f / sqrtf(128.0f);
+    a.scores = s->scores; a.score_ld = s->score_ld; a.stats = s->stats; a.max_chunks = s->max_chunks;
+    a.opart = s->opart; a.pv_splits = s->pv_splits; a.counters = s->attn_counters;
+    a.O = B(ws->attn_out); a.ldo = H;
+    REQUIRE(n_img <= s->score_ld, "image run longer than the scratch's score rows");
+    CK(vs::launch_attention(a, st));
+    RET(linear(s, B(ws->attn_out), H, B(ad->w_o), nullptr, ad->num_q, H, H, vs::EPI_STORE, adapted, H, nullptr, 0, st));
+    CK(cudaMemcpyAsync(g_out, adapted + (long)(ad->num_q - 1) * H, (size_t)H * 2, cudaMemcpyDeviceToDevice, st));   // :930
+  } else {
+    CK(cudaMemsetAsync(g_out, 0, (size_t)H * 2, st));                 // :977-981: the dummy adaptor call adds 0
+  }
+  // ---- text rows: fc(cat(emb, img_fc(cat(hid, g)))) with g = 0 before the image run and the new g behind it (:918-948)
+  if (n_text > 0) {
+    CK(copy_rows(x1, 2L * H, hid, H, n_pre, H, st));
+    CK(copy_rows(x1 + (long)n_pre * 2 * H, 2L * H, hid + (long)img_end * H, H, n_post, H, st));
+    CK(cudaMemset2DAsync(x1 + H, 2L * H * 2, 0, (size_t)H * 2, n_pre, st));
+    if (n_post > 0) CK(vs::launch_broadcast_row(B(g_out), x1 + (long)n_pre * 2 * H + H, 2L * H, n_post, H, st));
+    CK(copy_rows(x2, 2L * H, emb, H, n_pre, H, st));
+    CK(copy_rows(x2 + (long)n_pre * 2 * H, 2L * H, emb + (long)img_end * H, H, n_post, H, st));
+    RET(linear(s, x1, 2L * H, B(dm->w_img_fc), B(dm->b_img_fc), n_text, H, 2 * H, vs::EPI_STORE, x2 + H, 2L * H, nullptr, 0, st));
+    RET(linear(s, x2, 2L * H, B(dm->w_fc), B(dm->b_fc), n_text, H, 2 * H, vs::EPI_STORE, fused, H, nullptr, 0, st));
+  }
+  // ---- packed order: pre-text, compressed image tokens, post-text; their position ids
+  CK(copy_rows(h, H, fused, H, n_pre, H, st));
+  if (n_c_img > 0) CK(copy_rows(h + (long)n_pre * H, H, adapted, H, n_c_img, H, st));
+  CK(copy_rows(h + (long)(n_pre + n_c_img) * H, H, fused + (long)n_pre * H, H, n_post, H, st));
+  prefill_positions_kernel<<<(n_c + 255) / 256, 256, 0, st>>>(ws->pos, n_pre, n_c_img, has_img ? img_end : 0, n_post);
+  CK(cudaGetLastError());
+  if (ws->packed) CK(copy_rows(B(ws->packed), H, h, H, n_c, H, st));
+  // ---- the draft's decoder layer over the packed rows (causal, cnets_ours.py:971-975), KV rows [0, n_c) of the cache
+  RET(vs_decoder_layer(d, &dm->layer, s, &dm->rope, n_c, ws->pos, nullptr, 0, nullptr, 0, n_c, 1, nullptr, 0, stream));
+  // ---- state for the decode calls: g in the right half of x1, the last row to continue from, lengths
+  CK(vs::launch_broadcast_row(B(g_out), B(dm->x1) + H, 2L * H, VS_TOK_BLOCK, H, st));
+  if (last_row_out) CK(cudaMemcpyAsync(last_row_out, h + (long)(n_c - 1) * H, (size_t)H * 2, cudaMemcpyDeviceToDevice, st));
+  CK(vs::launch_set_state(state, VS_ST_D_LEN, n_c, st));
+  CK(vs::launch_set_state(state, VS_ST_D_POS, L, st));
+  CK(vs::launch_set_state(state, VS_ST_LAST_ROW, 0, st));
+  return n_c;
 }
 
 int vs_draft_levels(const vs_draft* dm, const vs_scratch* s, const vs_tree_bufs* tb, int32_t* state, int head_rows,

@@ -214,6 +214,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
               const uint32_t nblk = (uint32_t)(min(kc, nk - j0) * nt);
               const uint8_t* src = ubase + (long)j0 * nt * blk;
               mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+              if (hdr.debug & 2) {
+                mbar_arrive(&full_w[stage]);
+                if (++stage == NS) { stage = 0; par ^= 1; }
+                continue;
+              }
               mbar_expect_tx(&full_w[stage], nblk * blk);
               uint8_t* dst = smem + stage * STAGE_BYTES;
               if (blk == blk_smem) {
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
                   const uint64_t da = rel ? make_desc_rel(blk) : make_desc(blk);
 #pragma unroll
                   for (int k = 0; k < BK / 16; ++k)
-                    tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
+                    if (!(hdr.debug & 4)) tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
                 }
               }
               tc_commit(&empty[stage]);
@@ -353,6 +358,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
             const int j0 = slab_stage(s % spp, rot, spp) * kc;
             const int nj = min(kc, nk - j0);
             mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+            if (hdr.debug & 1) {
+              mbar_arrive(&full_x[stage]);
+              if (++stage == NS) { stage = 0; par ^= 1; }
+              continue;
+            }
             mbar_expect_tx(&full_x[stage], nj * X_STAGE);
             uint8_t* dst = smem + stage * STAGE_BYTES + x_off;
             if (tm3 && nj == kc) {
@@ -434,7 +444,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
           }
         } break;
         case PH_GEMM2:
-          slab_epilogue(ph, epoch, b, G, wtid, tmem_base, acc, acc_par, tfull, tempty, *reinterpret_cast<SlabRed*>(team_base));
+          slab_epilogue(ph, epoch, b, G, wtid, tmem_base, acc, acc_par, tfull, tempty, *reinterpret_cast<SlabRed*>(team_base),
+                        (hdr.debug & 8) != 0);
           break;
         case PH_EPI: epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
@@ -517,6 +528,7 @@ struct vs_program {
   int pf_ahead = 0;            // L2 prefetch distance (tensor-map prefetch costs as much TMA issue as the load itself: off)
   int inflight = 0;           // weight stages in flight per SM (0 = the whole ring)
   int spin_ns = 100;          // back-off of the single-lane role warps between barrier polls
+  int debug = 0;              // ProgramHeader::debug
   bool committed = false;
   bool trace_on = false;
   // device workspace layout (set by commit)
@@ -934,6 +946,8 @@ int vs_program_create(vs_program** out) {
   if (e) (*out)->spin_ns = atoi(e);
   e = getenv("VS_X3D");
   if (e) (*out)->x3d = atoi(e) != 0;
+  e = getenv("VS_PG_DEBUG");
+  if (e) (*out)->debug = atoi(e);
   return VS_OK;
 }
 
@@ -961,6 +975,7 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   }
   else if (!strcmp(name, "spin_ns")) pg->spin_ns = value;
   else if (!strcmp(name, "x3d")) pg->x3d = value != 0;
+  else if (!strcmp(name, "debug")) pg->debug = value;
 
   else if (!strcmp(name, "grid")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "grid must be set before adding phases");
@@ -1098,6 +1113,7 @@ int vs_program_run(const vs_program* pg, void* stream) {
   h.pf_ahead = pg->pf_ahead;
   h.inflight = pg->inflight;
   h.spin_ns = pg->spin_ns;
+  h.debug = pg->debug;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pg->grid);
   cfg.blockDim = dim3(PG_THREADS);

@@ -105,6 +105,8 @@ struct ProgramHeader {
   int pf_ahead;                    // L2 prefetch distance in 16 KB weight chunks per CTA (0 = off)
   int inflight;                    // weight stages issued-but-not-landed per CTA (0 = whole ring)
   unsigned int spin_ns;            // back-off of the role warps between barrier polls
+  int debug;                       // ablation switches for tools/bench_slab_phases.py (results are garbage): 1 = no activation
+                                   // loads, 2 = no weight loads, 4 = no MMAs, 8 = workers back off while the GEMM streams
 };
 
 // ---- host-side phase constructors (program.cu); the C API and the composite builders live in program_api.cu ----

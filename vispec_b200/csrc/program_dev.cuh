@@ -341,7 +341,8 @@ struct SlabRed {
 };
 
 __device__ __noinline__ void slab_epilogue(const Phase& ph, unsigned int epoch, int b, int G, int wtid, uint32_t tmem_base,
-                                           int& acc, int& acc_par, uint64_t* tfull, uint64_t* tempty, SlabRed& red) {
+                                           int& acc, int& acc_par, uint64_t* tfull, uint64_t* tempty, SlabRed& red,
+                                           bool backoff = false) {
   const int wwarp = wtid >> 5, lane = wtid & 31, quarter = wwarp & 3, cg = wwarp >> 2;
   const int T = ph.T, epi = ph.epi;
   const int passes = ph.s_passes, n_tiles = ph.s_ntiles, rows_alloc = ph.s_rows_alloc, pair = ph.s_pair;
@@ -409,7 +410,8 @@ __device__ __noinline__ void slab_epilogue(const Phase& ph, unsigned int epoch, 
       }
     }
     // ---- the accumulators of this pass
-    mbar_wait(&tfull[acc], acc_par);
+    if (backoff) mbar_wait_sleep(&tfull[acc], acc_par, 200);
+    else mbar_wait(&tfull[acc], acc_par);
     tc_fence_after();
     float a[2][8];
     tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 64 + t0, a[0]);

@@ -598,6 +598,8 @@ class DraftEngine:
         self.last_img_hidden = torch.zeros(1, H, dtype=self.dtype, device=dev)
         self._alloc_tree()
         self.state: Optional[torch.Tensor] = None       # shared with the target engine (bind_state)
+        self.adaptor_c = L.Adaptor(L.ptr(self.w_akv), L.ptr(self.b_akv), L.ptr(self.w_ao), L.ptr(self.adpt_q), cfg.num_q)
+        self._ws_cache: Dict[int, tuple] = {}           # prefill work buffers by row count (vs_img_adaptor_prefill)
         self._prog_levels: Dict[bool, Program] = {}     # LM head + draft levels + tree build after the prefill
         self._prog_tree: Dict[bool, Program] = {}       # stable forward of the accepted rows + the above
         # (keyed by: single-phase attention usable for the current draft KV length)
@@ -641,9 +643,85 @@ class DraftEngine:
         self.state[L.ST_D_POS] = 0
 
     # -- first call: image/prefill branch (cnets_ours.py:879-975) -----------------------------------------
+    def _prefill_ws(self, rows: int):
+        """Work buffers of vs_img_adaptor_prefill for prompts of up to `rows` rows, cached by size (no per-prompt
+        allocation once a size has been seen)."""
+        rows = _ceil(max(rows, 32), 32)
+        ws = self._ws_cache.get(rows)
+        if ws is None:
+            cfg, dev, H, nh = self.cfg, self.device, self.cfg.hidden, self.cfg.heads
+            z = lambda *s, dtype=self.dtype: torch.zeros(*s, dtype=dtype, device=dev)
+            t = dict(img_k=z(nh, rows, 128), img_v=z(nh, rows, 128), x1=z(rows, 2 * H), x2=z(rows, 2 * H), fused=z(rows, H),
+                     adapted=z(32, H), attn_out=z(32, H), pos=z(rows, dtype=torch.int32), packed=z(rows, H))
+            sc = ScratchBuffers(H, cfg.inter, nh, cfg.vocab, rows, rows, dev, extra_n=2 * H)
+            c = L.PrefillWs(rows, *[L.ptr(t[k]) for k in ("img_k", "img_v", "x1", "x2", "fused", "adapted", "attn_out", "pos",
+                                                           "packed")])
+            ws = self._ws_cache[rows] = (t, sc, c)
+            while len(self._ws_cache) > 4:                       # keep the few most recent sizes
+                self._ws_cache.pop(next(iter(self._ws_cache)))
+        return ws
+
     @torch.no_grad()
     def prefill(self, hidden: torch.Tensor, inputs_embeds: torch.Tensor, image_mask: Optional[torch.Tensor],
                 sample_token: int):
+        """hidden [1,L,H] target features; inputs_embeds [1,L,H] ALREADY shifted by one (cnets_ours.py:1066-1082);
+        image_mask [1,L] bool in the unshifted frame or None.  One C-ABI call (vs_img_adaptor_prefill) builds the packed
+        sequence (text rows through fc/img_fc, the image run compressed by the adaptor to num_q-1 tokens at the run's last
+        positions) and runs the decoder layer over it; a second one expands the draft tree."""
+        if os.environ.get("VS_DRAFT_PREFILL", "native") == "python":
+            return self.prefill_python(hidden, inputs_embeds, image_mask, sample_token)
+        cfg, lib, dev, H = self.cfg, self.lib, self.device, self.cfg.hidden
+        hid = hidden[0].to(dev, self.dtype).contiguous()
+        emb = inputs_embeds[0].to(dev, self.dtype).contiguous()
+        Lq = hid.shape[0]
+        img_start, img_end = -1, -1
+        if image_mask is not None:
+            im = image_mask[0, 1:].to(dev)                                  # :880 (shifted frame, L-1 entries)
+            idx = torch.nonzero(im).flatten()
+            if idx.numel() == 0:
+                raise NotImplementedError("image_mask without an image token (the reference fails too, cnets_ours.py:938-941)")
+            first, last = [int(v) for v in torch.stack((idx[0], idx[-1])).tolist()]     # the one host sync: two ints
+            if last - first + 1 != idx.numel():
+                raise NotImplementedError("exactly one contiguous image run is supported "
+                                          "(the reference fails on more, cnets_ours.py:938-941,1021)")
+            img_start, img_end = first, last + 1
+        n_c = Lq if img_start < 0 else Lq - (img_end - img_start) + cfg.num_q - 1
+        if n_c + 8 * (cfg.depth + 1) + 8 > self.cache_rows:
+            raise ValueError("draft KV cache too small for this prompt")
+        if Lq + cfg.depth + 2 > self.rope_rows:
+            raise ValueError("prompt positions exceed the draft's rotary table")
+        t, sc, ws = self._prefill_ws(max(n_c, img_end - img_start, 1))
+        g_new = torch.empty(1, H, dtype=self.dtype, device=dev)
+        got = lib.vs_img_adaptor_prefill(C.byref(self.c), C.byref(self.adaptor_c), C.byref(sc.c), C.byref(ws), L.ptr(hid),
+                                         L.ptr(emb), Lq, img_start, img_end, L.ptr(g_new), L.ptr(self.scratch.h),
+                                         L.ptr(self.state), _stream())
+        if got < 0:
+            L.check(got, "vs_img_adaptor_prefill")
+        assert got == n_c
+        self.last_img_hidden = g_new
+        self.prefill_packed = t["packed"][:n_c]                              # views kept for the parity tests
+        self.prefill_out = sc.h[:n_c]
+        self.prefill_pos = t["pos"][:n_c]
+        self._expand_after_prefill(n_c, sample_token)
+
+    def _expand_after_prefill(self, n_c: int, sample_token: int):
+        cfg, lib, dev = self.cfg, self.lib, self.device
+        if use_programs():
+            self.state[L.ST_NEXT_TOKEN] = int(sample_token)
+            fused = n_c + 8 * (cfg.depth + 1) <= self.scratch.fused_kv_capacity
+            if self._prog_levels.get(fused) is None:
+                pr = Program(dev, attn_fused=fused).register_tiled(self.tiled)
+                pr.add("draft_levels", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb),
+                       L.ptr(self.state), 1, self.state.data_ptr() + 4 * L.ST_NEXT_TOKEN, 0)
+                self._prog_levels[fused] = pr.commit()
+            self._prog_levels[fused].run()
+            return
+        L.check(lib.vs_draft_levels(C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state), 1,
+                                    None, int(sample_token), _stream()), "vs_draft_levels")
+
+    @torch.no_grad()
+    def prefill_python(self, hidden: torch.Tensor, inputs_embeds: torch.Tensor, image_mask: Optional[torch.Tensor],
+                       sample_token: int):
         """hidden [1,L,H] target features; inputs_embeds [1,L,H] ALREADY shifted by one (cnets_ours.py:1066-1082);
         image_mask [1,L] bool in the unshifted frame or None.  Builds the packed sequence (text rows through
         fc/img_fc, the image run compressed by the adaptor to num_q-1 tokens at the run's last positions),
