@@ -192,197 +192,249 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The three role warps run CONVERGED (all 32 lanes walk the program) and one elected lane issues each TMA / tcgen05
+  // instruction.  Those instructions take their operands from uniform registers; inside a single-lane branch the compiler
+  // cannot prove an operand warp-uniform and wraps every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop --
+  // measured ~85 ns per tcgen05.mma and ~190 ns per bulk copy from one lane (tools/bench_slab_phases.py, ablation 3 / 4),
+  // which capped a GEMM phase at ~13 MMAs per microsecond whatever the operand sizes.  Values read from the phase table are
+  // made provably uniform with a shuffle from lane 0.
   if (warp == 0) {
     // ===================== weight producer =====================
-    // Walks every GEMM phase of the program in order.  Weights never depend on activations, so this thread runs ahead of
+    // Walks every GEMM phase of the program in order.  Weights never depend on activations, so this warp runs ahead of
     // the rest of the CTA across phase boundaries: the ring (NS x 32 KB) is the run-ahead buffer.
-    if (lane == 0) {
-      int stage = 0, par = 0;
-      for (int p = 0; p < hdr.n_phases; ++p) {
-        const Phase& ph = hdr.phases[p];
-        if (ph.type == PH_GEMM2) {
-          const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
-          const uint32_t blk = (uint32_t)ph.s_blk_bytes, blk_smem = (uint32_t)ph.s_blk_smem;
-          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(ph.Wt);
-          const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
-          for (int ps = 0; ps < passes; ++ps) {
-            const int u = b * passes + ps;
-            if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
-            const uint8_t* ubase = wbase + (long)u * ph.s_unit_stride;
-            for (int s = 0; s < spp; ++s) {
-              const int j0 = slab_stage(s, rot, spp) * kc;          // (rotated k order, see slab_stage)
-              const uint32_t nblk = (uint32_t)(min(kc, nk - j0) * nt);
-              const uint8_t* src = ubase + (long)j0 * nt * blk;
-              mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
-              if (hdr.debug & 2) {
-                mbar_arrive(&full_w[stage]);
-                if (++stage == NS) { stage = 0; par ^= 1; }
-                continue;
-              }
-              mbar_expect_tx(&full_w[stage], nblk * blk);
-              uint8_t* dst = smem + stage * STAGE_BYTES;
-              if (blk == blk_smem) {
+    int stage = 0, par = 0;
+    const unsigned int spin = hdr.spin_ns;
+    for (int p = 0; p < hdr.n_phases; ++p) {
+      const Phase& ph = hdr.phases[p];
+      const int type = uni(ph.type);
+      if (type == PH_GEMM2) {
+        const int passes = uni(ph.s_passes), kc = uni(ph.s_kc), nk = uni(ph.nk), nt = uni(ph.s_ntiles);
+        const uint32_t blk = (uint32_t)uni(ph.s_blk_bytes), blk_smem = (uint32_t)uni(ph.s_blk_smem);
+        const int e_per = uni(ph.s_eper), e_rem = uni(ph.s_erem);
+        const long unit_stride = (long)uni64((unsigned long long)ph.s_unit_stride);
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(uni64(reinterpret_cast<unsigned long long>(ph.Wt)));
+        const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
+        for (int ps = 0; ps < passes; ++ps) {
+          const int u = b * passes + ps;
+          if (e_per + (u < e_rem ? 1 : 0) == 0) continue;
+          const uint8_t* ubase = wbase + (long)u * unit_stride;
+          for (int s = 0; s < spp; ++s) {
+            const int j0 = slab_stage(s, rot, spp) * kc;          // (rotated k order, see slab_stage)
+            const uint32_t nblk = (uint32_t)(min(kc, nk - j0) * nt);
+            const uint8_t* src = ubase + (long)j0 * nt * blk;
+            if (lane == 0) mbar_wait_sleep(&empty[stage], par ^ 1, spin);
+            __syncwarp();
+            uint8_t* dst = smem + stage * STAGE_BYTES;
+            if (hdr.debug & 2) {
+              if (elect_one()) mbar_arrive(&full_w[stage]);
+            } else if (blk == blk_smem) {
+              if (elect_one()) {
+                mbar_expect_tx(&full_w[stage], nblk * blk);
                 bulk_load(dst, src, nblk * blk, &full_w[stage], HINT_EVICT_FIRST);     // the whole stage: one copy
-              } else {
-                for (uint32_t i = 0; i < nblk; ++i)
-                  bulk_load(dst + i * blk_smem, src + i * blk, blk, &full_w[stage], HINT_EVICT_FIRST);
               }
-              if (++stage == NS) { stage = 0; par ^= 1; }
+            } else {
+              if (elect_one()) mbar_expect_tx(&full_w[stage], nblk * blk);
+              __syncwarp();
+              for (uint32_t i = 0; i < nblk; ++i)
+                if (elect_one()) bulk_load(dst + i * blk_smem, src + i * blk, blk, &full_w[stage], HINT_EVICT_FIRST);
             }
+            __syncwarp();
+            if (++stage == NS) { stage = 0; par ^= 1; }
           }
-        } else if (ph.type == PH_GEMM) {
-          const int2 r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
-          const int nk = ph.nk;
-          const CUtensorMap* tm = hdr.maps + ph.tmW;
-          const bf16* wt = ph.Wt;                            // tiled layout: chunk c is the 16 KB block c of the matrix
-          int tile = r.x / nk, kc = r.x % nk;
-          for (int c = r.x; c < r.y; ++c) {
-            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+        }
+      } else if (type == PH_GEMM) {
+        const int off = uni(ph.range_off);
+        const int2 r = *reinterpret_cast<const int2*>(hdr.tables + off + 2 * b);
+        const int lo = uni(r.x), hi = uni(r.y);
+        const int nk = uni(ph.nk);
+        const CUtensorMap* tm = hdr.maps + uni(ph.tmW);
+        const bf16* wt = reinterpret_cast<const bf16*>(uni64(reinterpret_cast<unsigned long long>(ph.Wt)));
+        int tile = lo / nk, kc = lo % nk;
+        for (int c = lo; c < hi; ++c) {
+          if (lane == 0) mbar_wait_sleep(&empty[stage], par ^ 1, spin);
+          __syncwarp();
+          if (elect_one()) {
             mbar_expect_tx(&full_w[stage], W_STAGE);
             if (wt) bulk_load(smem + stage * STAGE_BYTES, wt + (long)c * (BM * BK), W_STAGE, &full_w[stage], HINT_EVICT_FIRST);
             else tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES, kc * BK, tile * BM, HINT_EVICT_FIRST);
-            if (++stage == NS) { stage = 0; par ^= 1; }
-            if (++kc == nk) { kc = 0; ++tile; }
           }
+          __syncwarp();
+          if (++stage == NS) { stage = 0; par ^= 1; }
+          if (++kc == nk) { kc = 0; ++tile; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0, par = 0, acc = 0, acc_par = 0;
-      for (int p = 0; p < hdr.n_phases; ++p) {
-        const Phase& ph = hdr.phases[p];
-        if (ph.type == PH_GEMM2) {
-          const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
-          const uint32_t blk_smem = (uint32_t)ph.s_blk_smem, x_off = (uint32_t)ph.s_xoff;
-          const uint32_t idesc = ph.s_m64 ? IDESC_M64 : IDESC;
-          const bool rel = ph.s_packed == 2;
-          const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
-          for (int ps = 0; ps < passes; ++ps) {
-            const int u = b * passes + ps;
-            if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
-            mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
+    int stage = 0, par = 0, acc = 0, acc_par = 0;
+    const unsigned int spin = hdr.spin_ns;
+    for (int p = 0; p < hdr.n_phases; ++p) {
+      const Phase& ph = hdr.phases[p];
+      const int type = uni(ph.type);
+      if (type == PH_GEMM2) {
+        const int passes = uni(ph.s_passes), kc = uni(ph.s_kc), nk = uni(ph.nk), nt = uni(ph.s_ntiles);
+        const uint32_t blk_smem = (uint32_t)uni(ph.s_blk_smem), x_off = (uint32_t)uni(ph.s_xoff);
+        const int e_per = uni(ph.s_eper), e_rem = uni(ph.s_erem);
+        const uint32_t idesc = uni(ph.s_m64) ? IDESC_M64 : IDESC;
+        const bool rel = uni(ph.s_packed) == 2;
+        const int spp = (nk + kc - 1) / kc;
+        for (int ps = 0; ps < passes; ++ps) {
+          const int u = b * passes + ps;
+          if (e_per + (u < e_rem ? 1 : 0) == 0) continue;
+          if (lane == 0) mbar_wait_sleep(&tempty[acc], acc_par ^ 1, spin);
+          __syncwarp();
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 64;
+          for (int s = 0; s < spp; ++s) {
+            const int nj = min(kc, nk - slab_stage(s, slab_rotation(b, G, spp), spp) * kc);
+            if (lane == 0) {
+              mbar_wait_sleep(&full_w[stage], par, spin);
+              mbar_wait_sleep(&full_x[stage], par, spin);
+            }
+            __syncwarp();
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 64;
-            for (int s = 0; s < spp; ++s) {
-              const int j0 = slab_stage(s, rot, spp) * kc;
-              const int nj = min(kc, nk - j0);
-              mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
-              mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
-              tc_fence_after();
-              const uint8_t* base = smem + stage * STAGE_BYTES;
+            const uint32_t base = smem_u32(smem) + stage * STAGE_BYTES;
+            if (!(hdr.debug & 4)) {
               for (int jj = 0; jj < nj; ++jj) {
-                const uint64_t db = make_desc(base + x_off + jj * X_STAGE);
+                const uint64_t db = make_desc_u32(base + x_off + jj * X_STAGE);
                 for (int t = 0; t < nt; ++t) {
-                  const uint8_t* blk = base + (uint32_t)(jj * nt + t) * blk_smem;
-                  const uint64_t da = rel ? make_desc_rel(blk) : make_desc(blk);
+                  const uint32_t blk = base + (uint32_t)(jj * nt + t) * blk_smem;
+                  const uint64_t da = rel ? make_desc_rel_u32(blk) : make_desc_u32(blk);
+                  if (elect_one()) {
 #pragma unroll
-                  for (int k = 0; k < BK / 16; ++k)
-                    if (!(hdr.debug & 4)) tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
+                    for (int k = 0; k < BK / 16; ++k)
+                      tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
+                  }
                 }
               }
-              tc_commit(&empty[stage]);
-              if (++stage == NS) { stage = 0; par ^= 1; }
             }
-            tc_commit(&tfull[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_par ^= 1;
+            if (elect_one()) tc_commit(&empty[stage]);
+            __syncwarp();
+            if (++stage == NS) { stage = 0; par ^= 1; }
           }
-        } else if (ph.type == PH_GEMM) {
-          const int2 r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
-          const int nk = ph.nk;
-          int c = r.x;
-          int tile = c / nk;
-          while (c < r.y) {
-            const int seg_end = min(r.y, (tile + 1) * nk);
-            mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
+          if (elect_one()) tc_commit(&tfull[acc]);
+          __syncwarp();
+          acc ^= 1;
+          if (acc == 0) acc_par ^= 1;
+        }
+      } else if (type == PH_GEMM) {
+        const int off = uni(ph.range_off);
+        const int2 r = *reinterpret_cast<const int2*>(hdr.tables + off + 2 * b);
+        const int lo = uni(r.x), hi = uni(r.y);
+        const int nk = uni(ph.nk);
+        int c = lo;
+        int tile = c / nk;
+        while (c < hi) {
+          const int seg_end = min(hi, (tile + 1) * nk);
+          if (lane == 0) mbar_wait_sleep(&tempty[acc], acc_par ^ 1, spin);
+          __syncwarp();
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 64;
+          bool first = true;
+          for (; c < seg_end; ++c) {
+            if (lane == 0) {
+              mbar_wait_sleep(&full_w[stage], par, spin);
+              mbar_wait_sleep(&full_x[stage], par, spin);
+            }
+            __syncwarp();
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 64;
-            bool first = true;
-            for (; c < seg_end; ++c) {
-              mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
-              mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
-              tc_fence_after();
-              const uint64_t da = make_desc(smem + stage * STAGE_BYTES);
-              const uint64_t db = make_desc(smem + stage * STAGE_BYTES + W_STAGE);
+            const uint32_t base = smem_u32(smem) + stage * STAGE_BYTES;
+            const uint64_t da = make_desc_u32(base);
+            const uint64_t db = make_desc_u32(base + W_STAGE);
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) tc_mma(d_tmem, da + 2 * k, db + 2 * k, (!first || k > 0) ? 1u : 0u);
               tc_commit(&empty[stage]);
-              first = false;
-              if (++stage == NS) { stage = 0; par ^= 1; }
             }
-            tc_commit(&tfull[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_par ^= 1;
-            ++tile;
+            __syncwarp();
+            first = false;
+            if (++stage == NS) { stage = 0; par ^= 1; }
           }
+          if (elect_one()) tc_commit(&tfull[acc]);
+          __syncwarp();
+          acc ^= 1;
+          if (acc == 0) acc_par ^= 1;
+          ++tile;
         }
       }
     }
   } else if (warp == 2) {
     // ===================== activation producer =====================
-    if (lane == 0) {
-      int stage = 0, par = 0;
-      for (int p = 0; p < hdr.n_phases; ++p) {
-        const Phase& ph = hdr.phases[p];
-        if (ph.type != PH_GEMM2 && ph.type != PH_GEMM) continue;
-        int n_stages;                                        // stages of this CTA in the phase
-        int2 r = make_int2(0, 0);
-        if (ph.type == PH_GEMM2) {
-          int units = 0;
-          for (int ps = 0; ps < ph.s_passes; ++ps) {
-            const int u = b * ph.s_passes + ps;
-            units += ph.s_eper + (u < ph.s_erem ? 1 : 0) > 0 ? 1 : 0;
-          }
-          n_stages = units * ((ph.nk + ph.s_kc - 1) / ph.s_kc);
-        } else {
-          r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
-          n_stages = r.y - r.x;
+    int stage = 0, par = 0;
+    const unsigned int spin = hdr.spin_ns;
+    for (int p = 0; p < hdr.n_phases; ++p) {
+      const Phase& ph = hdr.phases[p];
+      const int type = uni(ph.type);
+      if (type != PH_GEMM2 && type != PH_GEMM) continue;
+      int n_stages;                                        // stages of this CTA in the phase
+      int lo = 0, hi = 0;
+      const int nk = uni(ph.nk);
+      int kc = 1, e_per = 0, e_rem = 0, passes = 1;
+      if (type == PH_GEMM2) {
+        kc = uni(ph.s_kc); e_per = uni(ph.s_eper); e_rem = uni(ph.s_erem); passes = uni(ph.s_passes);
+        int units = 0;
+        for (int ps = 0; ps < passes; ++ps) {
+          const int u = b * passes + ps;
+          units += e_per + (u < e_rem ? 1 : 0) > 0 ? 1 : 0;
         }
-        if (n_stages <= 0) continue;
-        // the token tile is produced by earlier phases of this launch: wait until all of them completed everywhere
-        // (relaxed polling, no L1 invalidation storm; the tile itself is read by the TMA unit from L2, ordered behind the
-        // observed counter value by the proxy fence)
-        const unsigned int need = (unsigned int)ph.bars_before * (unsigned int)G;
+        n_stages = units * ((nk + kc - 1) / kc);
+      } else {
+        const int off = uni(ph.range_off);
+        const int2 r = *reinterpret_cast<const int2*>(hdr.tables + off + 2 * b);
+        lo = uni(r.x); hi = uni(r.y);
+        n_stages = hi - lo;
+      }
+      if (n_stages <= 0) continue;
+      // the token tile is produced by earlier phases of this launch: wait until all of them completed everywhere
+      // (relaxed polling, no L1 invalidation storm; the tile itself is read by the TMA unit from L2, ordered behind the
+      // observed counter value by the proxy fence)
+      const unsigned int need = (unsigned int)uni(ph.bars_before) * (unsigned int)G;
+      if (lane == 0) {
         while (ld_relaxed_u32(hdr.counters) < need) __nanosleep(64);
-        fence_proxy_async();
-        if (ph.type == PH_GEMM2) {
-          const int kc = ph.s_kc, nk = ph.nk;
-          const uint32_t x_off = (uint32_t)ph.s_xoff;
-          const CUtensorMap* tm3 = ph.tmX3 >= 0 ? hdr.maps + ph.tmX3 : nullptr;
-          const CUtensorMap* tm = hdr.maps + ph.tmX;
-          const int spp = (nk + kc - 1) / kc;                // stages per pass: every pass walks the same k-chunks
-          const int rot = slab_rotation(b, G, spp);
-          for (int s = 0; s < n_stages; ++s) {
-            const int j0 = slab_stage(s % spp, rot, spp) * kc;
-            const int nj = min(kc, nk - j0);
-            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
-            if (hdr.debug & 1) {
-              mbar_arrive(&full_x[stage]);
-              if (++stage == NS) { stage = 0; par ^= 1; }
-              continue;
-            }
-            mbar_expect_tx(&full_x[stage], nj * X_STAGE);
-            uint8_t* dst = smem + stage * STAGE_BYTES + x_off;
-            if (tm3 && nj == kc) {
+      }
+      __syncwarp();
+      fence_proxy_async();
+      const CUtensorMap* tm = hdr.maps + uni(ph.tmX);
+      if (type == PH_GEMM2) {
+        const uint32_t x_off = (uint32_t)uni(ph.s_xoff);
+        const int t3 = uni(ph.tmX3);
+        const CUtensorMap* tm3 = t3 >= 0 ? hdr.maps + t3 : nullptr;
+        const int spp = (nk + kc - 1) / kc;                // stages per pass: every pass walks the same k-chunks
+        const int rot = slab_rotation(b, G, spp);
+        for (int s = 0; s < n_stages; ++s) {
+          const int j0 = slab_stage(s % spp, rot, spp) * kc;
+          const int nj = min(kc, nk - j0);
+          if (lane == 0) mbar_wait_sleep(&empty[stage], par ^ 1, spin);
+          __syncwarp();
+          uint8_t* dst = smem + stage * STAGE_BYTES + x_off;
+          if (hdr.debug & 1) {
+            if (elect_one()) mbar_arrive(&full_x[stage]);
+          } else if (tm3 && nj == kc) {
+            if (elect_one()) {
+              mbar_expect_tx(&full_x[stage], nj * X_STAGE);
               tma_load_3d(tm3, &full_x[stage], dst, 0, 0, j0, HINT_EVICT_LAST);      // {64, 32, kc} box: kc blocks at once
-            } else {
-              for (int jj = 0; jj < nj; ++jj)
-                tma_load_2d(tm, &full_x[stage], dst + jj * X_STAGE, (j0 + jj) * BK, 0, HINT_EVICT_LAST);
             }
-            if (++stage == NS) { stage = 0; par ^= 1; }
+          } else {
+            if (elect_one()) mbar_expect_tx(&full_x[stage], nj * X_STAGE);
+            __syncwarp();
+            for (int jj = 0; jj < nj; ++jj)
+              if (elect_one()) tma_load_2d(tm, &full_x[stage], dst + jj * X_STAGE, (j0 + jj) * BK, 0, HINT_EVICT_LAST);
           }
-        } else {
-          const CUtensorMap* tm = hdr.maps + ph.tmX;
-          int kc = r.x % ph.nk;
-          for (int c = r.x; c < r.y; ++c) {
-            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+          __syncwarp();
+          if (++stage == NS) { stage = 0; par ^= 1; }
+        }
+      } else {
+        int kcc = lo % nk;
+        for (int c = lo; c < hi; ++c) {
+          if (lane == 0) mbar_wait_sleep(&empty[stage], par ^ 1, spin);
+          __syncwarp();
+          if (elect_one()) {
             mbar_expect_tx(&full_x[stage], X_STAGE);
-            tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kc * BK, 0, HINT_EVICT_LAST);
-            if (++stage == NS) { stage = 0; par ^= 1; }
-            if (++kc == ph.nk) kc = 0;
+            tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kcc * BK, 0, HINT_EVICT_LAST);
           }
+          __syncwarp();
+          if (++stage == NS) { stage = 0; par ^= 1; }
+          if (++kcc == nk) kcc = 0;
         }
       }
     }

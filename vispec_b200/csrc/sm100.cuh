@@ -86,6 +86,32 @@ __device__ __forceinline__ uint64_t make_desc_rel(const void* smem_tile) {
   uint64_t addr = smem_u32(smem_tile);
   return make_desc(smem_tile) | (((addr >> 7) & 7ull) << 49);
 }
+// descriptor builders from a 32-bit shared-memory address (warp-uniform arithmetic stays in uniform registers)
+__device__ __forceinline__ uint64_t make_desc_u32(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t make_desc_rel_u32(uint32_t addr) {
+  return make_desc_u32(addr) | ((uint64_t)((addr >> 7) & 7u) << 49);
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// a value every lane holds, made PROVABLY warp-uniform for the compiler
+__device__ __forceinline__ int uni(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ unsigned long long uni64(unsigned long long v) {
+  const unsigned int lo = __shfl_sync(0xffffffffu, (unsigned int)v, 0);
+  const unsigned int hi = __shfl_sync(0xffffffffu, (unsigned int)(v >> 32), 0);
+  return ((unsigned long long)hi << 32) | lo;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
