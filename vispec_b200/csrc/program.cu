@@ -43,21 +43,22 @@ namespace vs {
 
 namespace {
 
-// Ring of the role warps: NS slots of 32 KB (slab.h).  A slab stage (PH_GEMM2) fills a slot with kc k-chunks of this
-// CTA's weight rows + the matching activation blocks; a stream-K stage (PH_GEMM, row-major / tiled weights) uses the
-// first 20 KB of a slot (one 128 x 64 weight chunk + one 32 x 64 activation block).
-#ifndef VS_PG_STAGES
-#define VS_PG_STAGES 4
-#endif
-constexpr int BM = PG_BM, BK = PG_BK, NS = VS_PG_STAGES;
+// Ring of the role warps (run-ahead buffer of the weight stream), RING_BYTES of shared memory cut at launch into
+//   * 6 slots of 20 KB for a stream-K program (PH_GEMM: one 128 x 64 weight chunk + one 32 x 64 activation block per
+//     stage) -- the round-1 geometry: bytes in flight, not slot count, set the streaming rate, or
+//   * 4 slots of 32 KB when the program holds slab GEMMs (PH_GEMM2, slab.h: kc k-chunks of this CTA's weight rows + the
+//     matching activation blocks per stage); stream-K stages then use the first 20 KB of a slot.
+constexpr int BM = PG_BM, BK = PG_BK;
+constexpr int NS_MAX = 6;
+constexpr int RING_BYTES = 4 * SLAB_SLOT_BYTES;  // 131072
 constexpr int W_STAGE = BM * BK * 2;             // 16384
 constexpr int X_STAGE = VS_TOK * BK * 2;         // 4096
-constexpr int STAGE_BYTES = SLAB_SLOT_BYTES;     // 32768
-static_assert(W_STAGE + X_STAGE <= STAGE_BYTES, "stream-K stage larger than a ring slot");
+static_assert(NS_MAX * (W_STAGE + X_STAGE) <= RING_BYTES, "stream-K ring larger than the ring region");
+static_assert(W_STAGE + X_STAGE <= SLAB_SLOT_BYTES, "stream-K stage larger than a slab slot");
 constexpr int BIG_SMEM = 44032;                  // scratch of one attention team (AttnSmem); both together also stage the
                                                  // tree ops and the top-k merge on CTA 0
 constexpr int TEAM_SMEM = 1024;                  // reduction scratch of one small team
-constexpr int TEAM_OFF = NS * STAGE_BYTES + PG_BIG_TEAMS * BIG_SMEM;
+constexpr int TEAM_OFF = RING_BYTES + PG_BIG_TEAMS * BIG_SMEM;
 constexpr int PHASE_WORDS = (sizeof(Phase) + 3) / 4;
 constexpr int PHASE_SLOT = (sizeof(Phase) + 127) / 128 * 128;
 constexpr int PHBUF_OFF = TEAM_OFF + PG_TEAMS * TEAM_SMEM;             // two phase descriptors (double buffer)
@@ -159,11 +160,12 @@ __device__ __forceinline__ int slab_stage(int s, int rot, int spp) {
 __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHeader hdr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* team_base = smem + NS * STAGE_BYTES;
+  uint8_t* team_base = smem + RING_BYTES;
+  const int NS = hdr.ns, STAGE_BYTES = hdr.stage_bytes;      // ring geometry of this program (see RING_BYTES)
   uint64_t* full_w = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-  uint64_t* full_x = full_w + NS;
-  uint64_t* empty = full_x + NS;
-  uint64_t* tfull = empty + NS;
+  uint64_t* full_x = full_w + NS_MAX;
+  uint64_t* empty = full_x + NS_MAX;
+  uint64_t* tfull = empty + NS_MAX;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
   const int G = gridDim.x, b = blockIdx.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) {
+    for (int i = 0; i < NS_MAX; ++i) {
       mbar_init(&full_w[i], 1);
       mbar_init(&full_x[i], 1);
       mbar_init(&empty[i], 1);
@@ -192,249 +194,197 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // The three role warps run CONVERGED (all 32 lanes walk the program) and one elected lane issues each TMA / tcgen05
-  // instruction.  Those instructions take their operands from uniform registers; inside a single-lane branch the compiler
-  // cannot prove an operand warp-uniform and wraps every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop --
-  // measured ~85 ns per tcgen05.mma and ~190 ns per bulk copy from one lane (tools/bench_slab_phases.py, ablation 3 / 4),
-  // which capped a GEMM phase at ~13 MMAs per microsecond whatever the operand sizes.  Values read from the phase table are
-  // made provably uniform with a shuffle from lane 0.
   if (warp == 0) {
     // ===================== weight producer =====================
-    // Walks every GEMM phase of the program in order.  Weights never depend on activations, so this warp runs ahead of
-    // the rest of the CTA across phase boundaries: the ring (NS x 32 KB) is the run-ahead buffer.
-    int stage = 0, par = 0;
-    const unsigned int spin = hdr.spin_ns;
-    for (int p = 0; p < hdr.n_phases; ++p) {
-      const Phase& ph = hdr.phases[p];
-      const int type = uni(ph.type);
-      if (type == PH_GEMM2) {
-        const int passes = uni(ph.s_passes), kc = uni(ph.s_kc), nk = uni(ph.nk), nt = uni(ph.s_ntiles);
-        const uint32_t blk = (uint32_t)uni(ph.s_blk_bytes), blk_smem = (uint32_t)uni(ph.s_blk_smem);
-        const int e_per = uni(ph.s_eper), e_rem = uni(ph.s_erem);
-        const long unit_stride = (long)uni64((unsigned long long)ph.s_unit_stride);
-        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(uni64(reinterpret_cast<unsigned long long>(ph.Wt)));
-        const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
-        for (int ps = 0; ps < passes; ++ps) {
-          const int u = b * passes + ps;
-          if (e_per + (u < e_rem ? 1 : 0) == 0) continue;
-          const uint8_t* ubase = wbase + (long)u * unit_stride;
-          for (int s = 0; s < spp; ++s) {
-            const int j0 = slab_stage(s, rot, spp) * kc;          // (rotated k order, see slab_stage)
-            const uint32_t nblk = (uint32_t)(min(kc, nk - j0) * nt);
-            const uint8_t* src = ubase + (long)j0 * nt * blk;
-            if (lane == 0) mbar_wait_sleep(&empty[stage], par ^ 1, spin);
-            __syncwarp();
-            uint8_t* dst = smem + stage * STAGE_BYTES;
-            if (hdr.debug & 2) {
-              if (elect_one()) mbar_arrive(&full_w[stage]);
-            } else if (blk == blk_smem) {
-              if (elect_one()) {
-                mbar_expect_tx(&full_w[stage], nblk * blk);
-                bulk_load(dst, src, nblk * blk, &full_w[stage], HINT_EVICT_FIRST);     // the whole stage: one copy
+    // Walks every GEMM phase of the program in order.  Weights never depend on activations, so this thread runs ahead of
+    // the rest of the CTA across phase boundaries: the ring is the run-ahead buffer.
+    if (lane == 0) {
+      int stage = 0, par = 0;
+      for (int p = 0; p < hdr.n_phases; ++p) {
+        const Phase& ph = hdr.phases[p];
+        if (ph.type == PH_GEMM2) {
+          const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
+          const uint32_t blk = (uint32_t)ph.s_blk_bytes, blk_smem = (uint32_t)ph.s_blk_smem;
+          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(ph.Wt);
+          const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
+          for (int ps = 0; ps < passes; ++ps) {
+            const int u = b * passes + ps;
+            if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
+            const uint8_t* ubase = wbase + (long)u * ph.s_unit_stride;
+            for (int s = 0; s < spp; ++s) {
+              const int j0 = slab_stage(s, rot, spp) * kc;          // (rotated k order, see slab_stage)
+              const uint32_t nblk = (uint32_t)(min(kc, nk - j0) * nt);
+              const uint8_t* src = ubase + (long)j0 * nt * blk;
+              mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+              if (hdr.debug & 2) {
+                mbar_arrive(&full_w[stage]);
+                if (++stage == NS) { stage = 0; par ^= 1; }
+                continue;
               }
-            } else {
-              if (elect_one()) mbar_expect_tx(&full_w[stage], nblk * blk);
-              __syncwarp();
-              for (uint32_t i = 0; i < nblk; ++i)
-                if (elect_one()) bulk_load(dst + i * blk_smem, src + i * blk, blk, &full_w[stage], HINT_EVICT_FIRST);
+              mbar_expect_tx(&full_w[stage], nblk * blk);
+              uint8_t* dst = smem + stage * STAGE_BYTES;
+              if (blk == blk_smem) {
+                bulk_load(dst, src, nblk * blk, &full_w[stage], HINT_EVICT_FIRST);     // the whole stage: one copy
+              } else {
+                for (uint32_t i = 0; i < nblk; ++i)
+                  bulk_load(dst + i * blk_smem, src + i * blk, blk, &full_w[stage], HINT_EVICT_FIRST);
+              }
+              if (++stage == NS) { stage = 0; par ^= 1; }
             }
-            __syncwarp();
-            if (++stage == NS) { stage = 0; par ^= 1; }
           }
-        }
-      } else if (type == PH_GEMM) {
-        const int off = uni(ph.range_off);
-        const int2 r = *reinterpret_cast<const int2*>(hdr.tables + off + 2 * b);
-        const int lo = uni(r.x), hi = uni(r.y);
-        const int nk = uni(ph.nk);
-        const CUtensorMap* tm = hdr.maps + uni(ph.tmW);
-        const bf16* wt = reinterpret_cast<const bf16*>(uni64(reinterpret_cast<unsigned long long>(ph.Wt)));
-        int tile = lo / nk, kc = lo % nk;
-        for (int c = lo; c < hi; ++c) {
-          if (lane == 0) mbar_wait_sleep(&empty[stage], par ^ 1, spin);
-          __syncwarp();
-          if (elect_one()) {
+        } else if (ph.type == PH_GEMM) {
+          const int2 r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
+          const int nk = ph.nk;
+          const CUtensorMap* tm = hdr.maps + ph.tmW;
+          const bf16* wt = ph.Wt;                            // tiled layout: chunk c is the 16 KB block c of the matrix
+          int tile = r.x / nk, kc = r.x % nk;
+          for (int c = r.x; c < r.y; ++c) {
+            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
             mbar_expect_tx(&full_w[stage], W_STAGE);
             if (wt) bulk_load(smem + stage * STAGE_BYTES, wt + (long)c * (BM * BK), W_STAGE, &full_w[stage], HINT_EVICT_FIRST);
             else tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES, kc * BK, tile * BM, HINT_EVICT_FIRST);
+            if (++stage == NS) { stage = 0; par ^= 1; }
+            if (++kc == nk) { kc = 0; ++tile; }
           }
-          __syncwarp();
-          if (++stage == NS) { stage = 0; par ^= 1; }
-          if (++kc == nk) { kc = 0; ++tile; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int stage = 0, par = 0, acc = 0, acc_par = 0;
-    const unsigned int spin = hdr.spin_ns;
-    for (int p = 0; p < hdr.n_phases; ++p) {
-      const Phase& ph = hdr.phases[p];
-      const int type = uni(ph.type);
-      if (type == PH_GEMM2) {
-        const int passes = uni(ph.s_passes), kc = uni(ph.s_kc), nk = uni(ph.nk), nt = uni(ph.s_ntiles);
-        const uint32_t blk_smem = (uint32_t)uni(ph.s_blk_smem), x_off = (uint32_t)uni(ph.s_xoff);
-        const int e_per = uni(ph.s_eper), e_rem = uni(ph.s_erem);
-        const uint32_t idesc = uni(ph.s_m64) ? IDESC_M64 : IDESC;
-        const bool rel = uni(ph.s_packed) == 2;
-        const int spp = (nk + kc - 1) / kc;
-        for (int ps = 0; ps < passes; ++ps) {
-          const int u = b * passes + ps;
-          if (e_per + (u < e_rem ? 1 : 0) == 0) continue;
-          if (lane == 0) mbar_wait_sleep(&tempty[acc], acc_par ^ 1, spin);
-          __syncwarp();
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * 64;
-          for (int s = 0; s < spp; ++s) {
-            const int nj = min(kc, nk - slab_stage(s, slab_rotation(b, G, spp), spp) * kc);
-            if (lane == 0) {
-              mbar_wait_sleep(&full_w[stage], par, spin);
-              mbar_wait_sleep(&full_x[stage], par, spin);
-            }
-            __syncwarp();
+    if (lane == 0) {
+      int stage = 0, par = 0, acc = 0, acc_par = 0;
+      for (int p = 0; p < hdr.n_phases; ++p) {
+        const Phase& ph = hdr.phases[p];
+        if (ph.type == PH_GEMM2) {
+          const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
+          const uint32_t blk_smem = (uint32_t)ph.s_blk_smem, x_off = (uint32_t)ph.s_xoff;
+          const uint32_t idesc = ph.s_m64 ? IDESC_M64 : IDESC;
+          const bool rel = ph.s_packed == 2;
+          const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
+          for (int ps = 0; ps < passes; ++ps) {
+            const int u = b * passes + ps;
+            if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
+            mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
             tc_fence_after();
-            const uint32_t base = smem_u32(smem) + stage * STAGE_BYTES;
-            if (!(hdr.debug & 4)) {
+            const uint32_t d_tmem = tmem_base + acc * 64;
+            for (int s = 0; s < spp; ++s) {
+              const int j0 = slab_stage(s, rot, spp) * kc;
+              const int nj = min(kc, nk - j0);
+              mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
+              mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
+              tc_fence_after();
+              const uint8_t* base = smem + stage * STAGE_BYTES;
               for (int jj = 0; jj < nj; ++jj) {
-                const uint64_t db = make_desc_u32(base + x_off + jj * X_STAGE);
+                const uint64_t db = make_desc(base + x_off + jj * X_STAGE);
                 for (int t = 0; t < nt; ++t) {
-                  const uint32_t blk = base + (uint32_t)(jj * nt + t) * blk_smem;
-                  const uint64_t da = rel ? make_desc_rel_u32(blk) : make_desc_u32(blk);
-                  if (elect_one()) {
+                  const uint8_t* blk = base + (uint32_t)(jj * nt + t) * blk_smem;
+                  const uint64_t da = rel ? make_desc_rel(blk) : make_desc(blk);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                      tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
-                  }
+                  for (int k = 0; k < BK / 16; ++k)
+                    if (!(hdr.debug & 4)) tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
                 }
               }
+              tc_commit(&empty[stage]);
+              if (++stage == NS) { stage = 0; par ^= 1; }
             }
-            if (elect_one()) tc_commit(&empty[stage]);
-            __syncwarp();
-            if (++stage == NS) { stage = 0; par ^= 1; }
+            tc_commit(&tfull[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_par ^= 1;
           }
-          if (elect_one()) tc_commit(&tfull[acc]);
-          __syncwarp();
-          acc ^= 1;
-          if (acc == 0) acc_par ^= 1;
-        }
-      } else if (type == PH_GEMM) {
-        const int off = uni(ph.range_off);
-        const int2 r = *reinterpret_cast<const int2*>(hdr.tables + off + 2 * b);
-        const int lo = uni(r.x), hi = uni(r.y);
-        const int nk = uni(ph.nk);
-        int c = lo;
-        int tile = c / nk;
-        while (c < hi) {
-          const int seg_end = min(hi, (tile + 1) * nk);
-          if (lane == 0) mbar_wait_sleep(&tempty[acc], acc_par ^ 1, spin);
-          __syncwarp();
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * 64;
-          bool first = true;
-          for (; c < seg_end; ++c) {
-            if (lane == 0) {
-              mbar_wait_sleep(&full_w[stage], par, spin);
-              mbar_wait_sleep(&full_x[stage], par, spin);
-            }
-            __syncwarp();
+        } else if (ph.type == PH_GEMM) {
+          const int2 r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
+          const int nk = ph.nk;
+          int c = r.x;
+          int tile = c / nk;
+          while (c < r.y) {
+            const int seg_end = min(r.y, (tile + 1) * nk);
+            mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
             tc_fence_after();
-            const uint32_t base = smem_u32(smem) + stage * STAGE_BYTES;
-            const uint64_t da = make_desc_u32(base);
-            const uint64_t db = make_desc_u32(base + W_STAGE);
-            if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + acc * 64;
+            bool first = true;
+            for (; c < seg_end; ++c) {
+              mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
+              mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
+              tc_fence_after();
+              const uint64_t da = make_desc(smem + stage * STAGE_BYTES);
+              const uint64_t db = make_desc(smem + stage * STAGE_BYTES + W_STAGE);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) tc_mma(d_tmem, da + 2 * k, db + 2 * k, (!first || k > 0) ? 1u : 0u);
               tc_commit(&empty[stage]);
+              first = false;
+              if (++stage == NS) { stage = 0; par ^= 1; }
             }
-            __syncwarp();
-            first = false;
-            if (++stage == NS) { stage = 0; par ^= 1; }
+            tc_commit(&tfull[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_par ^= 1;
+            ++tile;
           }
-          if (elect_one()) tc_commit(&tfull[acc]);
-          __syncwarp();
-          acc ^= 1;
-          if (acc == 0) acc_par ^= 1;
-          ++tile;
         }
       }
     }
   } else if (warp == 2) {
     // ===================== activation producer =====================
-    int stage = 0, par = 0;
-    const unsigned int spin = hdr.spin_ns;
-    for (int p = 0; p < hdr.n_phases; ++p) {
-      const Phase& ph = hdr.phases[p];
-      const int type = uni(ph.type);
-      if (type != PH_GEMM2 && type != PH_GEMM) continue;
-      int n_stages;                                        // stages of this CTA in the phase
-      int lo = 0, hi = 0;
-      const int nk = uni(ph.nk);
-      int kc = 1, e_per = 0, e_rem = 0, passes = 1;
-      if (type == PH_GEMM2) {
-        kc = uni(ph.s_kc); e_per = uni(ph.s_eper); e_rem = uni(ph.s_erem); passes = uni(ph.s_passes);
-        int units = 0;
-        for (int ps = 0; ps < passes; ++ps) {
-          const int u = b * passes + ps;
-          units += e_per + (u < e_rem ? 1 : 0) > 0 ? 1 : 0;
+    if (lane == 0) {
+      int stage = 0, par = 0;
+      for (int p = 0; p < hdr.n_phases; ++p) {
+        const Phase& ph = hdr.phases[p];
+        if (ph.type != PH_GEMM2 && ph.type != PH_GEMM) continue;
+        int n_stages;                                        // stages of this CTA in the phase
+        int2 r = make_int2(0, 0);
+        if (ph.type == PH_GEMM2) {
+          int units = 0;
+          for (int ps = 0; ps < ph.s_passes; ++ps) {
+            const int u = b * ph.s_passes + ps;
+            units += ph.s_eper + (u < ph.s_erem ? 1 : 0) > 0 ? 1 : 0;
+          }
+          n_stages = units * ((ph.nk + ph.s_kc - 1) / ph.s_kc);
+        } else {
+          r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
+          n_stages = r.y - r.x;
         }
-        n_stages = units * ((nk + kc - 1) / kc);
-      } else {
-        const int off = uni(ph.range_off);
-        const int2 r = *reinterpret_cast<const int2*>(hdr.tables + off + 2 * b);
-        lo = uni(r.x); hi = uni(r.y);
-        n_stages = hi - lo;
-      }
-      if (n_stages <= 0) continue;
-      // the token tile is produced by earlier phases of this launch: wait until all of them completed everywhere
-      // (relaxed polling, no L1 invalidation storm; the tile itself is read by the TMA unit from L2, ordered behind the
-      // observed counter value by the proxy fence)
-      const unsigned int need = (unsigned int)uni(ph.bars_before) * (unsigned int)G;
-      if (lane == 0) {
+        if (n_stages <= 0) continue;
+        // the token tile is produced by earlier phases of this launch: wait until all of them completed everywhere
+        // (relaxed polling, no L1 invalidation storm; the tile itself is read by the TMA unit from L2, ordered behind the
+        // observed counter value by the proxy fence)
+        const unsigned int need = (unsigned int)ph.bars_before * (unsigned int)G;
         while (ld_relaxed_u32(hdr.counters) < need) __nanosleep(64);
-      }
-      __syncwarp();
-      fence_proxy_async();
-      const CUtensorMap* tm = hdr.maps + uni(ph.tmX);
-      if (type == PH_GEMM2) {
-        const uint32_t x_off = (uint32_t)uni(ph.s_xoff);
-        const int t3 = uni(ph.tmX3);
-        const CUtensorMap* tm3 = t3 >= 0 ? hdr.maps + t3 : nullptr;
-        const int spp = (nk + kc - 1) / kc;                // stages per pass: every pass walks the same k-chunks
-        const int rot = slab_rotation(b, G, spp);
-        for (int s = 0; s < n_stages; ++s) {
-          const int j0 = slab_stage(s % spp, rot, spp) * kc;
-          const int nj = min(kc, nk - j0);
-          if (lane == 0) mbar_wait_sleep(&empty[stage], par ^ 1, spin);
-          __syncwarp();
-          uint8_t* dst = smem + stage * STAGE_BYTES + x_off;
-          if (hdr.debug & 1) {
-            if (elect_one()) mbar_arrive(&full_x[stage]);
-          } else if (tm3 && nj == kc) {
-            if (elect_one()) {
-              mbar_expect_tx(&full_x[stage], nj * X_STAGE);
-              tma_load_3d(tm3, &full_x[stage], dst, 0, 0, j0, HINT_EVICT_LAST);      // {64, 32, kc} box: kc blocks at once
+        fence_proxy_async();
+        if (ph.type == PH_GEMM2) {
+          const int kc = ph.s_kc, nk = ph.nk;
+          const uint32_t x_off = (uint32_t)ph.s_xoff;
+          const CUtensorMap* tm3 = ph.tmX3 >= 0 ? hdr.maps + ph.tmX3 : nullptr;
+          const CUtensorMap* tm = hdr.maps + ph.tmX;
+          const int spp = (nk + kc - 1) / kc;                // stages per pass: every pass walks the same k-chunks
+          const int rot = slab_rotation(b, G, spp);
+          for (int s = 0; s < n_stages; ++s) {
+            const int j0 = slab_stage(s % spp, rot, spp) * kc;
+            const int nj = min(kc, nk - j0);
+            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
+            if (hdr.debug & 1) {
+              mbar_arrive(&full_x[stage]);
+              if (++stage == NS) { stage = 0; par ^= 1; }
+              continue;
             }
-          } else {
-            if (elect_one()) mbar_expect_tx(&full_x[stage], nj * X_STAGE);
-            __syncwarp();
-            for (int jj = 0; jj < nj; ++jj)
-              if (elect_one()) tma_load_2d(tm, &full_x[stage], dst + jj * X_STAGE, (j0 + jj) * BK, 0, HINT_EVICT_LAST);
+            mbar_expect_tx(&full_x[stage], nj * X_STAGE);
+            uint8_t* dst = smem + stage * STAGE_BYTES + x_off;
+            if (tm3 && nj == kc) {
+              tma_load_3d(tm3, &full_x[stage], dst, 0, 0, j0, HINT_EVICT_LAST);      // {64, 32, kc} box: kc blocks at once
+            } else {
+              for (int jj = 0; jj < nj; ++jj)
+                tma_load_2d(tm, &full_x[stage], dst + jj * X_STAGE, (j0 + jj) * BK, 0, HINT_EVICT_LAST);
+            }
+            if (++stage == NS) { stage = 0; par ^= 1; }
           }
-          __syncwarp();
-          if (++stage == NS) { stage = 0; par ^= 1; }
-        }
-      } else {
-        int kcc = lo % nk;
-        for (int c = lo; c < hi; ++c) {
-          if (lane == 0) mbar_wait_sleep(&empty[stage], par ^ 1, spin);
-          __syncwarp();
-          if (elect_one()) {
+        } else {
+          const CUtensorMap* tm = hdr.maps + ph.tmX;
+          int kc = r.x % ph.nk;
+          for (int c = r.x; c < r.y; ++c) {
+            mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
             mbar_expect_tx(&full_x[stage], X_STAGE);
-            tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kcc * BK, 0, HINT_EVICT_LAST);
+            tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kc * BK, 0, HINT_EVICT_LAST);
+            if (++stage == NS) { stage = 0; par ^= 1; }
+            if (++kc == ph.nk) kc = 0;
           }
-          __syncwarp();
-          if (++stage == NS) { stage = 0; par ^= 1; }
-          if (++kcc == nk) kcc = 0;
         }
       }
     }
@@ -1166,6 +1116,10 @@ int vs_program_run(const vs_program* pg, void* stream) {
   h.inflight = pg->inflight;
   h.spin_ns = pg->spin_ns;
   h.debug = pg->debug;
+  bool has_slab = false;
+  for (const auto& ph : pg->phases) has_slab = has_slab || ph.type == PH_GEMM2;
+  h.ns = has_slab ? RING_BYTES / SLAB_SLOT_BYTES : NS_MAX;
+  h.stage_bytes = has_slab ? SLAB_SLOT_BYTES : W_STAGE + X_STAGE;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pg->grid);
   cfg.blockDim = dim3(PG_THREADS);

@@ -30,12 +30,14 @@ def use_tiled() -> bool:
 
 
 def weight_layout() -> str:
-    """HBM layout of the decode weights streamed by the program kernel: "slab" (default, round 2: whole output rows per
-    CTA, epilogue from TMEM -- csrc/slab.h), "tiled" (round 1: 16 KB tiles, stream-K + partial-tile epilogues) or
-    "rowmajor" (tensor maps over the row-major copy).  VS_LAYOUT / VS_TILED=0 select the older ones for A/B runs."""
+    """HBM layout of the decode weights streamed by the program kernel: "tiled" (default: 16 KB tiles, stream-K over
+    (tile, k-chunk) ranges + partial-tile epilogues), "slab" (round-2 experiment, csrc/slab.h: whole output rows per CTA,
+    epilogue from TMEM, no cross-CTA reduction -- correct, but every CTA then walks the full K range and the path is bound
+    by tcgen05.mma issue (K/16 instructions per CTA and GEMM): measured 130 vs 196 tokens/s) or
+    "rowmajor" (tensor maps over the row-major copy).  VS_LAYOUT / VS_TILED=0 select the alternatives for A/B runs."""
     if not use_tiled():
         return "rowmajor"
-    v = os.environ.get("VS_LAYOUT", "slab")
+    v = os.environ.get("VS_LAYOUT", "tiled")
     if v not in ("slab", "tiled", "rowmajor"):
         raise ValueError(f"VS_LAYOUT={v!r}: expected slab, tiled or rowmajor")
     return v
