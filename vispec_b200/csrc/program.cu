@@ -39,6 +39,10 @@
 #include "slab.h"
 #include "sm100.cuh"
 
+#ifndef VS_MMA_CONVERGED
+#define VS_MMA_CONVERGED 0
+#endif
+
 namespace vs {
 
 namespace {
@@ -251,70 +255,100 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // VS_MMA_CONVERGED=1 (build macro, A/B): the whole warp walks the program and one ELECTED lane issues the MMAs of a
+    // stage back to back.  tcgen05.mma takes its operands from uniform registers; inside a single-lane branch the
+    // compiler cannot prove them warp-uniform and wraps every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+    // (~85 ns per MMA measured, tools/bench_slab_phases.py), which caps the stream at 16 KB per 4 x 85 ns = 7.1 TB/s.
+#if VS_MMA_CONVERGED
+#define MMA_ENTER if (true)
+#define MMA_WAIT(call) do { if (lane == 0) { call; } __syncwarp(); } while (0)
+#define MMA_ISSUE if (elect_one())
+#define MMA_SYNC() __syncwarp()
+#define MMA_UNI(v) uni(v)
+#else
+#define MMA_ENTER if (lane == 0)
+#define MMA_WAIT(call) do { call; } while (0)
+#define MMA_ISSUE
+#define MMA_SYNC() do { } while (0)
+#define MMA_UNI(v) (v)
+#endif
+    MMA_ENTER {
       int stage = 0, par = 0, acc = 0, acc_par = 0;
+      const unsigned int spin = hdr.spin_ns;
       for (int p = 0; p < hdr.n_phases; ++p) {
         const Phase& ph = hdr.phases[p];
-        if (ph.type == PH_GEMM2) {
-          const int passes = ph.s_passes, kc = ph.s_kc, nk = ph.nk, nt = ph.s_ntiles;
-          const uint32_t blk_smem = (uint32_t)ph.s_blk_smem, x_off = (uint32_t)ph.s_xoff;
-          const uint32_t idesc = ph.s_m64 ? IDESC_M64 : IDESC;
-          const bool rel = ph.s_packed == 2;
+        const int type = MMA_UNI(ph.type);
+        if (type == PH_GEMM2) {
+          const int passes = MMA_UNI(ph.s_passes), kc = MMA_UNI(ph.s_kc), nk = MMA_UNI(ph.nk), nt = MMA_UNI(ph.s_ntiles);
+          const uint32_t blk_smem = (uint32_t)MMA_UNI(ph.s_blk_smem), x_off = (uint32_t)MMA_UNI(ph.s_xoff);
+          const int e_per = MMA_UNI(ph.s_eper), e_rem = MMA_UNI(ph.s_erem);
+          const uint32_t idesc = MMA_UNI(ph.s_m64) ? IDESC_M64 : IDESC;
+          const bool rel = MMA_UNI(ph.s_packed) == 2;
           const int spp = (nk + kc - 1) / kc, rot = slab_rotation(b, G, spp);
           for (int ps = 0; ps < passes; ++ps) {
             const int u = b * passes + ps;
-            if (ph.s_eper + (u < ph.s_erem ? 1 : 0) == 0) continue;
-            mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
+            if (e_per + (u < e_rem ? 1 : 0) == 0) continue;
+            MMA_WAIT(mbar_wait_sleep(&tempty[acc], acc_par ^ 1, spin));
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 64;
             for (int s = 0; s < spp; ++s) {
               const int j0 = slab_stage(s, rot, spp) * kc;
               const int nj = min(kc, nk - j0);
-              mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
-              mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
+              MMA_WAIT(mbar_wait_sleep(&full_w[stage], par, spin); mbar_wait_sleep(&full_x[stage], par, spin));
               tc_fence_after();
-              const uint8_t* base = smem + stage * STAGE_BYTES;
-              for (int jj = 0; jj < nj; ++jj) {
-                const uint64_t db = make_desc(base + x_off + jj * X_STAGE);
-                for (int t = 0; t < nt; ++t) {
-                  const uint8_t* blk = base + (uint32_t)(jj * nt + t) * blk_smem;
-                  const uint64_t da = rel ? make_desc_rel(blk) : make_desc(blk);
+              const uint32_t base = smem_u32(smem) + stage * STAGE_BYTES;
+              MMA_ISSUE {
+                if (!(hdr.debug & 4)) {
+                  for (int jj = 0; jj < nj; ++jj) {
+                    const uint64_t db = make_desc_u32(base + x_off + jj * X_STAGE);
+                    for (int t = 0; t < nt; ++t) {
+                      const uint32_t blk = base + (uint32_t)(jj * nt + t) * blk_smem;
+                      const uint64_t da = rel ? make_desc_rel_u32(blk) : make_desc_u32(blk);
 #pragma unroll
-                  for (int k = 0; k < BK / 16; ++k)
-                    if (!(hdr.debug & 4)) tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
+                      for (int k = 0; k < BK / 16; ++k)
+                        tc_mma(d_tmem + t * 32, da + 2 * k, db + 2 * k, (s | jj | k) ? 1u : 0u, idesc);
+                    }
+                  }
                 }
+                tc_commit(&empty[stage]);
               }
-              tc_commit(&empty[stage]);
+              MMA_SYNC();
               if (++stage == NS) { stage = 0; par ^= 1; }
             }
-            tc_commit(&tfull[acc]);
+            MMA_ISSUE tc_commit(&tfull[acc]);
+            MMA_SYNC();
             acc ^= 1;
             if (acc == 0) acc_par ^= 1;
           }
-        } else if (ph.type == PH_GEMM) {
-          const int2 r = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
-          const int nk = ph.nk;
-          int c = r.x;
+        } else if (type == PH_GEMM) {
+          const int2 r = *reinterpret_cast<const int2*>(hdr.tables + MMA_UNI(ph.range_off) + 2 * b);
+          const int lo = MMA_UNI(r.x), hi = MMA_UNI(r.y);
+          const int nk = MMA_UNI(ph.nk);
+          int c = lo;
           int tile = c / nk;
-          while (c < r.y) {
-            const int seg_end = min(r.y, (tile + 1) * nk);
-            mbar_wait_sleep(&tempty[acc], acc_par ^ 1, hdr.spin_ns);
+          while (c < hi) {
+            const int seg_end = min(hi, (tile + 1) * nk);
+            MMA_WAIT(mbar_wait_sleep(&tempty[acc], acc_par ^ 1, spin));
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 64;
             bool first = true;
             for (; c < seg_end; ++c) {
-              mbar_wait_sleep(&full_w[stage], par, hdr.spin_ns);
-              mbar_wait_sleep(&full_x[stage], par, hdr.spin_ns);
+              MMA_WAIT(mbar_wait_sleep(&full_w[stage], par, spin); mbar_wait_sleep(&full_x[stage], par, spin));
               tc_fence_after();
-              const uint64_t da = make_desc(smem + stage * STAGE_BYTES);
-              const uint64_t db = make_desc(smem + stage * STAGE_BYTES + W_STAGE);
+              const uint32_t base = smem_u32(smem) + stage * STAGE_BYTES;
+              const uint64_t da = make_desc_u32(base);
+              const uint64_t db = make_desc_u32(base + W_STAGE);
+              MMA_ISSUE {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) tc_mma(d_tmem, da + 2 * k, db + 2 * k, (!first || k > 0) ? 1u : 0u);
-              tc_commit(&empty[stage]);
+                for (int k = 0; k < BK / 16; ++k) tc_mma(d_tmem, da + 2 * k, db + 2 * k, (!first || k > 0) ? 1u : 0u);
+                tc_commit(&empty[stage]);
+              }
+              MMA_SYNC();
               first = false;
               if (++stage == NS) { stage = 0; par ^= 1; }
             }
-            tc_commit(&tfull[acc]);
+            MMA_ISSUE tc_commit(&tfull[acc]);
+            MMA_SYNC();
             acc ^= 1;
             if (acc == 0) acc_par ^= 1;
             ++tile;
