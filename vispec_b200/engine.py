@@ -328,6 +328,11 @@ class TargetEngine:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         tp_prefill.check_shardable(self.cfg.heads, self.cfg.kv_heads, self.cfg.inter, world)
         self._tp = (group, rank, world)
+        # per-rank weight slices for the pass on the library's own kernels (VS_TP_PREFILL=library keeps the torch pass)
+        self._tp_local = None
+        if world > 1 and os.environ.get("VS_TP_PREFILL", "native") != "library":
+            self._tp_local = tp_prefill.shard_layer_weights(self.layers_t, heads=self.cfg.heads, kv_heads=self.cfg.kv_heads,
+                                                            inter=self.cfg.inter, rank=rank, world=world)
         return self
 
     def _verify_program(self, T: int, has_bits: bool, fused: bool) -> Program:
@@ -362,7 +367,8 @@ class TargetEngine:
         """LlamaModel.forward over the prompt (modeling_llama_kv.py:927-1080): writes K/V rows [past, past+L) of the slab,
         returns (last-row logits fp32 [V], hidden [1,L,H] post-norm).  Runs on the library's own kernels
         (`prefill_native`) unless the tensor-parallel prompt pass is enabled or VS_PREFILL=library."""
-        if self._tp is None and os.environ.get("VS_PREFILL", "native") != "library":
+        tp_native = self._tp is not None and getattr(self, "_tp_local", None) is not None
+        if (self._tp is None or tp_native) and os.environ.get("VS_PREFILL", "native") != "library":
             return self.prefill_native(inputs_embeds, past, position_ids)
         return self.prefill_library(inputs_embeds, past, position_ids)
 
@@ -494,10 +500,17 @@ class TargetEngine:
             rope = L.Rope(L.ptr(self.cos), L.ptr(self.sin))
         st = _stream()
         eager = 0 if cfg.attn_impl == "sdpa" else 1
-        for li in range(cfg.layers):
-            L.check(self.lib.vs_decoder_layer(C.byref(self.dims), C.byref(self._layer_arr[li]), C.byref(big.c), C.byref(rope),
-                                              Lq, L.ptr(pos), None, past, None, past, Lq, 1, None, eager, st),
-                    "prefill layer")
+        if self._tp is not None and getattr(self, "_tp_local", None) is not None:
+            # tensor-parallel prompt pass on the same kernels: local heads / gate|up groups, bf16 all-reduce on the two
+            # row-parallel boundaries, KV all-gather (vispec_b200/tp_prefill.py)
+            from . import tp_prefill
+            group, rank, world = self._tp
+            tp_prefill.prefill_layers_native(self, x, self._tp_local, big, pos, rope, past, rank, world, group)
+        else:
+            for li in range(cfg.layers):
+                L.check(self.lib.vs_decoder_layer(C.byref(self.dims), C.byref(self._layer_arr[li]), C.byref(big.c),
+                                                  C.byref(rope), Lq, L.ptr(pos), None, past, None, past, Lq, 1, None, eager,
+                                                  st), "prefill layer")
         hidden = torch.empty(Lq, cfg.hidden, dtype=self.dtype, device=self.device)
         L.check(self.lib.vs_rmsnorm(L.ptr(big.h), cfg.hidden, L.ptr(self.norm), L.ptr(hidden), cfg.hidden, Lq, cfg.hidden,
                                     cfg.eps, st), "vs_rmsnorm")

@@ -137,6 +137,110 @@ def prefill_layers(x: torch.Tensor, layers: Sequence[Dict[str, torch.Tensor]], k
     return h
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the same pass on the library's own kernels (CUDA): sharded weights through the C ABI, bf16 all-reduce
+# ---------------------------------------------------------------------------------------------------------------------
+def shard_layer_weights(layers: Sequence[Dict[str, torch.Tensor]], *, heads: int, kv_heads: int, inter: int, rank: int,
+                        world: int) -> List[Dict[str, torch.Tensor]]:
+    """Per-rank contiguous copies of the weight slices (1 / world of the model): q|k|v rows of the local heads packed as
+    [q_local | k_local | v_local] (so that the fused RoPE + KV-append epilogue sees whole heads), the o_proj / down_proj
+    COLUMN slices made contiguous, the gate|up rows of the local 64-wide groups (already contiguous)."""
+    check_shardable(heads, kv_heads, inter, world)
+    D = 128
+    h0, h1 = shard_bounds(heads, rank, world)
+    k0, k1 = shard_bounds(kv_heads, rank, world)
+    g0, g1 = shard_bounds(inter // 64, rank, world)
+    out = []
+    for t in layers:
+        rows = [(h0 * D, h1 * D), (heads * D + k0 * D, heads * D + k1 * D),
+                ((heads + kv_heads) * D + k0 * D, (heads + kv_heads) * D + k1 * D)]
+        w_qkv = torch.cat([t["w_qkv"][a:b] for a, b in rows], dim=0).contiguous()
+        b_qkv = None if t.get("b_qkv") is None else torch.cat([t["b_qkv"][a:b] for a, b in rows], dim=0).contiguous()
+        out.append(dict(ln_in=t["ln_in"], ln_post=t["ln_post"], w_qkv=w_qkv, b_qkv=b_qkv,
+                        w_o=t["w_o"][:, h0 * D:h1 * D].contiguous(), w_gateup=t["w_gateup"][g0 * 128:g1 * 128],
+                        w_down=t["w_down"][:, g0 * 64:g1 * 64].contiguous()))
+    return out
+
+
+@torch.no_grad()
+def prefill_layers_native(engine, x: torch.Tensor, local: Sequence[Dict[str, torch.Tensor]], scratch, pos: torch.Tensor,
+                          rope, past: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """The sharded prompt pass on the engine's own kernels (C ABI): per layer
+      RMSNorm (vs_rmsnorm, replicated) -> local q|k|v GEMM with RoPE + in-place KV append of the LOCAL kv heads
+      (vs_linear, VS_EPI_HEADS) -> causal attention over the local heads (vs_attention) -> row-parallel o_proj partial
+      product (vs_linear) -> bf16 all-reduce (NCCL over NVLink / NVSwitch) -> residual add -> RMSNorm -> local gate|up with
+      SiLU*up (VS_EPI_SWIGLU) -> row-parallel down_proj partial product -> bf16 all-reduce -> residual add,
+    then one all-gather of the local kv-head rows so that every rank leaves with the complete KV slab.
+    The partial products round to bf16 before the sum (half the all-reduce bytes of the fp32 variant; the single-device
+    pass rounds the complete sum once), so the result differs from it by a few bf16 ulps -- the decode that follows is
+    checked to produce the same tokens (tests/tp_prefill_gpu_check.py).
+    `scratch`: engine ScratchBuffers for >= L rows; `pos` int32 [L]; `rope` L.Rope.  Returns the residual stream [L, H]."""
+    import ctypes as C
+
+    from . import _lib as L
+    from .engine import _stream, run_linear
+    cfg, lib = engine.cfg, engine.lib
+    heads, kv_heads, inter, H, D = cfg.heads, cfg.kv_heads, cfg.inter, cfg.hidden, 128
+    Lq = x.shape[0]
+    S = past + Lq
+    h0, h1 = shard_bounds(heads, rank, world)
+    k0, k1 = shard_bounds(kv_heads, rank, world)
+    g0, g1 = shard_bounds(inter // 64, rank, world)
+    nh_l, nkv_l, I_l = h1 - h0, k1 - k0, (g1 - g0) * 64
+    st = _stream()
+    sc = scratch
+    h = sc.h
+    h[:Lq] = x
+    part = torch.empty(Lq, H, dtype=x.dtype, device=x.device)
+    eager = 0 if cfg.attn_impl == "sdpa" else 1
+    kvs = engine.kv_max * 128
+    for li, t in enumerate(local):
+        k_rows, v_rows = engine.kv[2 * li, 0, k0:k1], engine.kv[2 * li + 1, 0, k0:k1]      # local kv heads of the slab
+        L.check(lib.vs_rmsnorm(L.ptr(h), H, L.ptr(t["ln_in"]), L.ptr(sc.x), H, Lq, H, cfg.eps, st), "vs_rmsnorm")
+        a = L.LinearArgs()
+        a.X, a.ldx, a.W, a.ldw, a.bias = L.ptr(sc.x), H, L.ptr(t["w_qkv"]), H, L.ptr(t["b_qkv"])
+        a.T, a.N, a.K = Lq, (nh_l + 2 * nkv_l) * D, H
+        a.splits = lib.vs_linear_splits(a.N, a.K, Lq)
+        while a.splits > 1 and lib.vs_linear_partials_floats(a.N, Lq, a.splits) > sc.partials.numel():
+            a.splits -= 1
+        a.partials, a.counters, a.epi = L.ptr(sc.partials), L.ptr(sc.counters), L.EPI_HEADS
+        a.n_q_tiles, a.n_k_tiles, a.rope = nh_l, nkv_l, 1
+        a.cos, a.sin, a.pos_ids = rope.cos, rope.sin, L.ptr(pos)
+        a.Qout, a.q_head_stride = L.ptr(sc.q), sc.max_rows * D
+        a.Kout, a.Vout, a.kv_head_stride = L.ptr(k_rows), L.ptr(v_rows), kvs
+        a.kv_row_base, a.kv_row_off = None, past
+        L.check(lib.vs_linear(C.byref(a), st), "tp q|k|v")
+        at = L.AttnArgs()
+        at.Q, at.q_head_stride, at.K, at.V, at.kv_head_stride = L.ptr(sc.q), sc.max_rows * D, L.ptr(k_rows), L.ptr(v_rows), kvs
+        at.n_heads, at.n_kv_heads, at.Tq = nh_l, nkv_l, Lq
+        at.n_ctx, at.n_ctx_host, at.n_new, at.causal, at.bits, at.eager = None, past, Lq, 1, None, eager
+        at.scale = 1.0 / math.sqrt(D)
+        at.scores, at.score_ld, at.stats, at.max_chunks = L.ptr(sc.scores), sc.score_ld, L.ptr(sc.stats), sc.max_chunks
+        at.opart, at.pv_splits, at.counters = L.ptr(sc.opart), sc.pv_splits, L.ptr(sc.attn_counters)
+        at.O, at.ldo = L.ptr(sc.attn), nh_l * D
+        L.check(lib.vs_attention(C.byref(at), st), "tp attention")
+        run_linear(lib, sc, sc.attn, nh_l * D, t["w_o"], None, Lq, H, nh_l * D, part, H)
+        if world > 1:
+            dist.all_reduce(part, group=group)
+        h[:Lq] += part
+        L.check(lib.vs_rmsnorm(L.ptr(h), H, L.ptr(t["ln_post"]), L.ptr(sc.x), H, Lq, H, cfg.eps, st), "vs_rmsnorm")
+        run_linear(lib, sc, sc.x, H, t["w_gateup"], None, Lq, 2 * I_l, H, sc.act, I_l, epi=L.EPI_SWIGLU)
+        run_linear(lib, sc, sc.act, I_l, t["w_down"], None, Lq, H, I_l, part, H)
+        if world > 1:
+            dist.all_reduce(part, group=group)
+        h[:Lq] += part
+    if world > 1:
+        n_layers = len(local)
+        mine = engine.kv[:2 * n_layers, 0, k0:k1, past:S].contiguous()
+        parts: List[torch.Tensor] = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        for r, p_ in enumerate(parts):
+            a0, b0 = shard_bounds(kv_heads, r, world)
+            if r != rank:
+                engine.kv[:2 * n_layers, 0, a0:b0, past:S] = p_
+    return h[:Lq]
+
+
 def collective_bytes_per_rank(n_layers: int, rows: int, hidden: int, kv_heads: int, world: int) -> Dict[str, int]:
     """Payload of the collectives of one TP prefill (for reports): 2 fp32 all-reduces per layer + the KV all-gather."""
     return {"all_reduce": 2 * n_layers * rows * hidden * 4,
