@@ -126,6 +126,9 @@ typedef struct vs_attn_args {
   float* opart; int32_t pv_splits;      /* [n_heads][ceil(Tq/32)][pv_splits][32][128] */
   int32_t* counters;                    /* [n_heads][ceil(Tq/32)] zero-initialised */
   void* O; int64_t ldo;
+  int32_t prefix_stable;                /* programs only: *n_ctx and the K/V rows [0, *n_ctx) are final when the launch starts
+                                           (nothing earlier in the program moves them): the kernel's KV producer may stage
+                                           those rows ahead of the phase.  0 = load everything inside the phase. */
 } vs_attn_args;
 int vs_attention(const vs_attn_args* a, void* stream);
 

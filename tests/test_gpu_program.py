@@ -199,7 +199,7 @@ def test_program_rows_argmax_topk():
     assert torch.equal(tv1, tv.view(8, k)[5]) and torch.equal(ti1, ti.view(8, k)[5])
 
 
-def program_attention(Q, K, V, nh, nkv, Tq, n_ctx, n_new, causal, bits, eager, n_ctx_dev=True, fused=False):
+def program_attention(Q, K, V, nh, nkv, Tq, n_ctx, n_new, causal, bits, eager, n_ctx_dev=True, fused=False, stable=0, **opts):
     sc = ScratchBuffers(nh * 128, 256, nh, 1000, 32, K.shape[1], DEV)
     O = torch.zeros(Tq, nh * 128, dtype=BF, device=DEV)
     a = L.AttnArgs()
@@ -210,9 +210,10 @@ def program_attention(Q, K, V, nh, nkv, Tq, n_ctx, n_new, causal, bits, eager, n
     a.n_new, a.causal, a.bits, a.eager, a.scale = n_new, int(causal), L.ptr(bits), int(eager), 1 / math.sqrt(128)
     a.scores, a.score_ld, a.stats, a.max_chunks = sc.scores.data_ptr(), sc.score_ld, sc.stats.data_ptr(), sc.max_chunks
     a.opart, a.pv_splits, a.counters, a.O, a.ldo = sc.opart.data_ptr(), sc.pv_splits, sc.attn_counters.data_ptr(), O.data_ptr(), nh * 128
+    a.prefix_stable = stable
     if fused:
         assert n_ctx + n_new <= sc.fused_kv_capacity
-    p = run_program(lambda p: p.add("attention", C.byref(a)), attn_fused=fused)
+    p = run_program(lambda p: p.add("attention", C.byref(a)), attn_fused=fused, **opts)
     assert p.phase_types() == ([L.PH_ATTN_FUSED] if fused else [L.PH_ATTN_S, L.PH_ATTN_PV])
     assert int(sc.attn_counters.abs().sum()) == 0
     if fused:                                 # relaunch: the per-head arrival counters are monotonic across launches
@@ -240,6 +241,64 @@ def test_program_attention_tree(eager, nh, nkv, n_ctx, fused):
     ref = tk.attention_ref(Q[:, :T], K, V, n_ctx, T, False, bits.tolist(), eager, nh, nkv)
     torch.testing.assert_close(O.float(), ref.float(), rtol=2 ** -6, atol=2e-2)
     assert (O.float() == ref.float()).float().mean() > 0.9
+
+
+@pytest.mark.parametrize("eager", [True, False])
+@pytest.mark.parametrize("opts", [dict(kv_two_loads=1), dict(attn_prefetch=0), dict()])
+@pytest.mark.parametrize("nh,nkv,n_ctx", [(32, 32, 734), (28, 4, 700), (4, 2, 61), (2, 2, 0), (32, 32, 2047), (8, 8, 5000), (4, 4, 31),
+                                          (4, 4, 32), (4, 4, 33), (32, 32, 1122)])
+def test_program_attention_tma_staged_variants(eager, opts, nh, nkv, n_ctx):
+    """The single-phase attention stages K/V through tensor-map TMA granules (attn_ring.cuh): the stable prefix staged ahead
+    of the phase (prefix_stable = 1), the same with the staging held back (attn_prefetch = 0) and the two-loads-per-granule
+    form of the tensor map must all give the result of the in-phase loads, bit for bit."""
+    T, rows = 30, max(4096, (n_ctx + 30 + 63) // 64 * 64)
+    Q = randn(nh, 32, 128, seed=30)
+    K, V = randn(nkv, rows, 128, seed=31), randn(nkv, rows, 128, seed=32)
+    K[:, n_ctx + T:] = float("nan")           # rows past the kv length may hold anything
+    V[:, n_ctx + T:] = float("nan")
+    bits = tk.tree_bits(T, 5)
+    base = program_attention(Q, K, V, nh, nkv, T, n_ctx, T, False, bits, eager, fused=True)
+    O = program_attention(Q, K, V, nh, nkv, T, n_ctx, T, False, bits, eager, fused=True, stable=1, **opts)
+    assert torch.equal(O, base)
+    ref = tk.attention_ref(Q[:, :T], K[:, :n_ctx + T], V[:, :n_ctx + T], n_ctx, T, False, bits.tolist(), eager, nh, nkv)
+    torch.testing.assert_close(O.float(), ref.float(), rtol=2 ** -6, atol=2e-2)
+    assert (O.float() == ref.float()).float().mean() > 0.9
+
+
+def test_program_attention_phases_back_to_back_with_staging():
+    """Several attention phases over different K/V slabs in one launch, all flagged prefix_stable: the KV producer runs
+    ahead of the workers across phase boundaries; every phase must give the result of a program of its own."""
+    nh = nkv = 32
+    T, n_ctx, rows, layers = 30, 900, 1024, 6
+    Q = randn(nh, 32, 128, seed=40)
+    Ks = [randn(nkv, rows, 128, seed=41 + i) for i in range(layers)]
+    Vs = [randn(nkv, rows, 128, seed=61 + i) for i in range(layers)]
+    bits = tk.tree_bits(T, 5)
+    single = [program_attention(Q, Ks[i], Vs[i], nh, nkv, T, n_ctx, T, False, bits, True, fused=True) for i in range(layers)]
+    sc = ScratchBuffers(nh * 128, 256, nh, 1000, 32, rows, DEV)
+    Os = [torch.zeros(T, nh * 128, dtype=BF, device=DEV) for _ in range(layers)]
+    nctx_t = torch.tensor([n_ctx], dtype=torch.int32, device=DEV)
+    args = []
+    for i in range(layers):
+        a = L.AttnArgs()
+        a.Q, a.q_head_stride, a.K, a.V, a.kv_head_stride = Q.data_ptr(), 32 * 128, Ks[i].data_ptr(), Vs[i].data_ptr(), rows * 128
+        a.n_heads, a.n_kv_heads, a.Tq = nh, nkv, T
+        a.n_ctx, a.n_ctx_host = nctx_t.data_ptr(), 0
+        a.n_new, a.causal, a.bits, a.eager, a.scale = T, 0, L.ptr(bits), 1, 1 / math.sqrt(128)
+        a.scores, a.score_ld, a.stats, a.max_chunks = sc.scores.data_ptr(), sc.score_ld, sc.stats.data_ptr(), sc.max_chunks
+        a.opart, a.pv_splits, a.counters, a.O, a.ldo = sc.opart.data_ptr(), sc.pv_splits, sc.attn_counters.data_ptr(), Os[i].data_ptr(), nh * 128
+        a.prefix_stable = 1
+        args.append(a)
+
+    def build(p):
+        for a in args:
+            p.add("attention", C.byref(a))
+    p = run_program(build, attn_fused=True)
+    for _ in range(3):
+        p.run()
+    torch.cuda.synchronize()
+    for i in range(layers):
+        assert torch.equal(Os[i], single[i]), f"phase {i}"
 
 
 @pytest.mark.parametrize("fused", [False, True])

@@ -33,7 +33,7 @@ def tree_bits(T, dev):
     return torch.tensor(bits, dtype=torch.int64, device=dev)
 
 
-def measure(kv_len, fused, layers=32, nh=32, nkv=32, T=30, reps=20, dev="cuda", eager=True, peak=None):
+def measure(kv_len, fused, layers=32, nh=32, nkv=32, T=30, reps=20, dev="cuda", eager=True, peak=None, **opts):
     rows = (kv_len + 63) // 64 * 64
     sc = ScratchBuffers(nh * 128, 256, nh, 1000, 32, rows, dev)
     g = torch.Generator(device=dev).manual_seed(1)
@@ -44,7 +44,7 @@ def measure(kv_len, fused, layers=32, nh=32, nkv=32, T=30, reps=20, dev="cuda", 
     bits = tree_bits(T, dev)
     nctx = torch.tensor([kv_len - T], dtype=torch.int32, device=dev)
     args = []
-    p = Program(dev, attn_fused=fused)
+    p = Program(dev, attn_fused=fused, **opts)
     for li in range(layers):
         a = L.AttnArgs()
         a.Q, a.q_head_stride, a.K, a.V, a.kv_head_stride = Q.data_ptr(), 32 * 128, K[li].data_ptr(), V[li].data_ptr(), rows * 128
@@ -53,6 +53,7 @@ def measure(kv_len, fused, layers=32, nh=32, nkv=32, T=30, reps=20, dev="cuda", 
         a.n_new, a.causal, a.bits, a.eager, a.scale = T, 0, bits.data_ptr(), int(eager), 1 / math.sqrt(128)
         a.scores, a.score_ld, a.stats, a.max_chunks = sc.scores.data_ptr(), sc.score_ld, sc.stats.data_ptr(), sc.max_chunks
         a.opart, a.pv_splits, a.counters, a.O, a.ldo = sc.opart.data_ptr(), sc.pv_splits, sc.attn_counters.data_ptr(), O.data_ptr(), nh * 128
+        a.prefix_stable = 1          # the verify step's case: kv length and prefix rows are final when the launch starts
         args.append(a)
         p.add("attention", C.byref(a))
     p.commit()
@@ -68,7 +69,8 @@ def measure(kv_len, fused, layers=32, nh=32, nkv=32, T=30, reps=20, dev="cuda", 
     us_layer = e0.elapsed_time(e1) * 1e3 / reps / layers
     kv_bytes = 2 * kv_len * nkv * 128 * 2
     gbs = kv_bytes / us_layer / 1e3
-    out = {"kv_len": kv_len, "path": "single-phase" if fused else "two-phase", "us_per_layer": round(us_layer, 2),
+    out = {"kv_len": kv_len, "path": ("single-phase (TMA-staged K/V)" if fused else "two-phase") + (" " + str(opts) if opts else ""),
+           "us_per_layer": round(us_layer, 2),
            "kv_bytes_per_layer": kv_bytes, "achieved_gbs": round(gbs, 1), "includes": "one grid barrier per phase"}
     if peak:
         out["frac_of_hbm_peak"] = round(gbs / peak, 4)
@@ -81,6 +83,9 @@ if __name__ == "__main__":
     ap.add_argument("--two-phase", action="store_true", help="also time the two-phase program")
     ap.add_argument("--heads", type=int, default=32)
     ap.add_argument("--kv-heads", type=int, default=32)
+    ap.add_argument("--no-stage", action="store_true", help="also time the program with the prefix staging held back")
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--reps", type=int, default=20)
     a = ap.parse_args()
     peak = None
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -88,4 +93,6 @@ if __name__ == "__main__":
         peak = json.load(open(pk)).get("hbm_gbs")
     for kv in a.kv:
         for fused in ([True, False] if a.two_phase else [True]):
-            print(json.dumps(measure(kv, fused, nh=a.heads, nkv=a.kv_heads, peak=peak)), flush=True)
+            print(json.dumps(measure(kv, fused, nh=a.heads, nkv=a.kv_heads, peak=peak, layers=a.layers, reps=a.reps)), flush=True)
+        if a.no_stage:
+            print(json.dumps(measure(kv, True, nh=a.heads, nkv=a.kv_heads, peak=peak, layers=a.layers, reps=a.reps, attn_prefetch=0)), flush=True)

@@ -42,7 +42,8 @@ class AttnArgs(C.Structure):
                 ("n_ctx", c_vp), ("n_ctx_host", c_i32), ("n_new", c_i32), ("causal", c_i32),
                 ("bits", c_vp), ("eager", c_i32), ("scale", c_f32),
                 ("scores", c_vp), ("score_ld", c_i64), ("stats", c_vp), ("max_chunks", c_i32),
-                ("opart", c_vp), ("pv_splits", c_i32), ("counters", c_vp), ("O", c_vp), ("ldo", c_i64)]
+                ("opart", c_vp), ("pv_splits", c_i32), ("counters", c_vp), ("O", c_vp), ("ldo", c_i64),
+                ("prefix_stable", c_i32)]
 
 
 class TreeBufs(C.Structure):

@@ -62,10 +62,10 @@ __device__ __forceinline__ unsigned long long att_low_mask(int n) {   // n lowes
 }
 // bit j = key (key0 + j) is visible to query row q_abs: inside the kv length, and either in the fully visible prefix,
 // or causal (key < n_ctx + q_abs + 1), or allowed by the query's tree word (bit i = key n_ctx + i)
-__device__ __forceinline__ unsigned long long att_visible_mask(const AttnArgs& p, int n_ctx, int kv_len, int q_abs,
+__device__ __forceinline__ unsigned long long att_visible_mask(bool causal, int n_ctx, int kv_len, int q_abs,
                                                                unsigned long long qbits, int key0) {
   unsigned long long m;
-  if (p.causal) {
+  if (causal) {
     m = att_low_mask(n_ctx + q_abs + 1 - key0);
   } else {
     m = att_low_mask(n_ctx - key0);
@@ -74,6 +74,10 @@ __device__ __forceinline__ unsigned long long att_visible_mask(const AttnArgs& p
     else m |= -sh < 64 ? (qbits << -sh) : 0ull;
   }
   return m & att_low_mask(kv_len - key0);
+}
+__device__ __forceinline__ unsigned long long att_visible_mask(const AttnArgs& p, int n_ctx, int kv_len, int q_abs,
+                                                               unsigned long long qbits, int key0) {
+  return att_visible_mask(p.causal != 0, n_ctx, kv_len, q_abs, qbits, key0);
 }
 
 // ---- pass 1: one (head, query block, key chunk) item: S = Q K^T, mask, scale, chunk max / sum -----------------

@@ -71,6 +71,9 @@ struct AttnArgs {
   float* opart = nullptr;   int pv_splits = 0;          // [nh][tq_blocks][pv_splits][32][128]
   int* counters = nullptr;                               // [nh][tq_blocks]
   bf16* O = nullptr;  long ldo = 0;                       // [Tq][nh*128]
+  // program kernel only: the caller asserts that *n_ctx and the K/V rows [0, *n_ctx) are final when the launch starts
+  // (no earlier phase of the program changes them), so the KV producer may stage them ahead of the phase
+  int prefix_stable = 0;
 };
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t st);
 

@@ -34,6 +34,7 @@
 
 #include "../../include/vispec_b200.h"
 #include "attn_dev.cuh"
+#include "attn_ring.cuh"
 #include "profile.h"
 #include "program_dev.cuh"
 #include "slab.h"
@@ -72,7 +73,9 @@ static_assert(PHASE_WORDS <= PG_WORKERS, "phase descriptor larger than one word 
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int TMEM_COLS = 128;               // two accumulator sets x two tiles x 32 token columns
 static_assert(sizeof(AttnSmem) <= BIG_SMEM, "team scratch too small for attention");
-static_assert(sizeof(AttnFusedSmem) <= BIG_SMEM, "team scratch too small for fused attention");
+static_assert(sizeof(AttnRingSmem) <= BIG_SMEM, "team scratch too small for the TMA-staged attention");
+static_assert(BIG_SMEM % 1024 == 0 && RING_BYTES % 1024 == 0, "granules are swizzled by shared-memory address");
+constexpr int ATT_BAR_OFF = BAR_OFF + 256;       // full[4] | empty[4] mbarriers of the granule FIFO, per attention team
 static_assert(sizeof(TreeSmem) <= BIG_SMEM, "team scratch too small for the tree ops");
 static_assert(sizeof(SampleSmem) <= BIG_SMEM, "team scratch too small for the sampling accept");
 static_assert(sizeof(ScanSmem) <= BIG_SMEM, "team scratch too small for the vocabulary scans");
@@ -99,26 +102,44 @@ __device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_tea
   for (int item = gteam; item < n_items; item += n_teams)
     attn_pv_item(a, sm, item / a.pv_splits, 0, 1, item % a.pv_splits, a.pv_splits, tt, tsync);
 }
-__device__ __noinline__ void attn_stream_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
-                                               BigTeamSync tsync, int n_ctx) {
-  AttnArgs a = ph.attn;
-  a.n_ctx = nullptr;                         // the kv length was read once by the dispatcher
-  a.n_ctx_host = n_ctx;
-  attn_stream_item(a, *reinterpret_cast<AttnFusedSmem*>(tsm), gteam / a.pv_splits, gteam % a.pv_splits, a.pv_splits,
-                   ph.tile_cnt, epoch, tt, tsync);
+// PH_ATTN_FUSED: one (head, kv split) item per team, K/V granules staged by the KV producer warp (attn_ring.cuh).
+// `fifo`: FIFO index of the team's next granule (advances identically on the producer side).  The arguments are read
+// from the staged phase descriptor in shared memory (no private copy in local memory).
+template <bool STREAM, bool EAGER>
+__device__ __noinline__ void attn_ring_phase(const Phase& ph, int n_ctx, AttnRingSmem& sm, uint64_t* bars, unsigned int& fifo,
+                                             unsigned int epoch, int gteam, int tt, BigTeamSync tsync) {
+  const int sp = ph.attn.pv_splits;
+  fifo += attn_ring_item<STREAM, EAGER>(ph.attn, n_ctx, sm, bars, fifo, gteam / sp, gteam % sp, sp, ph.tile_cnt, epoch, tt, tsync);
 }
-__device__ __noinline__ void attn_fused_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
-                                              BigTeamSync tsync) {
-  AttnArgs a = ph.attn;
-  if (gteam >= a.n_heads * a.pv_splits) return;   // one resident item per team: the items of a head wait for each other
-  // up to ATT_FUSED_CPS chunks per split the scores stay in registers; longer contexts stream (same for every item)
-  const int n_ctx = a.n_ctx ? ld_vol(a.n_ctx) : a.n_ctx_host;
-  const int n_chunks = (n_ctx + a.n_new + ATT_CHUNK - 1) / ATT_CHUNK;
-  if (n_chunks > ATT_FUSED_CPS * a.pv_splits) { attn_stream_phase(ph, epoch, gteam, tt, tsm, tsync, n_ctx); return; }
-  a.n_ctx = nullptr;                         // one L2 round trip for the kv length, not two
-  a.n_ctx_host = n_ctx;
-  attn_fused_item(a, *reinterpret_cast<AttnFusedSmem*>(tsm), gteam / a.pv_splits, gteam % a.pv_splits, a.pv_splits,
-                  ph.tile_cnt, epoch, tt, tsync);
+// kv length of a prefix_stable phase: the same device int for every layer of a verify step and unchanged since the launch
+// started, so one L2 round trip serves all of them
+struct KvLenCache { const int* ptr; int val; };
+__device__ __forceinline__ void attn_fused_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
+                                                 uint64_t* bars, unsigned int& fifo, KvLenCache& kvc, BigTeamSync tsync) {
+  const AttnArgs& a = ph.attn;
+  const int sp = a.pv_splits;
+  if (gteam >= a.n_heads * sp) return;            // one resident item per team: the items of a head wait for each other
+  int n_ctx = a.n_ctx_host;
+  if (a.n_ctx) {
+    if (a.prefix_stable && kvc.ptr == a.n_ctx) n_ctx = kvc.val;
+    else {
+      n_ctx = ld_vol(a.n_ctx);
+      if (a.prefix_stable) { kvc.ptr = a.n_ctx; kvc.val = n_ctx; }
+    }
+  }
+  const int kv_len = n_ctx + a.n_new;
+  if (kv_len > a.score_ld) __trap();              // the score scratch bounds the context
+  AttnRingSmem& sm = *reinterpret_cast<AttnRingSmem*>(tsm);
+  // up to 2 * ATT_RING_NG granules per split the scores stay in registers; longer contexts park them (uniform over the items)
+  const int n_gran = (kv_len + ATT_GRAN - 1) / ATT_GRAN;
+  const bool stream = (n_gran + sp - 1) / sp > 2 * ATT_RING_NG;
+  if (a.eager) {
+    if (stream) attn_ring_phase<true, true>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
+    else attn_ring_phase<false, true>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
+  } else {
+    if (stream) attn_ring_phase<true, false>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
+    else attn_ring_phase<false, false>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
+  }
 }
 __device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team_base) {
   // the tree bodies read device state with plain loads: drop whatever this SM's L1 still holds from an earlier phase of
@@ -186,6 +207,12 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], PG_WORKERS / 32);
     }
+    uint64_t* att_bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR_OFF);
+    for (int t = 0; t < PG_BIG_TEAMS; ++t)
+      for (int i = 0; i < ATT_SLOTS; ++i) {
+        mbar_init(&att_bars[t * 2 * ATT_SLOTS + i], 1);                      // full: the producer's expect_tx arrival
+        mbar_init(&att_bars[t * 2 * ATT_SLOTS + ATT_SLOTS + i], ATT_WARPS);       // empty: 8 arrivals (attn_ring.cuh)
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -422,7 +449,38 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         }
       }
     }
-  } else if (warp >= 4) {        // (warp 3 is idle: it was the L2 prefetcher of round 1)
+  } else if (warp == 3) {
+    // ===================== KV producer =====================
+    // Walks the attention phases of the program in order and keeps the granule FIFO of both attention teams full
+    // (attn_ring.cuh).  The fully visible prefix of a phase flagged prefix_stable does not depend on this launch, so its K
+    // granules are staged as soon as the team scratch is free (ph.pf_bars grid barriers), long before the phase starts.
+    if (lane == 0) {
+      unsigned int fifo[2] = {0u, 0u};
+      uint64_t* att_bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR_OFF);
+      for (int p = 0; p < hdr.n_phases; ++p) {
+        const Phase& ph = hdr.phases[p];
+        if (ph.type != PH_ATTN_FUSED) continue;
+        const unsigned int need_start = (unsigned int)ph.pf_bars * (unsigned int)G;
+        const unsigned int need_tail = (unsigned int)ph.bars_before * (unsigned int)G;
+        while (ld_relaxed_u32(hdr.counters) < need_start) __nanosleep(100);
+#ifdef VS_PROGRAM_CLK
+        if (b == 0) g_clk[20] = clock64();
+#endif
+        const bool tail_ok = need_start >= need_tail;
+        if (tail_ok) fence_proxy_async();
+        const AttnArgs a = ph.attn;
+        const int n_ctx = a.n_ctx ? __ldcg(a.n_ctx) : a.n_ctx_host;
+#ifdef VS_PROGRAM_CLK
+        if (b == 0) g_clk[21] = clock64() + (n_ctx & 0);
+#endif
+        att_ring_produce(a, hdr.maps + ph.tmK, hdr.maps + ph.tmV, ph.kv_two_loads, n_ctx, team_base, BIG_SMEM, att_bars, fifo,
+                         hdr.counters, need_tail, tail_ok, b, G);
+#ifdef VS_PROGRAM_CLK
+        if (b == 0) g_clk[23] = clock64();
+#endif
+      }
+    }
+  } else if (warp >= 4) {
     // ===================== workers (16 warps: four teams of 128 threads / two attention teams of 256) =====================
     const int wtid = threadIdx.x - 4 * 32;          // 0..511
     const int team = wtid >> 7, tt = wtid & 127;    // small team
@@ -436,6 +494,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     const int gteam = team * G + b, n_teams = PG_TEAMS * G;
     const int gbteam = bteam * G + b, n_bteams = PG_BIG_TEAMS * G;
     int acc = 0, acc_par = 0;
+    unsigned int att_fifo = 0;                      // granules of the attention FIFO this team consumed so far
+    KvLenCache kvc{nullptr, 0};
+    uint64_t* att_bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR_OFF) + bteam * 2 * ATT_SLOTS;
     const unsigned int epoch = ld_relaxed_u32(hdr.counters + 2);     // launches completed before this one
     // Phase descriptors are staged through shared memory: the words of phase p+1 are loaded while phase p runs and
     // stored just before the barrier, so no phase starts with a chain of L2 round trips for its own arguments.
@@ -488,7 +549,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
         case PH_ATTN_S: attn_s_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
         case PH_ATTN_PV: attn_pv_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
-        case PH_ATTN_FUSED: attn_fused_phase(ph, epoch, gbteam, btt, bsm, bsync); break;
+        case PH_ATTN_FUSED: attn_fused_phase(ph, epoch, gbteam, btt, bsm, att_bars, att_fifo, kvc, bsync); break;
         case PH_ARGMAX: argmax_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_LSM_STATS: lsm_stats_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_LSM_CAND: lsm_cand_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
@@ -544,7 +605,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
 // =================================================================================================================
 struct vs_program {
   std::vector<vs::Phase> phases;
-  struct MapReq { const void* ptr; long ld; int rows, cols, box_rows, box_depth; };   // box_depth > 0: 3-D {64, rows, depth}
+  // box_depth > 0: 3-D {64, rows, depth}; kv != 0: K / V rows of an attention phase (ld = head stride in elements,
+  // rows = rows per head, cols = kv heads): 4-D {64 dims, rows, 2 halves, heads} with a {64, 32, 2, 1} box
+  struct MapReq { const void* ptr; long ld; int rows, cols, box_rows, box_depth, kv; };
   struct SlabReg { const void* w; const void* slab; int pair, grid, packed; };
   std::vector<SlabReg> slabs; // row-major weight pointer -> slab image (vs_program_register_slab)
   int last_ssq_rows = 0;      // rows of [.][32] partial sums the last residual epilogue left in the ssq workspace
@@ -565,6 +628,8 @@ struct vs_program {
   int inflight = 0;           // weight stages in flight per SM (0 = the whole ring)
   int spin_ns = 100;          // back-off of the single-lane role warps between barrier polls
   int debug = 0;              // ProgramHeader::debug
+  int kv_two_loads = 0;       // option "kv_two_loads": force the 3-D form of the K / V tensor maps (A/B, tests)
+  bool attn_prefetch = true;  // option "attn_prefetch": stage the stable K prefix of an attention phase ahead of the phase
   bool committed = false;
   bool trace_on = false;
   // device workspace layout (set by commit)
@@ -599,10 +664,20 @@ int device_sms() {     // of the CURRENT device (one process may drive several G
 int add_map(vs_program* pg, const void* ptr, long ld, int rows, int cols, int box_rows, int box_depth = 0) {
   for (size_t i = 0; i < pg->maps.size(); ++i) {
     const auto& m = pg->maps[i];
-    if (m.ptr == ptr && m.ld == ld && m.rows == rows && m.cols == cols && m.box_rows == box_rows && m.box_depth == box_depth)
+    if (m.ptr == ptr && m.ld == ld && m.rows == rows && m.cols == cols && m.box_rows == box_rows && m.box_depth == box_depth &&
+        !m.kv)
       return (int)i;
   }
-  pg->maps.push_back({ptr, ld, rows, cols, box_rows, box_depth});
+  pg->maps.push_back({ptr, ld, rows, cols, box_rows, box_depth, 0});
+  return (int)pg->maps.size() - 1;
+}
+int add_kv_map(vs_program* pg, const void* ptr, long head_stride, int n_kv) {
+  const int rows = (int)(head_stride / 128);
+  for (size_t i = 0; i < pg->maps.size(); ++i) {
+    const auto& m = pg->maps[i];
+    if (m.kv && m.ptr == ptr && m.ld == head_stride && m.cols == n_kv) return (int)i;
+  }
+  pg->maps.push_back({ptr, head_stride, rows, n_kv, ATT_GRAN, 0, 1});
   return (int)pg->maps.size() - 1;
 }
 
@@ -823,9 +898,17 @@ int prog_add_attention(vs_program* pg, const AttnArgs& a) {
     const int sp = fused_splits(G, a.n_heads, a.pv_splits, a.max_chunks);
     if (sp < 1 || a.n_heads * sp > PG_BIG_TEAMS * G)
       return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_attention", "too many heads for the fused attention phase");
+    if (a.kv_head_stride % 128 != 0 || a.kv_head_stride < 128 || reinterpret_cast<uintptr_t>(a.K) % 16 != 0 ||
+        reinterpret_cast<uintptr_t>(a.V) % 16 != 0 || a.score_ld % ATT_GRAN != 0)
+      return pfail(VS_ERR_INVALID, "vs_program_add_attention", "K / V rows must be 16-byte aligned with a head stride that is a multiple of 128 elements, score_ld a multiple of 32");
     Phase f = blank(PH_ATTN_FUSED, a.Tq);
     f.attn = a;
     f.attn.pv_splits = sp;
+    f.tmK = add_kv_map(pg, a.K, a.kv_head_stride, a.n_kv_heads);
+    f.tmV = add_kv_map(pg, a.V, a.kv_head_stride, a.n_kv_heads);
+    // the prefix may be staged ahead only if nothing earlier in the program moves the kv length or the rows
+    for (const auto& ph : pg->phases)
+      if (ph.type == PH_TREE || ph.type == PH_SPLICE) f.attn.prefix_stable = 0;
     // per-head arrival counters live with the per-tile counters of the fused epilogues (+1: 0 stays "none")
     f.tile_cnt = reinterpret_cast<unsigned int*>(uintptr_t(pg->tile_cnt_count + 1));
     pg->tile_cnt_count += 2 * a.n_heads;
@@ -1012,6 +1095,8 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   else if (!strcmp(name, "spin_ns")) pg->spin_ns = value;
   else if (!strcmp(name, "x3d")) pg->x3d = value != 0;
   else if (!strcmp(name, "debug")) pg->debug = value;
+  else if (!strcmp(name, "kv_two_loads")) pg->kv_two_loads = value != 0;
+  else if (!strcmp(name, "attn_prefetch")) pg->attn_prefetch = value != 0;
 
   else if (!strcmp(name, "grid")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "grid must be set before adding phases");
@@ -1068,7 +1153,33 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
     const auto& m = pg->maps[i];
     CUtensorMap tm;
     CUresult r;
-    if (m.box_depth > 0) {
+    if (m.kv) {
+      // K or V rows [heads][rows][128]: {64 dims, rows, 2 halves of a row, heads}; one box = 32 rows x both halves lands as
+      // [half][32 rows][64 dims] = two 128-byte-swizzled 4 KB tiles (attn_ring.cuh).  If the driver refuses the view
+      // (the half stride is smaller than the row stride), a 3-D {128, rows, heads} map with two loads per granule.
+      cuuint64_t dims[4] = {64, (cuuint64_t)m.rows, 2, (cuuint64_t)m.cols};
+      cuuint64_t strides[3] = {256, 128, (cuuint64_t)m.ld * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)m.box_rows, 2, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      if (!pg->kv_two_loads) {
+        r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(m.ptr), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {       // every K / V map of the program takes the 3-D form: start over
+          pg->kv_two_loads = 1;
+          i = (size_t)-1;
+          continue;
+        }
+      } else {
+        cuuint64_t dims3[3] = {128, (cuuint64_t)m.rows, (cuuint64_t)m.cols};
+        cuuint64_t strides3[2] = {256, (cuuint64_t)m.ld * 2};
+        cuuint32_t box3[3] = {64, (cuuint32_t)m.box_rows, 1};
+        r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(m.ptr), dims3, strides3, box3, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return pfail(VS_ERR_CUDA, "vs_program_commit", "cuTensorMapEncodeTiled failed (K / V rows)");
+      }
+    } else if (m.box_depth > 0) {
       // [rows][cols] viewed as {64 columns, rows, cols / 64 chunks}: one box = box_depth consecutive [rows x 64] blocks,
       // each landing as its own 128-byte-swizzled 4 KB tile (the activation side of a slab stage)
       cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)m.rows, (cuuint64_t)(m.cols / BK)};
@@ -1101,9 +1212,16 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
   memcpy(host.data() + pg->off_tables, pg->tables.data(), pg->tables.size() * sizeof(int));
   float* partials = reinterpret_cast<float*>(pg->ws + pg->off_partials);
   int bars = 0;
+  int scratch_free_bars = 0;     // grid barriers after which the attention teams' scratch is no longer in use by a phase
   for (size_t i = 0; i < pg->phases.size(); ++i) {
     Phase ph = pg->phases[i];
     ph.bars_before = bars;
+    if (ph.type == PH_ATTN_FUSED) {
+      ph.kv_two_loads = pg->kv_two_loads;
+      ph.pf_bars = (ph.attn.prefix_stable && pg->attn_prefetch) ? scratch_free_bars : bars;
+    }
+    if (ph.type != PH_GEMM && ph.type != PH_EPI && ph.type != PH_NORM && ph.type != PH_ROWS && ph.type != PH_SPLICE)
+      scratch_free_bars = bars + 1;
     if (!(ph.type == PH_GEMM && ph.no_barrier)) ++bars;
     if (ph.tile_cnt)
       ph.tile_cnt = reinterpret_cast<unsigned int*>(pg->ws + pg->off_tilecnt) + (reinterpret_cast<uintptr_t>(ph.tile_cnt) - 1);

@@ -79,6 +79,9 @@ struct Phase {
   const float* ssq_in; int ssq_tiles;
   // ---- PH_ATTN_*
   AttnArgs attn;
+  int tmK, tmV;               // PH_ATTN_FUSED: tensor maps of the K / V rows (attn_ring.cuh granules)
+  int kv_two_loads;           // the driver refused the 4-D {64, rows, 2, heads} view: two 3-D loads per granule
+  int pf_bars;                // grid barriers after which the KV producer may start staging this phase's granules
   // ---- PH_ARGMAX / PH_LSM_TOPK
   const bf16* logits; long ldl; int V; int k;
   const int* row_sel; float* top_val; int* top_idx; int* amax_out;

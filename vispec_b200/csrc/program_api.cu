@@ -48,7 +48,7 @@ int linear(vs_program* pg, const bf16* X, long ldx, const bf16* W, const bf16* b
 // residual epilogue that produced it); updated for the caller.
 int decoder_layer(vs_program* pg, const vs_dims* d, const vs_layer* l, const vs_scratch* s, const vs_rope* rope, int T,
                   const int32_t* pos_ids, const int32_t* kv_row_base, int kv_row_off, const int32_t* n_ctx, int n_ctx_host,
-                  int n_new, int causal, const uint64_t* bits, int eager, bool* h_has_ssq) {
+                  int n_new, int causal, const uint64_t* bits, int eager, bool* h_has_ssq, int prefix_stable = 0) {
   REQUIRE(T >= 1 && T <= VS_TOK_BLOCK && s->max_rows >= VS_TOK_BLOCK, "programs handle 1..32 rows");
   REQUIRE(d->hidden % 64 == 0 && d->inter % 64 == 0, "hidden and inter must be multiples of 64");
   const int H = d->hidden, I = d->inter, nh = d->n_heads, nkv = d->n_kv_heads;
@@ -79,6 +79,7 @@ int decoder_layer(vs_program* pg, const vs_dims* d, const vs_layer* l, const vs_
     a.scores = s->scores; a.score_ld = s->score_ld; a.stats = s->stats; a.max_chunks = s->max_chunks;
     a.opart = s->opart; a.pv_splits = s->pv_splits; a.counters = s->attn_counters;
     a.O = B(s->attn); a.ldo = (long)nh * 128;
+    a.prefix_stable = prefix_stable;
     RET(vs::prog_add_attention(pg, a));
   }
   REQUIRE(H % 128 == 0, "hidden must be a multiple of 128");
@@ -100,7 +101,9 @@ int verify_step(vs_program* pg, const vs_target* t, const vs_scratch* s, const i
   const int32_t* cur = state + VS_ST_CUR_LEN;
   bool has_ssq = false;
   for (int li = 0; li < d->n_layers; ++li)
-    RET(decoder_layer(pg, d, &t->layers[li], s, &t->rope, T, pos_ids, cur, 0, cur, 0, T, bits ? 0 : 1, bits, t->sdpa_attention ? 0 : 1, &has_ssq));
+    // the kv length and the prefix rows of the verify step are final when the launch starts (prog_add_attention drops the
+    // flag when a tree / splice phase precedes it in the program)
+    RET(decoder_layer(pg, d, &t->layers[li], s, &t->rope, T, pos_ids, cur, 0, cur, 0, T, bits ? 0 : 1, bits, t->sdpa_attention ? 0 : 1, &has_ssq, 1));
   RET(vs::prog_add_norm(pg, B(s->h), H, B(t->norm), B(hidden_out), H, T, H, d->eps, has_ssq ? PROG_WS_SSQ : nullptr, H / 128));
   RET(linear(pg, B(hidden_out), H, B(t->lm_head), nullptr, T, V, H, vs::EPI_STORE, B(logits), V, nullptr, 0, nullptr));
   if (amax) RET(vs::prog_add_argmax(pg, B(logits), V, T, V, amax, fuse_argmax));
@@ -203,6 +206,7 @@ int vs_program_add_attention(vs_program* pg, const vs_attn_args* a) {
   g.eager = a->eager; g.scale = a->scale; g.scores = a->scores; g.score_ld = a->score_ld; g.stats = a->stats;
   g.max_chunks = a->max_chunks; g.opart = a->opart; g.pv_splits = a->pv_splits; g.counters = a->counters;
   g.O = B(a->O); g.ldo = a->ldo;
+  g.prefix_stable = a->prefix_stable;
   return vs::prog_add_attention(pg, g);
 }
 int vs_program_add_draft_level0(vs_program* pg, const vs_tree_bufs* tb, int32_t* state) {

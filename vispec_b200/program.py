@@ -14,7 +14,7 @@ class Program:
     """Build with the `add_*` methods (thin wrappers of `vs_program_add_*`; `p.lib` exposes the rest), `commit()`, then
     `run()` any number of times."""
 
-    def __init__(self, device, pf_ahead: Optional[int] = None, trace: bool = False, attn_fused: bool = False):
+    def __init__(self, device, pf_ahead: Optional[int] = None, trace: bool = False, attn_fused: bool = False, **options):
         if torch.device(device).type != "cuda":
             raise RuntimeError("vispec_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = L.load()
@@ -30,6 +30,8 @@ class Program:
             self.set_option("trace", 1)
         if attn_fused:
             self.set_option("attn_fused", 1)
+        for name, value in options.items():        # any other vs_program_set_option switch (kv_two_loads, attn_prefetch, ...)
+            self.set_option(name, value)
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
