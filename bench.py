@@ -854,6 +854,8 @@ def run_tp13b(args):
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             res[mode + "_ms"] = tm.item()
             res[mode + "_next_token"] = int(torch.argmax(lg))
+            if mode == "tp" and getattr(eng, "_tp_timing", None):      # VS_TP_TIMING=1: ms per kind of step (rank 0)
+                res["tp_breakdown_ms"] = eng._tp_timing
         if use_dist:
             res["speedup_tp_over_native"] = res["native_1gpu_ms"] / res["tp_ms"]
             res["next_token_equal"] = res["native_1gpu_next_token"] == res["tp_next_token"]

@@ -62,6 +62,18 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// L2 prefetch of one box (no shared-memory destination, no completion)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // How a (head, split) item cuts the keys: granules [g_lo, g_hi) of ceil(kv_len / 32).  Producer and workers both use this.
 struct AttRingCut {
   int n_gran, cps, g_lo, n;
@@ -85,17 +97,17 @@ __device__ __forceinline__ AttRingCut att_ring_cut(int kv_len, int split, int n_
 __device__ __forceinline__ void att_ring_produce(const AttnArgs& a, const CUtensorMap* mapK, const CUtensorMap* mapV, int two_loads,
                                                  int n_ctx, uint8_t* team_base, int team_stride, uint64_t* bars,
                                                  unsigned int* fifo, const unsigned int* grid_ctr, unsigned int need_tail,
-                                                 bool tail_ok, int b, int G) {
+                                                 bool tail_ok, int b, int G, int pf_dist) {
   const int n_splits = a.pv_splits;
   const int kv_len = n_ctx + a.n_new;
   const int tail_g = n_ctx / ATT_GRAN;                    // first granule that holds rows written by this launch
   const int group = a.n_heads / a.n_kv_heads;
   const uint64_t hint = group == 1 ? HINT_EVICT_FIRST : 0x1000000000000000ull /* evict normal */;
-  int n[2], g_lo[2], kvh[2], issued[2];
+  int n[2], g_lo[2], kvh[2], issued[2], pf[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int gb = t * G + b;
-    n[t] = 0; g_lo[t] = 0; kvh[t] = 0; issued[t] = 0;
+    n[t] = 0; g_lo[t] = 0; kvh[t] = 0; issued[t] = 0; pf[t] = 0;
     if (gb < a.n_heads * n_splits) {
       const AttRingCut c = att_ring_cut(kv_len, gb % n_splits, n_splits);
       n[t] = c.n;
@@ -108,6 +120,24 @@ __device__ __forceinline__ void att_ring_produce(const AttnArgs& a, const CUtens
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       if (issued[t] >= 2 * n[t]) continue;
+      // L2 prefetch `pf_dist` granules ahead of the FIFO: four 8 KB slots per team are ~2 us of HBM latency at 15 GB/s per
+      // team; with the lines already in L2 the same slots turn around several times faster.  (Rows this launch is still
+      // writing may be prefetched too: L2 is the point of coherence, the later stores update the line.)
+      while (pf[t] < 2 * n[t] && pf[t] < issued[t] + pf_dist) {
+        const int j = pf[t];
+        const bool pv = j >= n[t];
+        const int pg = g_lo[t] + (pv ? j - n[t] : j);
+        const CUtensorMap* pm = pv ? mapV : mapK;
+        if (j >= issued[t] + ATT_SLOTS) {       // the next ATT_SLOTS granules are about to be loaded anyway
+          if (two_loads) {
+            tma_prefetch_3d(pm, 0, pg * ATT_GRAN, kvh[t]);
+            tma_prefetch_3d(pm, 64, pg * ATT_GRAN, kvh[t]);
+          } else {
+            tma_prefetch_4d(pm, 0, pg * ATT_GRAN, 0, kvh[t]);
+          }
+        }
+        ++pf[t];
+      }
       const int i = issued[t];
       const bool is_v = i >= n[t];
       const int g = g_lo[t] + (is_v ? i - n[t] : i);
@@ -146,11 +176,29 @@ __device__ __forceinline__ void att_ring_produce(const AttnArgs& a, const CUtens
 // ---------------------------------------------------------------------------------------------------------------------
 // shared tails (same exchanges as attn_dev.cuh, on this shared-memory layout)
 // ---------------------------------------------------------------------------------------------------------------------
-// split statistics -> head-wide softmax denominators; on entry sm.red / sm.red2 hold every warp's (max, sum exp) per row
+// split statistics -> head-wide softmax denominators; on entry sm.red / sm.red2 hold every warp's (max, sum exp) per row.
+// The exchange is ONE L2 round trip: every split stores its (m, l) per row as two 8-byte words that carry the launch tag in
+// their upper half (an aligned 8-byte store is single-copy atomic: value and flag arrive together, no fence, no counter),
+// and every reader spins on exactly the words it needs until they carry this launch's tag.
+// `ll`: [head][split][32 rows][2] words in the program workspace, private to the phase.
+__device__ __forceinline__ void att_ll_store(unsigned long long* at, float m, float l, unsigned int tag) {
+  const unsigned long long w0 = ((unsigned long long)tag << 32) | __float_as_uint(m);
+  const unsigned long long w1 = ((unsigned long long)tag << 32) | __float_as_uint(l);
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(at), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ float2 att_ll_wait(const unsigned long long* at, unsigned int tag) {
+  unsigned long long w0, w1;
+  do {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(at) : "memory");
+  } while ((unsigned int)(w0 >> 32) != tag || (unsigned int)(w1 >> 32) != tag);
+  return make_float2(__uint_as_float((unsigned int)w0), __uint_as_float((unsigned int)w1));
+}
 template <class Sync>
 __device__ __forceinline__ void att_ring_exchange_stats(const AttnArgs& p, AttnRingSmem& sm, int head, int split, int n_splits,
                                                         unsigned int* head_cnt, unsigned int epoch, int tid, Sync sync) {
-  float* stat_head = p.stats + (long)head * p.max_chunks * VS_TOK * 2;
+  unsigned long long* ll = reinterpret_cast<unsigned long long*>(head_cnt + ((2 * p.n_heads + 3) & ~3)) +
+                           (long)head * n_splits * VS_TOK * 2;
+  const unsigned int tag = epoch + 1u;
   if (tid < VS_TOK) {
     float m = sm.red[0][tid];
 #pragma unroll
@@ -161,29 +209,21 @@ __device__ __forceinline__ void att_ring_exchange_stats(const AttnArgs& p, AttnR
       const float mw = sm.red[w][tid];
       if (mw != -INFINITY) l += sm.red2[w][tid] * expf(mw - m);
     }
-    *reinterpret_cast<float2*>(stat_head + ((long)split * VS_TOK + tid) * 2) = make_float2(m, l);
+    att_ll_store(ll + ((long)split * VS_TOK + tid) * 2, m, l, tag);
   }
-  sync();
-  if (tid == 0) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(head_cnt + head) : "memory");
-    const unsigned int want = (epoch + 1u) * (unsigned int)n_splits;
-    while (att_ld_relaxed(head_cnt + head) < want) {
-    }
-  }
-  sync();
+  // ---- exact global denominators from the split statistics: 8 lanes per row, splits part, part+8 (fixed order)
   {
     const int q = tid >> 3, part = tid & 7;
-    float2 st[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      st[j] = __ldcg(reinterpret_cast<const float2*>(stat_head + ((long)min(part + 8 * j, n_splits - 1) * VS_TOK + q) * 2));
     float m = -INFINITY, l = 0.f;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      if (part + 8 * j < n_splits && st[j].x != -INFINITY) {
-        const float mn = fmaxf(m, st[j].x);
-        l = l * expf(m - mn) + st[j].y * expf(st[j].x - mn);
-        m = mn;
+      if (part + 8 * j < n_splits) {
+        const float2 st = att_ll_wait(ll + ((long)(part + 8 * j) * VS_TOK + q) * 2, tag);
+        if (st.x != -INFINITY) {
+          const float mn = fmaxf(m, st.x);
+          l = l * expf(m - mn) + st.y * expf(st.x - mn);
+          m = mn;
+        }
       }
     }
 #pragma unroll
@@ -530,22 +570,21 @@ __device__ __forceinline__ unsigned int attn_ring_item(const AttnArgs& p, int n_
     const int slot = f & (ATT_SLOTS - 1);
     mbar_wait(&full[slot], (f >> 2) & 1u);
     if (i == 0) ACLK(8);
-    uint8_t* vt = sm.ring[slot];
+    const uint8_t* vt = sm.ring[slot];
+    // rows past the kv length hold whatever the cache holds: their probabilities are zero, but 0 x NaN is not, so the V
+    // fragments of those keys are cleared in registers (fragment register 0 / 2: keys 16 kg + 2 t4, +1; 1 / 3: +8)
+    uint32_t vm0 = 0xffffffffu, vm1 = 0xffffffffu;
     if (i == i_zero) {
-      // rows past the kv length hold whatever the cache holds: their probabilities are zero, but 0 x NaN is not.
-      // Every consumer warp of the slot writes the same zeros before it reads.
-      const int r0 = kv_len - (g_lo + i) * ATT_GRAN;
-      for (int j = lane; j < (ATT_GRAN - r0) * 16; j += 32) {
-        const int r = r0 + (j >> 4), c = j & 15;
-        *reinterpret_cast<uint4*>(vt + att_gran_off(r, c)) = make_uint4(0, 0, 0, 0);
-      }
-      __syncwarp();
+      const int r0 = kv_len - (g_lo + i) * ATT_GRAN, k = 16 * kg + 2 * t4;
+      vm0 = (k < r0 ? 0x0000ffffu : 0u) | (k + 1 < r0 ? 0xffff0000u : 0u);
+      vm1 = (k + 8 < r0 ? 0x0000ffffu : 0u) | (k + 9 < r0 ? 0xffff0000u : 0u);
     }
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn) {
       uint32_t bfr[4];
       // chunk = dh * 8 + dn * 2 + v_ch: bits 1..2 of the chunk index take dn, swizzled by XOR with the row bits
       ldmatrix_x4_trans(bfr, vt + (v_off ^ (uint32_t)(dn << 5)));
+      if (i == i_zero) { bfr[0] &= vm0; bfr[1] &= vm1; bfr[2] &= vm0; bfr[3] &= vm1; }
       mma_bf16(oacc[2 * dn], pa, bfr[0], bfr[1]);
       mma_bf16(oacc[2 * dn + 1], pa, bfr[2], bfr[3]);
     }

@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         if (b == 0) g_clk[21] = clock64() + (n_ctx & 0);
 #endif
         att_ring_produce(a, hdr.maps + ph.tmK, hdr.maps + ph.tmV, ph.kv_two_loads, n_ctx, team_base, BIG_SMEM, att_bars, fifo,
-                         hdr.counters, need_tail, tail_ok, b, G);
+                         hdr.counters, need_tail, tail_ok, b, G, hdr.attn_pf);
 #ifdef VS_PROGRAM_CLK
         if (b == 0) g_clk[23] = clock64();
 #endif
@@ -630,6 +630,8 @@ struct vs_program {
   int debug = 0;              // ProgramHeader::debug
   int kv_two_loads = 0;       // option "kv_two_loads": force the 3-D form of the K / V tensor maps (A/B, tests)
   bool attn_prefetch = true;  // option "attn_prefetch": stage the stable K prefix of an attention phase ahead of the phase
+  int attn_pf = 0;            // option "attn_pf": L2 prefetch distance of the KV producer in granules (0 = off; measured
+                              // slower at every distance: 8192 keys 60.1 -> 62.6 / 65.7 / 69.4 us per layer at 8 / 16 / 32)
   bool committed = false;
   bool trace_on = false;
   // device workspace layout (set by commit)
@@ -910,8 +912,10 @@ int prog_add_attention(vs_program* pg, const AttnArgs& a) {
     for (const auto& ph : pg->phases)
       if (ph.type == PH_TREE || ph.type == PH_SPLICE) f.attn.prefix_stable = 0;
     // per-head arrival counters live with the per-tile counters of the fused epilogues (+1: 0 stays "none")
+    // (+ the tagged split statistics of attn_ring.cuh: [heads][splits][32 rows] x 16 bytes, 16-byte aligned)
+    pg->tile_cnt_count = (pg->tile_cnt_count + 3) & ~size_t(3);
     f.tile_cnt = reinterpret_cast<unsigned int*>(uintptr_t(pg->tile_cnt_count + 1));
-    pg->tile_cnt_count += 2 * a.n_heads;
+    pg->tile_cnt_count += ((2 * a.n_heads + 3) & ~3) + (size_t)a.n_heads * sp * VS_TOK * 4;
     pg->phases.push_back(f);
     return VS_OK;
   }
@@ -1067,6 +1071,10 @@ int vs_program_create(vs_program** out) {
   if (e) (*out)->x3d = atoi(e) != 0;
   e = getenv("VS_PG_DEBUG");
   if (e) (*out)->debug = atoi(e);
+  e = getenv("VS_ATTN_PF");           // A/B switches of the TMA-staged attention (attn_ring.cuh)
+  if (e) (*out)->attn_pf = atoi(e);
+  e = getenv("VS_ATTN_PREFETCH");
+  if (e) (*out)->attn_prefetch = atoi(e) != 0;
   return VS_OK;
 }
 
@@ -1097,6 +1105,7 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   else if (!strcmp(name, "debug")) pg->debug = value;
   else if (!strcmp(name, "kv_two_loads")) pg->kv_two_loads = value != 0;
   else if (!strcmp(name, "attn_prefetch")) pg->attn_prefetch = value != 0;
+  else if (!strcmp(name, "attn_pf")) pg->attn_pf = value;
 
   else if (!strcmp(name, "grid")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "grid must be set before adding phases");
@@ -1106,10 +1115,7 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
 }
 
 int vs_attention_fused_capacity(int n_heads, int pv_splits_cap, int max_chunks) {
-  // beyond splits * ATT_FUSED_CPS chunks (scores in registers) the phase streams its chunks: the scratch is the limit
-  const char* e = getenv("VS_ATTN_STREAM");
-  if (e && atoi(e) == 0)
-    return vs::fused_splits(vs::device_sms(), n_heads, pv_splits_cap, max_chunks) * vs::ATT_FUSED_CPS * vs::ATT_CHUNK;
+  // beyond 2 * ATT_RING_NG granules per split (scores in registers) the phase parks its scores: the scratch is the limit
   return vs::fused_splits(vs::device_sms(), n_heads, pv_splits_cap, max_chunks) < 1 ? 0 : max_chunks * vs::ATT_CHUNK;
 }
 
@@ -1268,6 +1274,7 @@ int vs_program_run(const vs_program* pg, void* stream) {
   h.inflight = pg->inflight;
   h.spin_ns = pg->spin_ns;
   h.debug = pg->debug;
+  h.attn_pf = pg->attn_pf;
   bool has_slab = false;
   for (const auto& ph : pg->phases) has_slab = has_slab || ph.type == PH_GEMM2;
   h.ns = has_slab ? RING_BYTES / SLAB_SLOT_BYTES : NS_MAX;

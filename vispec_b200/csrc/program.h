@@ -109,6 +109,7 @@ struct ProgramHeader {
   int inflight;                    // weight stages issued-but-not-landed per CTA (0 = whole ring)
   unsigned int spin_ns;            // back-off of the role warps between barrier polls
   int ns, stage_bytes;             // ring geometry: 6 x 20480 (stream-K programs) or 4 x 32768 (programs with slab GEMMs)
+  int attn_pf;                     // L2 prefetch distance of the KV producer, in 8 KB granules per team (attn_ring.cuh)
   int debug;                       // ablation switches for tools/bench_slab_phases.py (results are garbage): 1 = no activation
                                    // loads, 2 = no weight loads, 4 = no MMAs, 8 = workers back off while the GEMM streams
 };

@@ -89,16 +89,10 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
 #define CLK(i)
 #endif
 
-// Tokens per thread of an epilogue item (item = 2 * EPI_TPT token rows).  4 -> groups of 8 rows: 30 tree tokens are 4
-// groups, and the gate|up epilogue of a 7B layer has 172 x 4 = 688 items for 592 teams (two rounds on 96 teams).
-// -DVS_EPI_TPT=5 -> groups of 10 rows, 3 groups, 516 items, one round (untested alternative for the next A/B; the default
-// build is bit-for-bit the validated one).
-#ifndef VS_EPI_TPT
-#define VS_EPI_TPT 4
-#endif
-constexpr int EPI_TPT = VS_EPI_TPT;     // tokens per thread
+// Tokens per thread of an epilogue item (item = 2 * EPI_TPT token rows): groups of 8 rows -- 30 tree tokens are 4 groups,
+// and the gate|up epilogue of a 7B layer has 172 x 4 = 688 items for 592 teams (two rounds on 96 teams).
+constexpr int EPI_TPT = 4;              // tokens per thread
 constexpr int EPI_TPI = 2 * EPI_TPT;    // tokens per item
-static_assert(EPI_TPT >= 4 && EPI_TPT <= 8 && (VS_TOK + EPI_TPI - 1) / EPI_TPI <= 4, "1..4 token groups per tile");
 constexpr int EPI_BATCH = 4;   // contributors whose partial tiles are loaded together (32 loads in flight per thread)
 
 // q = k / d for k * d < 2^32, with magic = floor(2^32 / d) + 1 precomputed on the host (d == 1: magic == 0 -> q = k)
@@ -183,20 +177,11 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
 #pragma unroll
       for (int c = 0; c < EPI_BATCH; ++c) {
         const int ci = min(c0 + c, n_c - 1);                                   // clamped: always a valid tile
-#if VS_EPI_TPT == 4
         const float* base = partials + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS + ts * PG_BM + col;
 #pragma unroll
         for (int i = 0; i < EPI_TPT; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + i * PG_BM + 64 * j);   // rows >= T hold stale finite data
-#else
-        // the last group may reach past the 32 rows of a partial tile: clamp the row
-        const float* base = partials + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS + col;
-#pragma unroll
-        for (int i = 0; i < EPI_TPT; ++i)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + min(ts + i, VS_TOK - 1) * PG_BM + 64 * j);
-#endif
       }
 #pragma unroll
       for (int c = 0; c < EPI_BATCH; ++c) {

@@ -17,6 +17,7 @@ an NCCL group (`TargetEngine.enable_tensor_parallel_prefill`)."""
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -194,9 +195,20 @@ def prefill_layers_native(engine, x: torch.Tensor, local: Sequence[Dict[str, tor
     part = torch.empty(Lq, H, dtype=x.dtype, device=x.device)
     eager = 0 if cfg.attn_impl == "sdpa" else 1
     kvs = engine.kv_max * 128
+    # VS_TP_TIMING=1: CUDA-event time per kind of step, summed over the layers -> engine._tp_timing (ms); diagnostics only
+    timing = os.environ.get("VS_TP_TIMING") == "1"
+    marks: List = []
+
+    def mark(name):
+        if timing:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+    mark("start")
     for li, t in enumerate(local):
         k_rows, v_rows = engine.kv[2 * li, 0, k0:k1], engine.kv[2 * li + 1, 0, k0:k1]      # local kv heads of the slab
         L.check(lib.vs_rmsnorm(L.ptr(h), H, L.ptr(t["ln_in"]), L.ptr(sc.x), H, Lq, H, cfg.eps, st), "vs_rmsnorm")
+        mark("rmsnorm")
         a = L.LinearArgs()
         a.X, a.ldx, a.W, a.ldw, a.bias = L.ptr(sc.x), H, L.ptr(t["w_qkv"]), H, L.ptr(t["b_qkv"])
         a.T, a.N, a.K = Lq, (nh_l + 2 * nkv_l) * D, H
@@ -210,6 +222,7 @@ def prefill_layers_native(engine, x: torch.Tensor, local: Sequence[Dict[str, tor
         a.Kout, a.Vout, a.kv_head_stride = L.ptr(k_rows), L.ptr(v_rows), kvs
         a.kv_row_base, a.kv_row_off = None, past
         L.check(lib.vs_linear(C.byref(a), st), "tp q|k|v")
+        mark("qkv_gemm")
         at = L.AttnArgs()
         at.Q, at.q_head_stride, at.K, at.V, at.kv_head_stride = L.ptr(sc.q), sc.max_rows * D, L.ptr(k_rows), L.ptr(v_rows), kvs
         at.n_heads, at.n_kv_heads, at.Tq = nh_l, nkv_l, Lq
@@ -219,16 +232,25 @@ def prefill_layers_native(engine, x: torch.Tensor, local: Sequence[Dict[str, tor
         at.opart, at.pv_splits, at.counters = L.ptr(sc.opart), sc.pv_splits, L.ptr(sc.attn_counters)
         at.O, at.ldo = L.ptr(sc.attn), nh_l * D
         L.check(lib.vs_attention(C.byref(at), st), "tp attention")
+        mark("attention")
         run_linear(lib, sc, sc.attn, nh_l * D, t["w_o"], None, Lq, H, nh_l * D, part, H)
+        mark("o_gemm")
         if world > 1:
             dist.all_reduce(part, group=group)
+        mark("all_reduce")
         h[:Lq] += part
+        mark("residual_add")
         L.check(lib.vs_rmsnorm(L.ptr(h), H, L.ptr(t["ln_post"]), L.ptr(sc.x), H, Lq, H, cfg.eps, st), "vs_rmsnorm")
+        mark("rmsnorm")
         run_linear(lib, sc, sc.x, H, t["w_gateup"], None, Lq, 2 * I_l, H, sc.act, I_l, epi=L.EPI_SWIGLU)
+        mark("gateup_gemm")
         run_linear(lib, sc, sc.act, I_l, t["w_down"], None, Lq, H, I_l, part, H)
+        mark("down_gemm")
         if world > 1:
             dist.all_reduce(part, group=group)
+        mark("all_reduce")
         h[:Lq] += part
+        mark("residual_add")
     if world > 1:
         n_layers = len(local)
         mine = engine.kv[:2 * n_layers, 0, k0:k1, past:S].contiguous()
@@ -238,6 +260,13 @@ def prefill_layers_native(engine, x: torch.Tensor, local: Sequence[Dict[str, tor
             a0, b0 = shard_bounds(kv_heads, r, world)
             if r != rank:
                 engine.kv[:2 * n_layers, 0, a0:b0, past:S] = p_
+    mark("kv_all_gather")
+    if timing:
+        torch.cuda.synchronize()
+        acc: Dict[str, float] = {}
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1)
+        engine._tp_timing = {k: round(v, 3) for k, v in acc.items()}
     return h[:Lq]
 
 
