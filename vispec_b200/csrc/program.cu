@@ -813,7 +813,8 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
   e.Y = a.Y; e.ldy = a.ldy; e.R = a.R; e.ldr = a.ldr;
   e.ssq = ssq;
   if (ssq == PROG_WS_SSQ) {
-    if ((size_t)g.n_tiles * VS_TOK > pg->ssq_floats) pg->ssq_floats = (size_t)g.n_tiles * VS_TOK;
+    // [n_tiles][32] floats + the same entries as tagged 8-byte words for a folded-in RMSNorm (program_dev.cuh)
+    if ((size_t)3 * g.n_tiles * VS_TOK > pg->ssq_floats) pg->ssq_floats = (size_t)3 * g.n_tiles * VS_TOK;
     pg->last_ssq_rows = g.n_tiles;
   }
   e.n_q_tiles = a.n_q_tiles; e.n_k_tiles = a.n_k_tiles; e.rope = a.rope;
@@ -1222,6 +1223,7 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
   for (size_t i = 0; i < pg->phases.size(); ++i) {
     Phase ph = pg->phases[i];
     ph.bars_before = bars;
+    ph.idx = (int)i;
     if (ph.type == PH_ATTN_FUSED) {
       ph.kv_two_loads = pg->kv_two_loads;
       ph.pf_bars = (ph.attn.prefix_stable && pg->attn_prefetch) ? scratch_free_bars : bars;

@@ -264,34 +264,43 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
           if (lane == 0) red[warp * EPI_TPT + i] = q;
         }
       }
+      // A folded-in RMSNorm exchanges the sums of squares as tagged 8-byte words (value + (launch, phase) tag in one
+      // single-copy-atomic store, behind the float entries): the readers spin on exactly the words they need -- one L2 round
+      // trip instead of store -> barrier -> release-increment -> spin -> barrier -> load
+      const int n_tiles = ph.n_tiles;
+      unsigned long long* ssq_ll = reinterpret_cast<unsigned long long*>(ssq + (long)n_tiles * VS_TOK);
+      const unsigned int ll_tag = ((epoch + 1u) << 16) | ((unsigned int)ph.idx & 0xffffu);
       if (ssq) {
         sync();
         if (tt < EPI_TPI) {                                            // token tt of the group: warps 2*h, 2*h+1 hold its half
           const int h = tt / EPI_TPT, i = tt % EPI_TPT;
           const int t = grp * EPI_TPI + tt;
-          if (t < T) ssq[tile * VS_TOK + t] = red[(2 * h) * EPI_TPT + i] + red[(2 * h + 1) * EPI_TPT + i];
+          if (t < T) {
+            const float q = red[(2 * h) * EPI_TPT + i] + red[(2 * h + 1) * EPI_TPT + i];
+            ssq[tile * VS_TOK + t] = q;
+            if (nw) {
+              const unsigned long long w = ((unsigned long long)ll_tag << 32) | __float_as_uint(q);
+              asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(ssq_ll + tile * VS_TOK + t), "l"(w) : "memory");
+            }
+          }
         }
       }
       if (nw) {
-        // LlamaRMSNorm of the finished rows (same arithmetic and summation order as norm_phase): publish this tile's
-        // sums of squares, wait until every tile of the token group has arrived, normalise the values still in registers
-        sync();
-        if (tt == 0) {
-          unsigned int* cnt = ph.norm_cnt + grp;
-          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
-          const unsigned int want = (epoch + 1u) * (unsigned int)ph.n_tiles;
-          while (ld_relaxed_u32(cnt) < want) {
-          }
-        }
-        sync();
-        const int n_tiles = ph.n_tiles;
+        // LlamaRMSNorm of the finished rows (same arithmetic and summation order as norm_phase): wait for the sums of
+        // squares of every tile of the token group, normalise the values still in registers
 #pragma unroll
         for (int q = 0; q < (EPI_TPI + 3) / 4; ++q) {                  // warp w: tokens 2w, 2w+1 of the group (3w.. for 10)
           const int tg = warp * ((EPI_TPI + 3) / 4) + q;
           const int t = grp * EPI_TPI + tg;
           float ss = 0.f;
           if (tg < EPI_TPI && t < T)
-            for (int i = lane; i < n_tiles; i += 32) ss += __ldcg(ssq + i * VS_TOK + t);
+            for (int i = lane; i < n_tiles; i += 32) {
+              unsigned long long w;
+              do {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(ssq_ll + i * VS_TOK + t) : "memory");
+              } while ((unsigned int)(w >> 32) != ll_tag);
+              ss += __uint_as_float((unsigned int)w);
+            }
           ss = warp_sum(ss);
           if (lane == 0 && tg < EPI_TPI) red[32 + tg] = 1.0f / sqrtf(ss / (float)ph.H + ph.eps);
         }
