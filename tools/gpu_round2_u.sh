@@ -11,3 +11,6 @@ print(round(d["value"],1), (d.get("roofline") or {}).get("frac"), d["e2e"]["valu
 PY
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_program.py -q -x -k "attention_tma_staged and (4-2-61 or 4-4-33) and opts2 or folded and 512-4" > gpurun_out/san_r2u_racecheck.log 2>&1; echo racecheck_rc=$?
 tail -n 3 gpurun_out/san_r2u_racecheck.log
+export VS_LIB_PATH=$PWD/vispec_b200/lib/variants/clk.so
+for sh in o down; do echo "== SHAPE=$sh"; SHAPE=$sh timeout 120 python tools/clk_epi.py 2>&1 | tail -n 16; done > gpurun_out/clk_epi_r2u.txt 2>&1
+cat gpurun_out/clk_epi_r2u.txt

@@ -536,6 +536,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
               if (ph.no_barrier) {       // publish this contribution: the tile's epilogue items poll the counter
                 named_bar_sync(1, PG_WORKERS);
                 if (wtid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ph.tile_cnt + tile) : "memory");
+#ifdef VS_PROGRAM_CLK
+                if (b == 0 && wtid == 0) g_clk[48 + min(tile - tile0, 3)] = clock64();     // CTA 0 published its tile
+#endif
               }
             }
           }
@@ -1223,7 +1226,7 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
   for (size_t i = 0; i < pg->phases.size(); ++i) {
     Phase ph = pg->phases[i];
     ph.bars_before = bars;
-    ph.idx = (int)i;
+    ph.phase_idx = (int)i;
     if (ph.type == PH_ATTN_FUSED) {
       ph.kv_two_loads = pg->kv_two_loads;
       ph.pf_bars = (ph.attn.prefix_stable && pg->attn_prefetch) ? scratch_free_bars : bars;

@@ -45,7 +45,7 @@ struct Phase {
   int n_tiles, nk, N;         // ceil(N/128) weight-row tiles, K/64 chunks
   int maxseg;                 // partial tiles per CTA
   int bars_before;            // grid barriers executed before this phase (every phase; set at commit)
-  int idx;                    // position of the phase in the program (set at commit): part of the tag of tagged exchanges
+  int phase_idx;              // position of the phase in the program (set at commit): part of the tag of tagged exchanges
   int no_barrier;             // PH_GEMM: the epilogue phase that follows waits on per-tile counters instead of a grid barrier
   unsigned int* tile_cnt;     // PH_GEMM / PH_EPI: [n_tiles] arrivals of contributors, monotonic across launches (workspace)
   int range_off;              // offset into the program's int tables: per-CTA chunk ranges [lo, hi)

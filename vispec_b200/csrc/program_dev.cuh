@@ -156,6 +156,23 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
         csraw[2][i] = ph.cos[(long)pos[i] * 128 + 64 + col]; csraw[3][i] = ph.sin[(long)pos[i] * 128 + 64 + col];
       }
     }
+    // bias and (folded RMSNorm) weight of this thread's two columns, and the KV append row: with the other operands, not
+    // behind the reduction (each is an L2 round trip of its own)
+    float bias_e[2] = {0.f, 0.f}, nwf[2] = {0.f, 0.f};
+    {
+      const bf16* bp = ph.bias;
+      const bf16* nwp = (!heads && epi != EPI_SWIGLU) ? ph.w : nullptr;
+      unsigned short braw[2] = {0, 0}, nraw[2] = {0, 0};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = min(tile * PG_BM + col + 64 * j, N - 1);
+        if (bp) braw[j] = __ldg(reinterpret_cast<const unsigned short*>(bp + n));
+        if (nwp) nraw[j] = __ldg(reinterpret_cast<const unsigned short*>(nwp + n));
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { bias_e[j] = bf_bits(braw[j]); nwf[j] = bf_bits(nraw[j]); }
+    }
+    const int row_base_e = heads ? (ph.kv_row_base ? __ldcg(ph.kv_row_base) : 0) + ph.kv_row_off : 0;
     CLK(2);
     // ---- fused GEMM+epilogue: no grid barrier separated us from the GEMM phase; wait until every contributor of this
     // tile has published its partial tile (monotonic counter: n_c arrivals per launch)
@@ -167,6 +184,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       }
       sync();
     }
+    CLK(7);
     // ---- reduction over the contributors in k order; the loads of EPI_BATCH contributors are in flight together
     float a[2][EPI_TPT];
 #pragma unroll
@@ -210,9 +228,8 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
         }
     } else if (heads) {
       // one 128-row tile == one head of q | k | v; optional RoPE; q -> Qout, k/v -> KV rows in place
-      const int row_base = (ph.kv_row_base ? __ldcg(ph.kv_row_base) : 0) + ph.kv_row_off;
-      const float b1 = ph.bias ? bf2f(ph.bias[tile * PG_BM + col]) : 0.f;
-      const float b2 = ph.bias ? bf2f(ph.bias[tile * PG_BM + 64 + col]) : 0.f;
+      const int row_base = row_base_e;
+      const float b1 = bias_e[0], b2 = bias_e[1];
       const int head = is_q ? tile : (is_k ? tile - ph.n_q_tiles : tile - ph.n_q_tiles - ph.n_k_tiles);
       bf16* dst = is_q ? ph.Qout + (long)head * ph.q_head_stride
                        : (is_k ? ph.Kout : ph.Vout) + (long)head * ph.kv_head_stride + (long)row_base * 128;
@@ -230,27 +247,21 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
         }
     } else {
       // STORE / RESID (+ per-tile sums of squares of the new rows for the RMSNorm that follows)
-      float bias[2];
       bool ok[2];
       bf16* Y = ph.Y;
       const long ldy = ph.ldy;
       float* ssq = ph.ssq;
       const bf16* nw = ph.w;                                           // folded-in RMSNorm (prog_add_norm) or null
-      float nwf[2], yv[2][EPI_TPT];
+      float yv[2][EPI_TPT];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int n = tile * PG_BM + col + 64 * j;
-        ok[j] = n < N;
-        bias[j] = ph.bias ? bf2f(ph.bias[min(n, N - 1)]) : 0.f;
-        nwf[j] = nw ? bf2f(nw[min(n, N - 1)]) : 0.f;
-      }
+      for (int j = 0; j < 2; ++j) ok[j] = tile * PG_BM + col + 64 * j < N;
       if (ssq) sync();                                                 // previous item's readers of `red` are done
 #pragma unroll
       for (int i = 0; i < EPI_TPT; ++i) {
         float q = 0.f;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          float v = a[j][i] + bias[j];
+          float v = a[j][i] + bias_e[j];
           if (resid) v = bf_bits(rraw[j][i]) + rbf(v);                 // Linear output rounds to bf16, then the add rounds again
           const bf16 y = f2bf(v);
           yv[j][i] = bf2f(y);
@@ -269,7 +280,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       // trip instead of store -> barrier -> release-increment -> spin -> barrier -> load
       const int n_tiles = ph.n_tiles;
       unsigned long long* ssq_ll = reinterpret_cast<unsigned long long*>(ssq + (long)n_tiles * VS_TOK);
-      const unsigned int ll_tag = ((epoch + 1u) << 16) | ((unsigned int)ph.idx & 0xffffu);
+      const unsigned int ll_tag = ((epoch + 1u) << 16) | ((unsigned int)ph.phase_idx & 0xffffu);
       if (ssq) {
         sync();
         if (tt < EPI_TPI) {                                            // token tt of the group: warps 2*h, 2*h+1 hold its half
@@ -285,6 +296,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
           }
         }
       }
+      CLK(8);
       if (nw) {
         // LlamaRMSNorm of the finished rows (same arithmetic and summation order as norm_phase): wait for the sums of
         // squares of every tile of the token group, normalise the values still in registers
@@ -305,6 +317,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
           if (lane == 0 && tg < EPI_TPI) red[32 + tg] = 1.0f / sqrtf(ss / (float)ph.H + ph.eps);
         }
         sync();
+        CLK(9);
         bf16* X = ph.dst;
         const long ldd = ph.ldd;
 #pragma unroll
