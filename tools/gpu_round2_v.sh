@@ -7,7 +7,7 @@ timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-base
 python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/bench_r2v.json").read().strip().splitlines()[-1])
-print(round(d["value"],1), (d.get("roofline") or {}).get("frac"), d["e2e"]["value"], {k:v["us"] for k,v in (d.get("phases_us_per_cycle") or {}).items()}, "qwen", d["qwen2_5_vl_7b"]["value"])
+print(round(d["value"],1), (d.get("roofline") or {}).get("frac"), d["e2e"]["value"], {k:v["us"] for k,v in (d.get("phases_us_per_cycle") or {}).items()})
 PY
 export VS_LIB_PATH=$PWD/vispec_b200/lib/variants/clk.so
 for sh in o; do echo "== SHAPE=$sh"; SHAPE=$sh timeout 120 python tools/clk_epi.py 2>&1 | tail -n 14; done > gpurun_out/clk_epi_r2v.txt 2>&1

@@ -93,13 +93,41 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
 // and the gate|up epilogue of a 7B layer has 172 x 4 = 688 items for 592 teams (two rounds on 96 teams).
 constexpr int EPI_TPT = 4;              // tokens per thread
 constexpr int EPI_TPI = 2 * EPI_TPT;    // tokens per item
-constexpr int EPI_BATCH = 4;   // contributors whose partial tiles are loaded together (32 loads in flight per thread)
+constexpr int EPI_BATCH = 4;        // contributors whose partial tiles are loaded together (32 loads in flight per thread)
+constexpr int EPI_BATCH_WIDE = 6;   // ... for tiles with more than EPI_BATCH contributors (48 loads in flight)
 
 // q = k / d for k * d < 2^32, with magic = floor(2^32 / d) + 1 precomputed on the host (d == 1: magic == 0 -> q = k)
 __device__ __forceinline__ int fast_div(int k, unsigned int magic) {
   return magic ? (int)__umulhi((unsigned int)k, magic) : k;
 }
 __device__ __forceinline__ float bf_bits(unsigned short u) { return __uint_as_float(((unsigned int)u) << 16); }
+
+// a[j][i] += sum over the contributors b0 .. b0 + n_c - 1 (k order) of their partial tile's element (token i, column j * 64):
+// `pbase` = partials + this thread's (first token, column) offset; B loads per element in flight
+template <int B>
+__device__ __forceinline__ void epi_reduce(float (&a)[2][EPI_TPT], const float* pbase, int b0, int n_c, int seg0, int maxseg) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < n_c; c0 += B) {
+    float v[B][2][EPI_TPT];
+#pragma unroll
+    for (int c = 0; c < B; ++c) {
+      const int ci = min(c0 + c, n_c - 1);                                   // clamped: always a valid tile
+      const float* base = pbase + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS;
+#pragma unroll
+      for (int i = 0; i < EPI_TPT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + i * PG_BM + 64 * j);   // rows >= T hold stale finite data
+    }
+#pragma unroll
+    for (int c = 0; c < B; ++c) {
+#pragma unroll
+      for (int i = 0; i < EPI_TPT; ++i) {
+        a[0][i] += c0 + c < n_c ? v[c][0][i] : 0.f;
+        a[1][i] += c0 + c < n_c ? v[c][1][i] : 0.f;
+      }
+    }
+  }
+}
 
 __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
                                        TeamSync sync) {
@@ -185,31 +213,15 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       sync();
     }
     CLK(7);
-    // ---- reduction over the contributors in k order; the loads of EPI_BATCH contributors are in flight together
+    // ---- reduction over the contributors in k order; the loads of B contributors are in flight together.  The square
+    // projections (o_proj, down_proj: 5-6 contributors per tile on 148 CTAs) take the wider batch: one L2 round trip
+    // instead of two.  Same order of additions either way.
     float a[2][EPI_TPT];
 #pragma unroll
     for (int i = 0; i < EPI_TPT; ++i) { a[0][i] = 0.f; a[1][i] = 0.f; }
-#pragma unroll 1
-    for (int c0 = 0; c0 < n_c; c0 += EPI_BATCH) {
-      float v[EPI_BATCH][2][EPI_TPT];
-#pragma unroll
-      for (int c = 0; c < EPI_BATCH; ++c) {
-        const int ci = min(c0 + c, n_c - 1);                                   // clamped: always a valid tile
-        const float* base = partials + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS + ts * PG_BM + col;
-#pragma unroll
-        for (int i = 0; i < EPI_TPT; ++i)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + i * PG_BM + 64 * j);   // rows >= T hold stale finite data
-      }
-#pragma unroll
-      for (int c = 0; c < EPI_BATCH; ++c) {
-#pragma unroll
-        for (int i = 0; i < EPI_TPT; ++i) {
-          a[0][i] += c0 + c < n_c ? v[c][0][i] : 0.f;
-          a[1][i] += c0 + c < n_c ? v[c][1][i] : 0.f;
-        }
-      }
-    }
+    const float* const pbase = partials + ts * PG_BM + col;
+    if (n_c > EPI_BATCH) epi_reduce<EPI_BATCH_WIDE>(a, pbase, b0, n_c, seg0, maxseg);
+    else epi_reduce<EPI_BATCH>(a, pbase, b0, n_c, seg0, maxseg);
 
     CLK(3);
 #ifdef VS_PROGRAM_CLK
