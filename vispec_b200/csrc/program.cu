@@ -507,11 +507,19 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       for (int i = wtid; i < PHASE_WORDS; i += PG_WORKERS) dst[i] = src[i];
       named_bar_sync(1, PG_WORKERS);
     }
-    for (int p = 0; p < hdr.n_phases; ++p) {
-      const Phase& ph = *reinterpret_cast<const Phase*>(phbuf + (p & 1) * PHASE_SLOT);
+    int cur = 0;                                    // slot of the staged descriptor of phase p
+    for (int p = 0; p < hdr.n_phases;) {
+      const Phase& ph = *reinterpret_cast<const Phase*>(phbuf + cur * PHASE_SLOT);
+      // A GEMM whose epilogue waits on per-tile counters (no grid barrier in between) runs together with that epilogue as
+      // ONE body: its descriptor carries the epilogue's fields as well (vs_program_commit), the PH_EPI descriptor that
+      // follows is skipped: no descriptor switch, no CTA-wide barrier and no dispatch between the two.  (Loading the
+      // epilogue's operands early, while the GEMM streams, was measured: 206 -> 194 tok/s -- the extra loads at the start of
+      // the GEMM phase delay the first accumulator drain.)
+      const bool pair = ph.type == PH_GEMM && ph.no_barrier && p + 1 < hdr.n_phases;
+      const int step = pair ? 2 : 1;
       unsigned int nxt0 = 0;
-      const bool has_next = p + 1 < hdr.n_phases;
-      if (has_next && wtid < PHASE_WORDS) nxt0 = reinterpret_cast<const unsigned int*>(hdr.phases + p + 1)[wtid];
+      const bool has_next = p + step < hdr.n_phases;
+      if (has_next && wtid < PHASE_WORDS) nxt0 = reinterpret_cast<const unsigned int*>(hdr.phases + p + step)[wtid];
       switch (ph.type) {
         case PH_GEMM: {
           const int2 rg = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
@@ -542,6 +550,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
               }
             }
           }
+          if (pair) {
+            if (hdr.trace_cta && wtid == 0) hdr.trace_cta[(long)p * G + b] = global_timer();
+            if (hdr.trace && b == 0 && wtid == 0) hdr.trace[p] = global_timer();
+#ifdef VS_PROGRAM_CLK
+            if (b == 0 && wtid == 0) g_clk[32 + (p & 15)] = clock64();      // "end" of the GEMM phase: this CTA's tiles are drained
+#endif
+            epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
+          }
         } break;
         case PH_GEMM2:
           slab_epilogue(ph, epoch, b, G, wtid, tmem_base, acc, acc_par, tfull, tempty, *reinterpret_cast<SlabRed*>(team_base),
@@ -564,17 +580,20 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         } break;
         default: break;
       }
+      const int pl = p + step - 1;                  // the last phase this body executed
       if (has_next && wtid < PHASE_WORDS)
-        reinterpret_cast<unsigned int*>(phbuf + ((p + 1) & 1) * PHASE_SLOT)[wtid] = nxt0;
-      if (hdr.trace_cta && wtid == 0) hdr.trace_cta[(long)p * G + b] = global_timer();   // this CTA's items are done
-      if (p + 1 < hdr.n_phases) {
-        if (ph.type == PH_GEMM && ph.no_barrier) named_bar_sync(1, PG_WORKERS);   // only the staged descriptor needs it
+        reinterpret_cast<unsigned int*>(phbuf + (cur ^ 1) * PHASE_SLOT)[wtid] = nxt0;
+      if (hdr.trace_cta && wtid == 0) hdr.trace_cta[(long)pl * G + b] = global_timer();   // this CTA's items are done
+      if (has_next) {
+        if (!pair && ph.type == PH_GEMM && ph.no_barrier) named_bar_sync(1, PG_WORKERS);   // only the staged descriptor needs it
         else grid_barrier(hdr.counters, (unsigned int)(ph.bars_before + 1) * (unsigned int)G, wtid);
       }
-      if (hdr.trace && b == 0 && wtid == 0) hdr.trace[p] = global_timer();
+      if (hdr.trace && b == 0 && wtid == 0) hdr.trace[pl] = global_timer();
 #ifdef VS_PROGRAM_CLK
-      if (b == 0 && wtid == 0) g_clk[32 + (p & 15)] = clock64();        // end of the barrier of phase p
+      if (b == 0 && wtid == 0) g_clk[32 + (pl & 15)] = clock64();        // end of the barrier of phase pl
 #endif
+      p += step;
+      cur ^= 1;
     }
     // leave the counters at zero for the next launch: the last CTA to get here resets them (every CTA has passed its
     // last barrier wait before it increments the exit counter)
@@ -1245,6 +1264,18 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
     if (ph.keys == PROG_WS_KEYS) ph.keys = reinterpret_cast<unsigned long long*>(pg->ws + pg->off_keys);
     if (ph.lstats == PROG_WS_LSTATS) ph.lstats = reinterpret_cast<float2*>(pg->ws + pg->off_lstats);
     memcpy(host.data() + pg->off_phases + i * sizeof(Phase), &ph, sizeof(Phase));
+  }
+  // A GEMM that is fused with its epilogue (no grid barrier in between) is executed together with it from ONE descriptor:
+  // the epilogue's (patched) descriptor was copied from the GEMM's when both were built, so it holds every GEMM field too.
+  {
+    Phase* hp = reinterpret_cast<Phase*>(host.data() + pg->off_phases);
+    for (size_t i = 0; i + 1 < pg->phases.size(); ++i)
+      if (hp[i].type == PH_GEMM && hp[i].no_barrier && hp[i + 1].type == PH_EPI) {
+        Phase m = hp[i + 1];
+        m.type = PH_GEMM;
+        m.bars_before = hp[i].bars_before;
+        hp[i] = m;
+      }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cudaMemcpyAsync(pg->ws, host.data(), host.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||

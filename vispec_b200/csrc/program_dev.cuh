@@ -129,6 +129,65 @@ __device__ __forceinline__ void epi_reduce(float (&a)[2][EPI_TPT], const float* 
   }
 }
 
+// Everything an epilogue item needs besides the partial tiles; loaded up front, before the item waits for its contributors.
+struct EpiOps {
+  unsigned short rraw[2][EPI_TPT];       // residual rows (RESID)
+  bf16 csraw[4][EPI_TPT];                // cos / sin of the two column halves (HEADS + RoPE)
+  float bias_e[2], nwf[2];               // bias and folded-RMSNorm weight of the thread's two columns
+  int row_base;                          // KV append row (HEADS)
+};
+__device__ __forceinline__ int epi_tile_of(int item, int groups) {
+  return groups == 1 ? item : (groups == 2 ? item >> 1 : (groups == 4 ? item >> 2 : item / 3));
+}
+// Indices are clamped instead of predicated so that the loads are plain back-to-back instructions.
+__device__ __forceinline__ void epi_load_ops(const Phase& ph, int item, int tt, EpiOps& o) {
+  const int T = ph.T, N = ph.N, epi = ph.epi;
+  const int groups = (T + EPI_TPI - 1) / EPI_TPI;
+  const int col = tt & 63, half = tt >> 6;
+  const int tile = epi_tile_of(item, groups);
+  const int grp = item - tile * groups;
+  const int ts = grp * EPI_TPI + half * EPI_TPT;     // first token of this thread
+  const bool resid = epi == EPI_RESID, heads = epi == EPI_HEADS;
+  const bool is_q = tile < ph.n_q_tiles;
+  const bool is_k = !is_q && tile < ph.n_q_tiles + ph.n_k_tiles;
+  const bool rope = heads && ph.rope && (is_q || is_k);
+  if (resid) {
+    const bf16* R = ph.R;
+    const long ldr = ph.ldr;
+#pragma unroll
+    for (int i = 0; i < EPI_TPT; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        o.rraw[j][i] = __ldcg(reinterpret_cast<const unsigned short*>(R + (long)min(ts + i, T - 1) * ldr +
+                                                                      min(tile * PG_BM + col + 64 * j, N - 1)));
+  }
+  if (rope) {
+    int pos[EPI_TPT];
+#pragma unroll
+    for (int i = 0; i < EPI_TPT; ++i) pos[i] = __ldcg(ph.pos_ids + min(ts + i, T - 1));
+#pragma unroll
+    for (int i = 0; i < EPI_TPT; ++i) {
+      o.csraw[0][i] = ph.cos[(long)pos[i] * 128 + col];      o.csraw[1][i] = ph.sin[(long)pos[i] * 128 + col];
+      o.csraw[2][i] = ph.cos[(long)pos[i] * 128 + 64 + col]; o.csraw[3][i] = ph.sin[(long)pos[i] * 128 + 64 + col];
+    }
+  }
+  // bias and (folded RMSNorm) weight of this thread's two columns, and the KV append row: with the other operands, not
+  // behind the reduction (each is an L2 round trip of its own)
+  {
+    const bf16* bp = ph.bias;
+    const bf16* nwp = (!heads && epi != EPI_SWIGLU) ? ph.w : nullptr;
+    unsigned short braw[2] = {0, 0}, nraw[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = min(tile * PG_BM + col + 64 * j, N - 1);
+      if (bp) braw[j] = __ldg(reinterpret_cast<const unsigned short*>(bp + n));
+      if (nwp) nraw[j] = __ldg(reinterpret_cast<const unsigned short*>(nwp + n));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { o.bias_e[j] = bf_bits(braw[j]); o.nwf[j] = bf_bits(nraw[j]); }
+  }
+  o.row_base = heads ? (ph.kv_row_base ? __ldcg(ph.kv_row_base) : 0) + ph.kv_row_off : 0;
+}
 __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
                                        TeamSync sync) {
   // everything an item needs from the descriptor, once (the descriptor lives in shared memory)
@@ -147,7 +206,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
   CLK(0);
   for (int item = gteam; item < n_items; item += n_teams) {
     CLK(1);
-    const int tile = groups == 1 ? item : (groups == 2 ? item >> 1 : (groups == 4 ? item >> 2 : item / 3));
+    const int tile = epi_tile_of(item, groups);
     const int grp = item - tile * groups;
     const int ts = grp * EPI_TPI + half * EPI_TPT;     // first token of this thread
     // contributors of the tile: consecutive CTAs b0 .. b0+n-1; closed form of the balanced partition of program.cu
@@ -157,50 +216,17 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
     const int n_c = b1 - b0 + 1;
     const int seg0 = tile - fast_div(b0 * per_lo + min(b0, rem), m_nk);
 
-    // ---- all operand loads that do not depend on the reduction, issued before anything is consumed.  Indices are
-    // clamped instead of predicated so that the loads are plain back-to-back instructions.
-    unsigned short rraw[2][EPI_TPT];
-    bf16 csraw[4][EPI_TPT];
+    // ---- all operand loads that do not depend on the reduction, issued before anything is consumed
+    EpiOps ops;
+    epi_load_ops(ph, item, tt, ops);
     const bool is_q = tile < ph.n_q_tiles;
     const bool is_k = !is_q && tile < ph.n_q_tiles + ph.n_k_tiles;
     const bool rope = heads && ph.rope && (is_q || is_k);
-    if (resid) {
-      const bf16* R = ph.R;
-      const long ldr = ph.ldr;
-#pragma unroll
-      for (int i = 0; i < EPI_TPT; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          rraw[j][i] = __ldcg(reinterpret_cast<const unsigned short*>(R + (long)min(ts + i, T - 1) * ldr +
-                                                                      min(tile * PG_BM + col + 64 * j, N - 1)));
-    }
-    if (rope) {
-      int pos[EPI_TPT];
-#pragma unroll
-      for (int i = 0; i < EPI_TPT; ++i) pos[i] = __ldcg(ph.pos_ids + min(ts + i, T - 1));
-#pragma unroll
-      for (int i = 0; i < EPI_TPT; ++i) {
-        csraw[0][i] = ph.cos[(long)pos[i] * 128 + col];      csraw[1][i] = ph.sin[(long)pos[i] * 128 + col];
-        csraw[2][i] = ph.cos[(long)pos[i] * 128 + 64 + col]; csraw[3][i] = ph.sin[(long)pos[i] * 128 + 64 + col];
-      }
-    }
-    // bias and (folded RMSNorm) weight of this thread's two columns, and the KV append row: with the other operands, not
-    // behind the reduction (each is an L2 round trip of its own)
-    float bias_e[2] = {0.f, 0.f}, nwf[2] = {0.f, 0.f};
-    {
-      const bf16* bp = ph.bias;
-      const bf16* nwp = (!heads && epi != EPI_SWIGLU) ? ph.w : nullptr;
-      unsigned short braw[2] = {0, 0}, nraw[2] = {0, 0};
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int n = min(tile * PG_BM + col + 64 * j, N - 1);
-        if (bp) braw[j] = __ldg(reinterpret_cast<const unsigned short*>(bp + n));
-        if (nwp) nraw[j] = __ldg(reinterpret_cast<const unsigned short*>(nwp + n));
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) { bias_e[j] = bf_bits(braw[j]); nwf[j] = bf_bits(nraw[j]); }
-    }
-    const int row_base_e = heads ? (ph.kv_row_base ? __ldcg(ph.kv_row_base) : 0) + ph.kv_row_off : 0;
+    const unsigned short (&rraw)[2][EPI_TPT] = ops.rraw;
+    const bf16 (&csraw)[4][EPI_TPT] = ops.csraw;
+    const float (&bias_e)[2] = ops.bias_e;
+    const float (&nwf)[2] = ops.nwf;
+    const int row_base_e = ops.row_base;
     CLK(2);
     // ---- fused GEMM+epilogue: no grid barrier separated us from the GEMM phase; wait until every contributor of this
     // tile has published its partial tile (monotonic counter: n_c arrivals per launch)
