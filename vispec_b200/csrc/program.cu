@@ -907,9 +907,12 @@ int prog_add_rows(vs_program* pg, const bf16* src, long lds, const int* idx, int
 // kv splits of the fused single-phase attention: every (head, split) item needs its own resident 256-thread team
 static int fused_splits(int G, int n_heads, int pv_splits_cap, int max_chunks) {
   int sp = (PG_BIG_TEAMS * G) / (n_heads > 0 ? n_heads : 1);
-  if (sp > 16) sp = 16;
+  if (sp > 8) sp = 8;     // measured: 8 splits beat 9 up to a few thousand keys (734 keys: 16.0 vs 17.1 us per layer; the
+                          // statistics of a head fit one load per lane, item -> (head, split) is a shift); 8192 keys: 58.8 vs 57.0
   if (sp > pv_splits_cap) sp = pv_splits_cap;
   if (sp > max_chunks) sp = max_chunks;
+  const char* e = getenv("VS_ATTN_SPLITS");       // A/B: fewer, longer splits per head
+  if (e && atoi(e) >= 1 && atoi(e) < sp) sp = atoi(e);
   return sp;
 }
 
