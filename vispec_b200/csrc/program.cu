@@ -556,14 +556,18 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
 #ifdef VS_PROGRAM_CLK
             if (b == 0 && wtid == 0) g_clk[32 + (p & 15)] = clock64();      // "end" of the GEMM phase: this CTA's tiles are drained
 #endif
-            epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
+            if (ph.tpi == 2 * EPI_TPI) epi_phase_wide(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
+            else epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
           }
         } break;
         case PH_GEMM2:
           slab_epilogue(ph, epoch, b, G, wtid, tmem_base, acc, acc_par, tfull, tempty, *reinterpret_cast<SlabRed*>(team_base),
                         (hdr.debug & 8) != 0);
           break;
-        case PH_EPI: epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
+        case PH_EPI:
+          if (ph.tpi == 2 * EPI_TPI) epi_phase_wide(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
+          else epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
+          break;
         case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
         case PH_ATTN_S: attn_s_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
@@ -829,7 +833,12 @@ int prog_add_linear(vs_program* pg, const GemmArgs& a, float* ssq) {
   pg->phases.push_back(g);
   Phase e = g;
   e.type = PH_EPI;
+  // token rows per epilogue item: 8; 16 where 8 would need a second round over the teams and the epilogue keeps no
+  // per-group state (SiLU*up, plain store: gate|up of a 7B layer = 172 tiles x 4 groups = 688 items on 592 teams, LM heads)
   e.tpi = EPI_TPI;
+  if ((a.epi == EPI_SWIGLU || (a.epi == EPI_STORE && !ssq)) && (long)g.n_tiles * ((a.T + EPI_TPI - 1) / EPI_TPI) > (long)PG_TEAMS * G &&
+      !getenv("VS_EPI_NARROW"))
+    e.tpi = 2 * EPI_TPI;
   e.epi = a.epi;
   e.bias = a.bias;
   e.Y = a.Y; e.ldy = a.ldy; e.R = a.R; e.ldr = a.ldr;
@@ -872,7 +881,7 @@ int prog_add_norm(vs_program* pg, const bf16* x, long ldx, const bf16* w, bf16* 
     const int G = pg->grid ? pg->grid : device_sms();
     const int groups = (T + EPI_TPI - 1) / EPI_TPI;
     if (e.type == PH_EPI && e.epi == EPI_RESID && e.ssq == ssq_in && e.Y == x && e.ldy == ldx && e.T == T && e.N == H &&
-        e.n_tiles == ssq_tiles && !e.w && e.n_tiles * groups <= PG_TEAMS * G) {
+        e.n_tiles == ssq_tiles && !e.w && e.tpi == EPI_TPI && e.n_tiles * groups <= PG_TEAMS * G) {
       e.w = w; e.dst = y; e.ldd = ldy; e.H = H; e.eps = eps;
       e.norm_cnt = reinterpret_cast<unsigned int*>(uintptr_t(pg->tile_cnt_count + 1));
       pg->tile_cnt_count += 4;

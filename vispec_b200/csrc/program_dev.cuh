@@ -104,24 +104,24 @@ __device__ __forceinline__ float bf_bits(unsigned short u) { return __uint_as_fl
 
 // a[j][i] += sum over the contributors b0 .. b0 + n_c - 1 (k order) of their partial tile's element (token i, column j * 64):
 // `pbase` = partials + this thread's (first token, column) offset; B loads per element in flight
-template <int B>
-__device__ __forceinline__ void epi_reduce(float (&a)[2][EPI_TPT], const float* pbase, int b0, int n_c, int seg0, int maxseg) {
+template <int B, int TPT>
+__device__ __forceinline__ void epi_reduce(float (&a)[2][TPT], const float* pbase, int b0, int n_c, int seg0, int maxseg) {
 #pragma unroll 1
   for (int c0 = 0; c0 < n_c; c0 += B) {
-    float v[B][2][EPI_TPT];
+    float v[B][2][TPT];
 #pragma unroll
     for (int c = 0; c < B; ++c) {
       const int ci = min(c0 + c, n_c - 1);                                   // clamped: always a valid tile
       const float* base = pbase + ((long)(b0 + ci) * maxseg + (ci == 0 ? seg0 : 0)) * TILE_FLOATS;
 #pragma unroll
-      for (int i = 0; i < EPI_TPT; ++i)
+      for (int i = 0; i < TPT; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) v[c][j][i] = __ldcg(base + i * PG_BM + 64 * j);   // rows >= T hold stale finite data
     }
 #pragma unroll
     for (int c = 0; c < B; ++c) {
 #pragma unroll
-      for (int i = 0; i < EPI_TPT; ++i) {
+      for (int i = 0; i < TPT; ++i) {
         a[0][i] += c0 + c < n_c ? v[c][0][i] : 0.f;
         a[1][i] += c0 + c < n_c ? v[c][1][i] : 0.f;
       }
@@ -130,9 +130,10 @@ __device__ __forceinline__ void epi_reduce(float (&a)[2][EPI_TPT], const float* 
 }
 
 // Everything an epilogue item needs besides the partial tiles; loaded up front, before the item waits for its contributors.
+template <int TPT>
 struct EpiOps {
-  unsigned short rraw[2][EPI_TPT];       // residual rows (RESID)
-  bf16 csraw[4][EPI_TPT];                // cos / sin of the two column halves (HEADS + RoPE)
+  unsigned short rraw[2][TPT];       // residual rows (RESID)
+  bf16 csraw[4][TPT];                // cos / sin of the two column halves (HEADS + RoPE)
   float bias_e[2], nwf[2];               // bias and folded-RMSNorm weight of the thread's two columns
   int row_base;                          // KV append row (HEADS)
 };
@@ -140,13 +141,14 @@ __device__ __forceinline__ int epi_tile_of(int item, int groups) {
   return groups == 1 ? item : (groups == 2 ? item >> 1 : (groups == 4 ? item >> 2 : item / 3));
 }
 // Indices are clamped instead of predicated so that the loads are plain back-to-back instructions.
-__device__ __forceinline__ void epi_load_ops(const Phase& ph, int item, int tt, EpiOps& o) {
+template <int TPT>
+__device__ __forceinline__ void epi_load_ops(const Phase& ph, int item, int tt, EpiOps<TPT>& o) {
   const int T = ph.T, N = ph.N, epi = ph.epi;
-  const int groups = (T + EPI_TPI - 1) / EPI_TPI;
+  const int groups = (T + (2 * TPT) - 1) / (2 * TPT);
   const int col = tt & 63, half = tt >> 6;
   const int tile = epi_tile_of(item, groups);
   const int grp = item - tile * groups;
-  const int ts = grp * EPI_TPI + half * EPI_TPT;     // first token of this thread
+  const int ts = grp * (2 * TPT) + half * TPT;     // first token of this thread
   const bool resid = epi == EPI_RESID, heads = epi == EPI_HEADS;
   const bool is_q = tile < ph.n_q_tiles;
   const bool is_k = !is_q && tile < ph.n_q_tiles + ph.n_k_tiles;
@@ -155,18 +157,18 @@ __device__ __forceinline__ void epi_load_ops(const Phase& ph, int item, int tt, 
     const bf16* R = ph.R;
     const long ldr = ph.ldr;
 #pragma unroll
-    for (int i = 0; i < EPI_TPT; ++i)
+    for (int i = 0; i < TPT; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j)
         o.rraw[j][i] = __ldcg(reinterpret_cast<const unsigned short*>(R + (long)min(ts + i, T - 1) * ldr +
                                                                       min(tile * PG_BM + col + 64 * j, N - 1)));
   }
   if (rope) {
-    int pos[EPI_TPT];
+    int pos[TPT];
 #pragma unroll
-    for (int i = 0; i < EPI_TPT; ++i) pos[i] = __ldcg(ph.pos_ids + min(ts + i, T - 1));
+    for (int i = 0; i < TPT; ++i) pos[i] = __ldcg(ph.pos_ids + min(ts + i, T - 1));
 #pragma unroll
-    for (int i = 0; i < EPI_TPT; ++i) {
+    for (int i = 0; i < TPT; ++i) {
       o.csraw[0][i] = ph.cos[(long)pos[i] * 128 + col];      o.csraw[1][i] = ph.sin[(long)pos[i] * 128 + col];
       o.csraw[2][i] = ph.cos[(long)pos[i] * 128 + 64 + col]; o.csraw[3][i] = ph.sin[(long)pos[i] * 128 + 64 + col];
     }
@@ -188,15 +190,19 @@ __device__ __forceinline__ void epi_load_ops(const Phase& ph, int item, int tt, 
   }
   o.row_base = heads ? (ph.kv_row_base ? __ldcg(ph.kv_row_base) : 0) + ph.kv_row_off : 0;
 }
-__device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
-                                       TeamSync sync) {
+// TPT tokens per thread, items of 2 * TPT token rows: 4 by default; 8 (`ph.tpi` = 16) for the epilogues whose item count
+// at 4 would not fit one round over the teams (gate|up: 172 tiles x 4 groups = 688 items on 592 teams; LM heads) -- an item
+// is a latency chain, twice the rows per thread cost far less than a second round.
+template <int TPT>
+__device__ __forceinline__ void epi_phase_t(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
+                                            TeamSync sync) {
   // everything an item needs from the descriptor, once (the descriptor lives in shared memory)
   const int T = ph.T, N = ph.N, nk = ph.nk, maxseg = ph.maxseg, epi = ph.epi;
   const int per_lo = ph.per_lo, rem = ph.rem;
   const unsigned int m_hi = ph.magic_per_hi, m_lo = ph.magic_per_lo, m_nk = ph.magic_nk;
   const float* partials = ph.partials;
   const unsigned int* tile_cnt = ph.tile_cnt;
-  const int groups = (T + EPI_TPI - 1) / EPI_TPI;      // 1..4
+  const int groups = (T + (2 * TPT) - 1) / (2 * TPT);      // 1..4
   const int n_items = ph.n_tiles * groups;
   const int col = tt & 63, half = tt >> 6;
   const int warp = tt >> 5, lane = tt & 31;
@@ -208,7 +214,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
     CLK(1);
     const int tile = epi_tile_of(item, groups);
     const int grp = item - tile * groups;
-    const int ts = grp * EPI_TPI + half * EPI_TPT;     // first token of this thread
+    const int ts = grp * (2 * TPT) + half * TPT;     // first token of this thread
     // contributors of the tile: consecutive CTAs b0 .. b0+n-1; closed form of the balanced partition of program.cu
     const int k0 = tile * nk, k1 = k0 + nk - 1;
     const int b0 = k0 < big ? fast_div(k0, m_hi) : rem + fast_div(k0 - big, m_lo);
@@ -217,13 +223,13 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
     const int seg0 = tile - fast_div(b0 * per_lo + min(b0, rem), m_nk);
 
     // ---- all operand loads that do not depend on the reduction, issued before anything is consumed
-    EpiOps ops;
-    epi_load_ops(ph, item, tt, ops);
+    EpiOps<TPT> ops;
+    epi_load_ops<TPT>(ph, item, tt, ops);
     const bool is_q = tile < ph.n_q_tiles;
     const bool is_k = !is_q && tile < ph.n_q_tiles + ph.n_k_tiles;
     const bool rope = heads && ph.rope && (is_q || is_k);
-    const unsigned short (&rraw)[2][EPI_TPT] = ops.rraw;
-    const bf16 (&csraw)[4][EPI_TPT] = ops.csraw;
+    const unsigned short (&rraw)[2][TPT] = ops.rraw;
+    const bf16 (&csraw)[4][TPT] = ops.csraw;
     const float (&bias_e)[2] = ops.bias_e;
     const float (&nwf)[2] = ops.nwf;
     const int row_base_e = ops.row_base;
@@ -242,12 +248,12 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
     // ---- reduction over the contributors in k order; the loads of B contributors are in flight together.  The square
     // projections (o_proj, down_proj: 5-6 contributors per tile on 148 CTAs) take the wider batch: one L2 round trip
     // instead of two.  Same order of additions either way.
-    float a[2][EPI_TPT];
+    float a[2][TPT];
 #pragma unroll
-    for (int i = 0; i < EPI_TPT; ++i) { a[0][i] = 0.f; a[1][i] = 0.f; }
+    for (int i = 0; i < TPT; ++i) { a[0][i] = 0.f; a[1][i] = 0.f; }
     const float* const pbase = partials + ts * PG_BM + col;
-    if (n_c > EPI_BATCH) epi_reduce<EPI_BATCH_WIDE>(a, pbase, b0, n_c, seg0, maxseg);
-    else epi_reduce<EPI_BATCH>(a, pbase, b0, n_c, seg0, maxseg);
+    if (n_c > EPI_BATCH) epi_reduce<EPI_BATCH_WIDE, TPT>(a, pbase, b0, n_c, seg0, maxseg);
+    else epi_reduce<EPI_BATCH, TPT>(a, pbase, b0, n_c, seg0, maxseg);
 
     CLK(3);
 #ifdef VS_PROGRAM_CLK
@@ -259,7 +265,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       bf16* Y = ph.Y;
       const long ldy = ph.ldy;
 #pragma unroll
-      for (int i = 0; i < EPI_TPT; ++i)
+      for (int i = 0; i < TPT; ++i)
         if (ts + i < T) {
           const float g = rbf(pg_silu(rbf(a[0][i])));                  // act_fn(gate) rounds, then * up rounds
           Y[(long)(ts + i) * ldy + tile * 64 + col] = f2bf(g * rbf(a[1][i]));
@@ -272,7 +278,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       bf16* dst = is_q ? ph.Qout + (long)head * ph.q_head_stride
                        : (is_k ? ph.Kout : ph.Vout) + (long)head * ph.kv_head_stride + (long)row_base * 128;
 #pragma unroll
-      for (int i = 0; i < EPI_TPT; ++i)
+      for (int i = 0; i < TPT; ++i)
         if (ts + i < T) {
           const float x1 = rbf(a[0][i] + b1), x2 = rbf(a[1][i] + b2);
           float o1 = x1, o2 = x2;
@@ -290,12 +296,12 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       const long ldy = ph.ldy;
       float* ssq = ph.ssq;
       const bf16* nw = ph.w;                                           // folded-in RMSNorm (prog_add_norm) or null
-      float yv[2][EPI_TPT];
+      float yv[2][TPT];
 #pragma unroll
       for (int j = 0; j < 2; ++j) ok[j] = tile * PG_BM + col + 64 * j < N;
       if (ssq) sync();                                                 // previous item's readers of `red` are done
 #pragma unroll
-      for (int i = 0; i < EPI_TPT; ++i) {
+      for (int i = 0; i < TPT; ++i) {
         float q = 0.f;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -310,7 +316,7 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
         }
         if (ssq) {
           q = warp_sum(q);
-          if (lane == 0) red[warp * EPI_TPT + i] = q;
+          if (lane == 0) red[warp * TPT + i] = q;
         }
       }
       // A folded-in RMSNorm exchanges the sums of squares as tagged 8-byte words (value + (launch, phase) tag in one
@@ -321,11 +327,11 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
       const unsigned int ll_tag = ((epoch + 1u) << 16) | ((unsigned int)ph.phase_idx & 0xffffu);
       if (ssq) {
         sync();
-        if (tt < EPI_TPI) {                                            // token tt of the group: warps 2*h, 2*h+1 hold its half
-          const int h = tt / EPI_TPT, i = tt % EPI_TPT;
-          const int t = grp * EPI_TPI + tt;
+        if (tt < (2 * TPT)) {                                            // token tt of the group: warps 2*h, 2*h+1 hold its half
+          const int h = tt / TPT, i = tt % TPT;
+          const int t = grp * (2 * TPT) + tt;
           if (t < T) {
-            const float q = red[(2 * h) * EPI_TPT + i] + red[(2 * h + 1) * EPI_TPT + i];
+            const float q = red[(2 * h) * TPT + i] + red[(2 * h + 1) * TPT + i];
             ssq[tile * VS_TOK + t] = q;
             if (nw) {
               const unsigned long long w = ((unsigned long long)ll_tag << 32) | __float_as_uint(q);
@@ -335,15 +341,15 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
         }
       }
       CLK(8);
-      if (nw) {
+      if (TPT == EPI_TPT && nw) {      // (the builder folds a norm only into epilogues of 8-row items)
         // LlamaRMSNorm of the finished rows (same arithmetic and summation order as norm_phase): wait for the sums of
         // squares of every tile of the token group, normalise the values still in registers
 #pragma unroll
-        for (int q = 0; q < (EPI_TPI + 3) / 4; ++q) {                  // warp w: tokens 2w, 2w+1 of the group (3w.. for 10)
-          const int tg = warp * ((EPI_TPI + 3) / 4) + q;
-          const int t = grp * EPI_TPI + tg;
+        for (int q = 0; q < ((2 * TPT) + 3) / 4; ++q) {                  // warp w: tokens 2w, 2w+1 of the group (3w.. for 10)
+          const int tg = warp * (((2 * TPT) + 3) / 4) + q;
+          const int t = grp * (2 * TPT) + tg;
           float ss = 0.f;
-          if (tg < EPI_TPI && t < T)
+          if (tg < (2 * TPT) && t < T)
             for (int i = lane; i < n_tiles; i += 32) {
               unsigned long long w;
               do {
@@ -352,15 +358,15 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
               ss += __uint_as_float((unsigned int)w);
             }
           ss = warp_sum(ss);
-          if (lane == 0 && tg < EPI_TPI) red[32 + tg] = 1.0f / sqrtf(ss / (float)ph.H + ph.eps);
+          if (lane == 0 && tg < (2 * TPT)) red[32 + tg] = 1.0f / sqrtf(ss / (float)ph.H + ph.eps);
         }
         sync();
         CLK(9);
         bf16* X = ph.dst;
         const long ldd = ph.ldd;
 #pragma unroll
-        for (int i = 0; i < EPI_TPT; ++i) {
-          const float rstd = red[32 + half * EPI_TPT + i];
+        for (int i = 0; i < TPT; ++i) {
+          const float rstd = red[32 + half * TPT + i];
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             if (ok[j] && ts + i < T)                                   // weight * bf16(x * rstd): two bf16 roundings
@@ -371,6 +377,14 @@ __device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int 
     CLK(5);
   }
   CLK(6);
+}
+__device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
+                                       TeamSync sync) {
+  epi_phase_t<EPI_TPT>(ph, epoch, gteam, n_teams, tt, red, sync);
+}
+__device__ __noinline__ void epi_phase_wide(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
+                                            TeamSync sync) {
+  epi_phase_t<2 * EPI_TPT>(ph, epoch, gteam, n_teams, tt, red, sync);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
