@@ -181,20 +181,20 @@ def test_specgenerate_fused_matches_reference_and_greedy(name):
     assert torch.equal(out2, out) and acc2 == acc
 
 
-def test_specgenerate_switches_attention_program_at_capacity():
-    """The single-phase attention holds a bounded number of keys; specgenerate must switch to the two-phase program
-    when the KV length is about to exceed it -- mid-generation, without changing a token."""
+def test_generation_crosses_the_register_resident_attention_limit(monkeypatch):
+    """The single-phase attention keeps its scores in registers up to 4 granules (128 keys) per kv split and parks them in
+    the score scratch beyond; with ONE split per head the generation crosses that limit mid-way -- same cycle program,
+    no token may change."""
     g, tcfg, dcfg, tw, dw, ids, emb, mask = load_case("bigram_noisy_img")
-    model = build(tcfg, dcfg, tw, dw)
-    kw = dict(temperature=0.0, log=True, return_acceptance_len=True, max_new_tokens=60)
+    kw = dict(temperature=0.0, log=True, return_acceptance_len=True, max_new_tokens=120)
     if emb is not None:
         kw.update(inputs_embeds=emb.to(DEV), image_mask=mask.to(DEV))
-    ref_out, _, _, ref_acc = model.specgenerate(ids.to(DEV), **kw)
-    assert set(model._cycle_progs) == {(True, 0.0)}                # everything fit the fused phase
-    # shrink the capacity so that the target crosses it after a few cycles
-    model.base_model_engine.scratch.fused_kv_capacity = ids.shape[1] + 2 * L.VS_MAX_ACCEPT + 30 + 12
+    ref_out, _, _, ref_acc = build(tcfg, dcfg, tw, dw).specgenerate(ids.to(DEV), **kw)
+    assert ids.shape[1] < 128 < ref_out.shape[1]                   # the kv length crosses 128 keys during the generation
+    monkeypatch.setenv("VS_ATTN_SPLITS", "1")
+    model = build(tcfg, dcfg, tw, dw)
     out, _, _, acc = model.specgenerate(ids.to(DEV), **kw)
-    assert set(model._cycle_progs) == {(True, 0.0), (False, 0.0)}  # both programs were used
+    assert set(model._cycle_progs) == {(True, 0.0)}                # one program for every context length
     assert torch.equal(out, ref_out) and acc == ref_acc
 
 

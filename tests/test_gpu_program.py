@@ -213,7 +213,12 @@ def program_attention(Q, K, V, nh, nkv, Tq, n_ctx, n_new, causal, bits, eager, n
     a.prefix_stable = stable
     if fused:
         assert n_ctx + n_new <= sc.fused_kv_capacity
-    p = run_program(lambda p: p.add("attention", C.byref(a)), attn_fused=fused, **opts)
+    try:
+        p = run_program(lambda p: p.add("attention", C.byref(a)), attn_fused=fused, **opts)
+    except RuntimeError as e:
+        if not fused and "two-phase attention program is not compiled" in str(e):
+            pytest.skip("two-phase attention program: build with -DVS_TWO_PHASE_ATTN=1 (tools/build_variant.py)")
+        raise
     assert p.phase_types() == ([L.PH_ATTN_FUSED] if fused else [L.PH_ATTN_S, L.PH_ATTN_PV])
     assert int(sc.attn_counters.abs().sum()) == 0
     if fused:                                 # relaunch: the per-head arrival counters are monotonic across launches

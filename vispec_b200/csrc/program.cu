@@ -43,6 +43,11 @@
 #ifndef VS_MMA_CONVERGED
 #define VS_MMA_CONVERGED 0
 #endif
+// The two-phase attention program (PH_ATTN_S + PH_ATTN_PV on the cp.async bodies of attn_dev.cuh) was the A/B reference of
+// the single-phase attention; it is compiled into the kernel only with -DVS_TWO_PHASE_ATTN=1 (tools/build_variant.py).
+#ifndef VS_TWO_PHASE_ATTN
+#define VS_TWO_PHASE_ATTN 0
+#endif
 
 namespace vs {
 
@@ -86,6 +91,7 @@ static_assert(sizeof(ScanSmem) <= BIG_SMEM, "team scratch too small for the voca
 // NOTE: the phase descriptor lives in shared memory; the bodies below read its fields many times between barriers and
 // inline asm with memory clobbers, which would turn every use into a fresh generic load.  Each phase therefore works on
 // a private (register) copy of the arguments it needs.
+#if VS_TWO_PHASE_ATTN
 __device__ __noinline__ void attn_s_phase(const Phase& ph, int gteam, int n_teams, int tt, uint8_t* tsm, BigTeamSync tsync) {
   const AttnArgs a = ph.attn;
   const int n_ctx = a.n_ctx ? ld_vol(a.n_ctx) : a.n_ctx_host;
@@ -102,6 +108,7 @@ __device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_tea
   for (int item = gteam; item < n_items; item += n_teams)
     attn_pv_item(a, sm, item / a.pv_splits, 0, 1, item % a.pv_splits, a.pv_splits, tt, tsync);
 }
+#endif
 // PH_ATTN_FUSED: one (head, kv split) item per team, K/V granules staged by the KV producer warp (attn_ring.cuh).
 // `fifo`: FIFO index of the team's next granule (advances identically on the producer side).  The arguments are read
 // from the staged phase descriptor in shared memory (no private copy in local memory).
@@ -570,8 +577,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
           break;
         case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
+#if VS_TWO_PHASE_ATTN
         case PH_ATTN_S: attn_s_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
         case PH_ATTN_PV: attn_pv_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
+#endif
         case PH_ATTN_FUSED: attn_fused_phase(ph, epoch, gbteam, btt, bsm, att_bars, att_fifo, kvc, bsync); break;
         case PH_ARGMAX: argmax_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_LSM_STATS: lsm_stats_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
@@ -954,6 +963,10 @@ int prog_add_attention(vs_program* pg, const AttnArgs& a) {
     pg->phases.push_back(f);
     return VS_OK;
   }
+#if !VS_TWO_PHASE_ATTN
+  return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_attention",
+               "the two-phase attention program is not compiled into this build (option attn_fused = 0 needs -DVS_TWO_PHASE_ATTN=1)");
+#endif
   Phase s = blank(PH_ATTN_S, a.Tq);
   s.attn = a;
   // as many kv splits as give every team one (head, split) item, bounded by the caller's workspace

@@ -525,14 +525,13 @@ class TargetEngine:
     def verify(self, token_ids: torch.Tensor, pos_ids: torch.Tensor, bits: Optional[torch.Tensor], T: int,
                cur_len: Optional[int] = None):
         """vs_verify_step on T <= 32 tokens appended (uncommitted) at CUR_LEN.  token_ids / pos_ids int32 device.
-        `cur_len` (host copy of CUR_LEN, if the caller has it) lets the short-context single-phase attention be used."""
+        (`cur_len` is accepted for compatibility; one verify program serves every context length.)"""
         if use_programs():
             self._v_ids[:T].copy_(token_ids[:T])
             self._v_pos[:T].copy_(pos_ids[:T])
             if bits is not None:
                 self._v_bits[:T].copy_(bits[:T])
-            fused = cur_len is not None and cur_len + T <= self.scratch.fused_kv_capacity
-            self._verify_program(T, bits is not None, fused).run()
+            self._verify_program(T, bits is not None, True).run()
             return
         L.check(self.lib.vs_verify_step(C.byref(self.c), C.byref(self.scratch.c), L.ptr(token_ids), L.ptr(pos_ids),
                                         L.ptr(bits), T, L.ptr(self.state), L.ptr(self.hidden_out), L.ptr(self.logits),
@@ -723,7 +722,7 @@ class DraftEngine:
         cfg, lib, dev = self.cfg, self.lib, self.device
         if use_programs():
             self.state[L.ST_NEXT_TOKEN] = int(sample_token)
-            fused = n_c + 8 * (cfg.depth + 1) <= self.scratch.fused_kv_capacity
+            fused = True
             if self._prog_levels.get(fused) is None:
                 pr = Program(dev, attn_fused=fused).register_tiled(self.tiled)
                 pr.add("draft_levels", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb),
@@ -841,7 +840,7 @@ class DraftEngine:
         self.prefill_pos = pos[:n_c]
         if use_programs():
             self.state[L.ST_NEXT_TOKEN] = int(sample_token)
-            fused = n_c + 8 * (cfg.depth + 1) <= self.scratch.fused_kv_capacity
+            fused = True
             if self._prog_levels.get(fused) is None:
                 pr = Program(dev, attn_fused=fused).register_tiled(self.tiled)
                 pr.add("draft_levels", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb),
@@ -876,7 +875,7 @@ class DraftEngine:
         self.state[L.ST_NEXT_TOKEN] = int(sample_token)
         if use_programs():
             d_len = int(self.state[L.ST_D_LEN].item())
-            fused = d_len + L.VS_MAX_ACCEPT + 8 * (self.cfg.depth + 1) <= self.scratch.fused_kv_capacity
+            fused = True
             if self._prog_tree.get(fused) is None:
                 pr = Program(self.device, attn_fused=fused).register_tiled(self.tiled)
                 pr.add("draft_tree", C.byref(self.c), C.byref(self.scratch.c), C.byref(self.tb), L.ptr(self.state))

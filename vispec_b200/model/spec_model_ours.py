@@ -170,8 +170,8 @@ class SpecModel:
     def cycle_program(self, trace: bool = False, pf_ahead: Optional[int] = None, inflight: Optional[int] = None,
                       attn_fused: bool = True, temperature: float = 0.0) -> Program:
         """The whole draft+verify cycle (spec_model_ours.py:484-547 loop body) as one persistent-kernel launch.
-        attn_fused: single-phase attention (target KV + tree and draft KV must stay within
-        `scratch.fused_kv_capacity`; specgenerate switches to the two-phase program beyond it)."""
+        attn_fused: single-phase attention on TMA-staged K/V (any context the scratch was sized for); False selects the
+        two-phase A/B program, which needs a -DVS_TWO_PHASE_ATTN=1 build of the library."""
         eng_t, eng_d = self.base_model_engine, self.spec_layer.engine
         p = Program(eng_t.device, pf_ahead=pf_ahead, trace=trace, attn_fused=attn_fused)
         p.register_tiled(eng_t.tiled + eng_d.tiled)
@@ -362,13 +362,12 @@ class SpecModel:
         lib = eng_t.lib
 
         programs = use_programs()
-        cap_t, cap_d = eng_t.scratch.fused_kv_capacity, eng_d.scratch.fused_kv_capacity
 
         def launch(slot):
             if programs:
-                # cur_len / d_rows are one cycle behind when a launch is issued ahead: VS_MAX_ACCEPT rows of slack
-                fused = (cur_len + 2 * L.VS_MAX_ACCEPT + T <= cap_t and
-                         d_rows + 3 * L.VS_MAX_ACCEPT + 8 * (self.spec_layer.depth + 1) <= cap_d)
+                # one cycle program serves every context length the scratch was sized for (the single-phase attention keeps
+                # its scores in registers up to 4 granules per split and parks them beyond, csrc/attn_ring.cuh)
+                fused = True
                 temp = logits_processor.temperature if logits_processor is not None else 0.0
                 prog = self._cycle_progs.get((fused, temp))
                 if prog is None:
