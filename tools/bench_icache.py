@@ -26,7 +26,7 @@ at.n_ctx, at.n_ctx_host, at.n_new, at.causal, at.bits, at.eager, at.scale = None
 at.scores, at.score_ld, at.stats, at.max_chunks = sc.scores.data_ptr(), sc.score_ld, sc.stats.data_ptr(), sc.max_chunks
 at.opart, at.pv_splits, at.counters, at.O, at.ldo = sc.opart.data_ptr(), sc.pv_splits, sc.attn_counters.data_ptr(), O.data_ptr(), nh * 128
 for interleave in (False, True):
-    p = Program(dev, trace=True, pf_ahead=0)
+    p = Program(dev, trace=True, pf_ahead=0, attn_fused=True)
     for i in range(10):
         p.add("linear", C.byref(a))
         if interleave:
@@ -38,7 +38,7 @@ for interleave in (False, True):
     us = p.read_trace_us()
     ty = p.phase_types()
     print("interleaved with attention" if interleave else "linears only")
-    for name, code in (("gemm", L.PH_GEMM), ("epilogue", L.PH_EPI), ("attn_scores", L.PH_ATTN_S), ("attn_pv", L.PH_ATTN_PV)):
+    for name, code in (("gemm", L.PH_GEMM), ("epilogue", L.PH_EPI), ("attention", L.PH_ATTN_FUSED)):
         v = [round(u, 2) for u, t in zip(us, ty) if t == code]
         if v:
             print(f"  {name:12s}", v)
