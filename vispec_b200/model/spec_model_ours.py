@@ -342,12 +342,16 @@ class SpecModel:
         input_len = input_ids.shape[1]
         reset_tree_mode(self)
         self.sampling_setup(logits_processor, reseed=True)
+        self._vs_seeded = True                           # initialize_tree reseeds only on the stage-by-stage route
         # Qwen2.5-VL target: [3, 1, L] multimodal prompt positions (what the reference's base model derives from
         # image_grid_thw, see `qwen_rope_index`); the decode positions are then offset by rope_deltas on the device
         self.base_model.rope_deltas = 0
         eng_t.set_rope_delta(0)
-        initialize_tree(input_ids, self, self.past_key_values, logits_processor, inputs_embeds, None,
-                        image_mask=special_image_mask, position_ids=kwargs.pop("position_ids", None))
+        try:
+            initialize_tree(input_ids, self, self.past_key_values, logits_processor, inputs_embeds, None,
+                            image_mask=special_image_mask, position_ids=kwargs.pop("position_ids", None))
+        finally:
+            self._vs_seeded = False
         new_token = 0
         acceptance_len = []
         if return_decode_time:

@@ -133,6 +133,10 @@ def initialize_tree(input_ids, model, past_key_values, logits_processor, inputs_
     outputs, orig, hidden_states = model(input_ids, past_key_values=past_key_values, output_orig=True,
                                          inputs_embeds=inputs_embeds, position_ids=kwargs.get("position_ids"))
     if logits_processor is not None:                                        # utils.py:284-288
+        # stage-by-stage route: a fresh Philox key per generation, drawn from torch's generator (torch.manual_seed makes
+        # the run reproducible, two generations do not share a uniform stream); specgenerate reseeds on its own
+        if hasattr(model, "sampling_setup") and not getattr(model, "_vs_seeded", False):
+            model.sampling_setup(logits_processor, reseed=True)
         probabilities = torch.nn.functional.softmax(logits_processor(None, orig[:, -1]), dim=1)
         token = torch.multinomial(probabilities, 1)
     else:
