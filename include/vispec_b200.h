@@ -312,13 +312,16 @@ typedef struct vs_program vs_program;
 int vs_program_create(vs_program** out);
 void vs_program_destroy(vs_program* pg);
 const char* vs_program_last_error(void);
-/* Attention inside a program runs either as two phases (scores | softmax + PV; any kv length) or, with option
- * "attn_fused" = 1, as ONE phase in which every (head, kv split) item is resident and the two passes meet at a per-head
- * arrival counter (K and V read once).  Up to 2 chunks of 64 keys per split (1152 keys for 32 heads on 148 SMs) the
- * scores never leave the SM; longer contexts are streamed through a 2-deep shared-memory ring with the scores parked in
- * the caller's fp32 score scratch (selected inside the kernel from the kv length).  The phase holds at most
+/* Attention inside a program: with option "attn_fused" = 1 (what every composite builder of the library's Python side
+ * uses) ONE phase in which every (head, kv split) item is resident, K / V rows reach shared memory through tensor-map TMA
+ * loads issued by a KV producer warp (csrc/attn_ring.cuh; vs_attn_args.prefix_stable lets it stage the cache prefix before
+ * the phase starts) and the two passes meet at per-head exchanges (K and V read once).  Up to 4 granules of 32 keys per
+ * split (1024 keys for 32 heads on 148 SMs) the scores never leave the SM; longer contexts park them in the caller's score
+ * scratch (selected inside the kernel from the kv length).  The phase holds at most
  * vs_attention_fused_capacity(n_heads, scratch pv_splits, scratch max_chunks) keys (n_ctx + n_new) = what the scratch was
- * sized for (max_chunks * 64; score_ld must cover it); the kernel traps beyond it. */
+ * sized for (max_chunks * 64; score_ld must cover it and be a multiple of 32); the kernel traps beyond it.
+ * "attn_fused" = 0 selects the two-phase A/B program (scores | softmax + PV on the cp.async kernels of vs_attention);
+ * it is compiled in only with -DVS_TWO_PHASE_ATTN=1 (VS_ERR_UNSUPPORTED otherwise). */
 int vs_attention_fused_capacity(int n_heads, int pv_splits_cap, int max_chunks);
 /* options: "pf_ahead" / "inflight" (accepted and ignored since round 2: the L2 prefetcher warp is gone), "x3d" (default 1:
  * the activations of a slab stage arrive through one 3-D tensor-map load instead of one 2-D load per k-chunk),
@@ -327,7 +330,11 @@ int vs_attention_fused_capacity(int n_heads, int pv_splits_cap, int max_chunks);
  * "attn_fused" (see above; before adding phases), "fuse_epilogue" (default 1: an epilogue waits on per-tile arrival
  * counters instead of a grid barrier), "fuse_norm" (default 1; before adding phases: an RMSNorm that follows the
  * residual epilogue which produced its rows runs inside that epilogue -- same bits, one phase fewer),
- * "inflight" / "spin_ns" (tuning of the producer warps) */
+ * "inflight" / "spin_ns" (tuning of the producer warps),
+ * "top_k" (TopKLogitsWarper of the T > 0 acceptance phases added AFTERWARDS -- vs_program_add_accept_sampling,
+ * vs_program_add_spec_cycle_sampling: every verify logit below the k-th largest of its row is dropped before the softmax,
+ * utils.py:39-55; 0 = off),
+ * "kv_two_loads" / "attn_prefetch" / "attn_pf" (A/B switches of the TMA-staged attention) */
 int vs_program_set_option(vs_program* pg, const char* name, int value);
 int vs_program_num_phases(const vs_program* pg);
 int vs_program_phase_types(const vs_program* pg, int32_t* out, int cap);

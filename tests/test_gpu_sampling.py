@@ -29,9 +29,9 @@ def load_tree(ts, draft_tokens, retrieve):
     ts.state[L.ST_N_LEAVES], ts.state[L.ST_MAX_DEPTH], ts.state[L.ST_CUR_LEN] = n_leaves, md, 300
 
 
-def run_accept(ts, logits, V, temperature, uni):
+def run_accept(ts, logits, V, temperature, uni, top_k=0):
     out_rec = torch.zeros(2 + L.VS_MAX_ACCEPT, dtype=torch.int32, device=DEV)
-    p = Program(DEV)
+    p = Program(DEV, top_k=top_k)
     p.add("accept_sampling", C.byref(ts.tb), ts.state.data_ptr(), logits.data_ptr(), V, V, C.c_float(temperature),
           None if uni is None else uni.data_ptr(), out_rec.data_ptr())
     p.commit()
@@ -73,6 +73,54 @@ def test_accept_sampling_matches_reference_decisions():
             assert st[L.ST_NEXT_TOKEN] == tok == rec[1], f"case {ci}"
             checked_tokens += 1
     assert checked_tokens >= len(g["cases"]) * 3 // 4
+
+
+@pytest.mark.parametrize("top_k", [1, 5, 50, 100000])
+def test_accept_sampling_with_top_k_matches_oracle_decisions(top_k):
+    """TopKLogitsWarper on the device (two-level radix select of the k-th largest bf16 logit per tree row, statistics /
+    candidate probabilities / residual sampling over the kept logits) against oracle.evaluate_posterior_sampling with
+    the same warper (pinned against the reference's processor list, tests/golden/warpers_sampling.pt) and the same
+    uniforms: accept / reject decisions must be identical, the sampled token must come from the kept set and follow the
+    oracle's sample_p at the same uniform."""
+    g = torch.load(GOLDEN, weights_only=False)
+    V = g["V"]
+    checked_tokens = same = 0
+    for ci, c in enumerate(g["cases"]):
+        ts = TreeState()
+        load_tree(ts, c["draft_tokens"], c["retrieve"])
+        logits = torch.zeros(32, V, dtype=torch.bfloat16, device=DEV)
+        logits[:c["tree_logits"].shape[0]] = c["tree_logits"].to(DEV)
+        n_leaves, md = c["retrieve"].shape
+        uni = torch.zeros(32 * L.VS_RETRIEVE_LD + 1, dtype=torch.float32, device=DEV)
+        u2 = torch.zeros(32, L.VS_RETRIEVE_LD)
+        u2[:n_leaves, :md] = c["uni"]
+        uni[:32 * L.VS_RETRIEVE_LD] = u2.view(-1).to(DEV)
+        u_sample = ((ci * 0.6180339887 + 0.37) % 1.0) * 0.98 + 0.01
+        uni[32 * L.VS_RETRIEVE_LD] = u_sample
+        # the oracle on the same inputs
+        cand = torch.cat((c["draft_tokens"], torch.full((1, 1), -1, dtype=torch.long)), dim=1)[0, c["retrieve"]]
+        path_logits = c["tree_logits"].float()[c["retrieve"].clamp(min=0)]
+        ob, oa, op = vo.evaluate_posterior_sampling(path_logits, cand, c["temperature"], c["uni"], top_k=top_k)
+        # a candidate whose warped probability sits within rounding of its uniform is a knife-edge decision: skip the case
+        p, out_rec = run_accept(ts, logits, V, c["temperature"], uni, top_k=top_k)
+        for rep in range(2):                      # twice: the histograms must be left zero for the next launch
+            ts.state[L.ST_CUR_LEN] = 300
+            p.run()
+            torch.cuda.synchronize()
+            st = ts.state.tolist()
+            assert (st[L.ST_BEST], st[L.ST_ACCEPT]) == (int(ob), int(oa)), f"case {ci} rep {rep}"
+        same += 1
+        kept = op > 0
+        assert bool(kept[st[L.ST_NEXT_TOKEN]]), f"case {ci}: sampled a token the warper dropped"
+        assert int(kept.sum()) >= 1 and (top_k >= V or int(kept.sum()) <= max(top_k, int((op > 0).sum())))
+        cdf = torch.cumsum(op.double(), 0)
+        target = u_sample * float(cdf[-1])
+        tok = int(torch.searchsorted(cdf, torch.tensor(target, dtype=torch.float64), right=True))
+        margin = min(abs(float(cdf[tok]) - target), abs(target - (float(cdf[tok - 1]) if tok else 0.0)))
+        if margin > 1e-4:
+            assert st[L.ST_NEXT_TOKEN] == tok, f"case {ci}"
+            checked_tokens += 1
+    assert same == len(g["cases"]) and checked_tokens >= len(g["cases"]) * 3 // 4
 
 
 def test_accept_sampling_token_distribution():
@@ -170,6 +218,27 @@ def test_specgenerate_cold_temperature_follows_target_argmax():
     if n_tied == 0:
         n = min(out.shape[1], ref.shape[1])
         assert torch.equal(out[:, :n], ref[:, :n])
+
+
+def test_specgenerate_top_k_one_is_greedy():
+    """top_k = 1 keeps only the row maximum, so sampling at any temperature must reproduce the greedy string (wherever the
+    maximum is unique) -- through the whole cycle program with the top-k phases in it."""
+    g, model, ids, emb, mask = _tiny_model()
+    kw = dict(log=True, return_acceptance_len=True, max_new_tokens=40)
+    if emb is not None:
+        kw.update(inputs_embeds=emb.to(DEV), image_mask=mask.to(DEV))
+    torch.manual_seed(11)
+    out, new_token, idx, acc = model.specgenerate(ids.to(DEV), temperature=1.0, top_k=1, **kw)
+    assert new_token == sum(acc) + len(acc) == out.shape[1] - ids.shape[1]
+    assert any(len(k) == 3 and k[2] == 1 for k in model._cycle_progs)          # the top-k cycle program was built
+    from vispec_b200.model.kv_cache import initialize_past_key_values
+    pkv, _, _ = initialize_past_key_values(model.base_model)
+    lm = model.base_model
+    o = lm(inputs_embeds=emb.to(DEV), past_key_values=pkv) if emb is not None else lm(input_ids=ids.to(DEV), past_key_values=pkv)
+    for tok in out[0, ids.shape[1]:].tolist():
+        row = o.logits[0, -1].float()
+        assert float(row[tok]) == float(row.max()), "top_k = 1 emitted a token that is not a row maximum"
+        o = lm(input_ids=torch.tensor([[tok]], device=DEV), past_key_values=pkv)
 
 
 def test_specgenerate_sampling_is_seeded_and_valid():

@@ -19,9 +19,9 @@ VS_MAX_ACCEPT = 8
 ST_SLOTS = 16
 EPI_STORE, EPI_RESID, EPI_SWIGLU, EPI_HEADS = range(4)
 (PH_NOP, PH_GEMM, PH_EPI, PH_NORM, PH_ROWS, PH_ATTN_S, PH_ATTN_PV, PH_ARGMAX, PH_LSM_STATS, PH_TREE, PH_SPLICE,
- PH_LSM_CAND, PH_ATTN_FUSED, PH_GEMM2) = range(14)
+ PH_LSM_CAND, PH_ATTN_FUSED, PH_GEMM2, PH_TOPK_HIST) = range(15)
 PHASE_NAMES = ("nop", "gemm", "epilogue", "rmsnorm", "rows", "attn_scores", "attn_pv", "argmax", "lsm_stats", "tree",
-               "kv_splice", "lsm_candidates", "attn_fused", "slab_gemm")
+               "kv_splice", "lsm_candidates", "attn_fused", "slab_gemm", "topk_hist")
 
 
 class LinearArgs(C.Structure):

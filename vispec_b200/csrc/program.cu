@@ -168,7 +168,8 @@ __device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team
   else if (ph.tree_op == TREE_COMMIT) tree_commit_body(ph.state, wtid);
   else if (ph.tree_op == TREE_ACCEPT_SAMPLE)
     tree_accept_sample_body(ph.tb, ph.state, ph.logits, ph.ldl, ph.V, ph.lstats, ph.n_slices, ph.inv_temp, ph.uni_override,
-                            ph.out_rec, *reinterpret_cast<SampleSmem*>(team_base), wtid, PG_WORKERS, WorkerSync());
+                            ph.out_rec, *reinterpret_cast<SampleSmem*>(team_base), wtid, PG_WORKERS, WorkerSync(), ph.top_k,
+                            ph.hist);
 }
 
 // Every CTA of a slab GEMM needs ALL activation blocks of the phase.  Walking the k-chunks in the same order on every CTA
@@ -584,6 +585,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         case PH_ATTN_FUSED: attn_fused_phase(ph, epoch, gbteam, btt, bsm, att_bars, att_fifo, kvc, bsync); break;
         case PH_ARGMAX: argmax_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_LSM_STATS: lsm_stats_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
+        case PH_TOPK_HIST: topk_hist_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_LSM_CAND: lsm_cand_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_TREE:
           if (b == 0) tree_phase(ph, wtid, team_base);
@@ -658,6 +660,8 @@ struct vs_program {
   bool attn_fused = false;    // attention as ONE phase (kv length limited to vs_attention_fused_capacity)
   size_t keys_count = 0;      // u64 entries of the arg-max / top-k candidate buffer
   size_t lstats_count = 0;    // float2 entries of the log-softmax slice statistics
+  size_t hist_count = 0;      // u32 entries of the top-k warper's histograms ([rows][2][256])
+  int top_k = 0;              // option "top_k": TopKLogitsWarper of the T > 0 acceptance phases added afterwards (0 = off)
   int grid = 0;
   int pf_ahead = 0;            // L2 prefetch distance (tensor-map prefetch costs as much TMA issue as the load itself: off)
   int inflight = 0;           // weight stages in flight per SM (0 = the whole ring)
@@ -673,7 +677,7 @@ struct vs_program {
   uint8_t* ws = nullptr;
   size_t off_trace_cta = 0;
   size_t off_tables = 0;
-  size_t off_maps = 0, off_phases = 0, off_counters = 0, off_trace = 0, off_ssq = 0, off_tilecnt = 0, off_keys = 0, off_lstats = 0, off_partials = 0, total = 0;
+  size_t off_maps = 0, off_phases = 0, off_counters = 0, off_trace = 0, off_ssq = 0, off_tilecnt = 0, off_keys = 0, off_lstats = 0, off_hist = 0, off_partials = 0, total = 0;
   std::string err;
 };
 
@@ -750,6 +754,8 @@ void layout(vs_program* pg) {
   off = align_up(off + pg->keys_count * sizeof(unsigned long long), 256);
   pg->off_lstats = off;
   off = align_up(off + pg->lstats_count * sizeof(float2), 256);
+  pg->off_hist = off;
+  off = align_up(off + pg->hist_count * sizeof(unsigned int), 256);
   pg->off_partials = off;
   off += pg->partial_floats * sizeof(float);
   pg->total = align_up(off, 256);
@@ -1058,6 +1064,19 @@ int prog_add_accept_sampling(vs_program* pg, const TreeBufs& tb, int* state, con
   if (ns > 64) return pfail(VS_ERR_UNSUPPORTED, "vs_program_add_accept_sampling", "vocabulary too large");
   Phase st = blank(PH_LSM_STATS, T);
   st.logits = logits; st.ldl = ldl; st.V = V; st.n_slices = ns; st.lstats = PROG_WS_LSTATS; st.inv_temp = 1.0f / temperature;
+  if (pg->top_k > 0) {
+    // TopKLogitsWarper (utils.py:39-55): the key of the k-th largest logit of every tree row by a two-level radix select
+    // (two histogram phases), then statistics, candidate probabilities and the residual sampling over the kept logits
+    st.top_k = pg->top_k < V ? pg->top_k : V;
+    st.hist = reinterpret_cast<unsigned int*>(uintptr_t(1));                 // patched at commit
+    if ((size_t)VS_TOK * 512 > pg->hist_count) pg->hist_count = (size_t)VS_TOK * 512;
+    for (int level = 0; level < 2; ++level) {
+      Phase h = st;
+      h.type = PH_TOPK_HIST;
+      h.hist_level = level;
+      pg->phases.push_back(h);
+    }
+  }
   pg->phases.push_back(st);
   if ((size_t)T * ns > pg->lstats_count) pg->lstats_count = (size_t)T * ns;
   Phase ph = st;
@@ -1154,6 +1173,7 @@ int vs_program_set_option(vs_program* pg, const char* name, int value) {
   else if (!strcmp(name, "kv_two_loads")) pg->kv_two_loads = value != 0;
   else if (!strcmp(name, "attn_prefetch")) pg->attn_prefetch = value != 0;
   else if (!strcmp(name, "attn_pf")) pg->attn_pf = value;
+  else if (!strcmp(name, "top_k")) pg->top_k = value > 0 ? value : 0;
 
   else if (!strcmp(name, "grid")) {
     if (!pg->phases.empty()) return vs::pfail(VS_ERR_INVALID, "vs_program_set_option", "grid must be set before adding phases");
@@ -1288,6 +1308,7 @@ int vs_program_commit(vs_program* pg, void* workspace, size_t bytes, void* strea
     if (ph.ssq_in == PROG_WS_SSQ) ph.ssq_in = reinterpret_cast<float*>(pg->ws + pg->off_ssq);
     if (ph.keys == PROG_WS_KEYS) ph.keys = reinterpret_cast<unsigned long long*>(pg->ws + pg->off_keys);
     if (ph.lstats == PROG_WS_LSTATS) ph.lstats = reinterpret_cast<float2*>(pg->ws + pg->off_lstats);
+    if (ph.hist) ph.hist = reinterpret_cast<unsigned int*>(pg->ws + pg->off_hist);
     memcpy(host.data() + pg->off_phases + i * sizeof(Phase), &ph, sizeof(Phase));
   }
   // A GEMM that is fused with its epilogue (no grid barrier in between) is executed together with it from ONE descriptor:

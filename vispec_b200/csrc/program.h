@@ -25,6 +25,7 @@ enum PhaseType : int {
   PH_SPLICE = 10,   // KV-cache splice
   PH_LSM_CAND = 11, // log-softmax + top-k, step 2: k best log-probs per (row, slice); merged by the next tree phase
   PH_ATTN_FUSED = 12, // both attention passes in one phase (every (head, split) item resident; per-head arrival counters)
+  PH_TOPK_HIST = 14, // top-k logits warper, threshold search: 256-bin histogram of one byte of the order-preserving bf16 key
   PH_GEMM2 = 13      // slab GEMM (slab.h): every CTA streams whole output rows over the full K range and runs the fused
                      // epilogue (and, optionally, the following RMSNorm) straight from TMEM -- no partial tiles, no PH_EPI
 };
@@ -90,6 +91,10 @@ struct Phase {
   unsigned long long* keys;   // PH_ARGMAX: [T][n_slices]; PH_LSM_CAND: [T][n_slices][8]  (program workspace)
   float2* lstats;             // PH_LSM_STATS: [T][n_slices] (max, sum exp)                 (program workspace)
   float inv_temp;             // PH_LSM_STATS / TREE_ACCEPT_SAMPLE: logits are scaled by 1 / temperature (0 -> 1)
+  int top_k;                  // PH_TOPK_HIST / PH_LSM_STATS / TREE_ACCEPT_SAMPLE: TopKLogitsWarper (0 = off): only logits >= the
+                              // k-th largest of their row count
+  unsigned int* hist;         // [T][2][256] histograms of the high / low key byte (program workspace; zero between launches)
+  int hist_level;             // PH_TOPK_HIST: 0 = high byte of every key, 1 = low byte of the keys in the selected high bin
   const float* uni_override;  // TREE_ACCEPT_SAMPLE: test hook, see vs_program_add_accept_sampling
   // ---- PH_TREE
   int tree_op, level;

@@ -678,6 +678,7 @@ struct ScanSmem {
   bf16 x[SCAN_MAX];
   unsigned long long red64[8];
   float redf[8];
+  unsigned int hist[256];            // PH_TOPK_HIST
 };
 
 __device__ __forceinline__ void slice_bounds(int V, int n_slices, int s, int& lo, int& hi) {
@@ -744,7 +745,33 @@ __device__ __noinline__ void argmax_phase(const Phase& ph, int gteam, int n_team
   }
 }
 
-// PH_LSM_STATS: lstats[row][slice] = (max, sum exp(x - max)) of the slice
+// PH_TOPK_HIST: hist[row][level][256] += histogram of the slice (level 0: high key byte; level 1: low byte of the keys
+// whose high byte is the bin selected from level 0)
+__device__ __noinline__ void topk_hist_phase(const Phase& ph, int gteam, int n_teams, int tid, ScanSmem& sm,
+                                             BigTeamSync sync) {
+  const int n_items = ph.T * ph.n_slices;
+  const int lane = tid & 31;
+  for (int item = gteam; item < n_items; item += n_teams) {
+    const int t = item / ph.n_slices, s = item % ph.n_slices;
+    int lo, hi;
+    slice_bounds(ph.V, ph.n_slices, s, lo, hi);
+    unsigned int above;
+    const int b1 = ph.hist_level ? hist_select(ph.hist + (long)t * 512, (unsigned int)ph.top_k, lane, above) : -1;
+    stage_slice(sm, ph.logits + (long)t * ph.ldl, lo, hi, tid, sync);
+    sm.hist[tid] = 0;                                             // 256 threads, 256 bins
+    sync();
+#pragma unroll 1
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) {
+      const unsigned int key = bf16_key(sm.x[i]);
+      if (b1 < 0) atomicAdd(&sm.hist[key >> 8], 1u);
+      else if ((int)(key >> 8) == b1) atomicAdd(&sm.hist[key & 255u], 1u);
+    }
+    sync();
+    if (sm.hist[tid]) atomicAdd(ph.hist + (long)t * 512 + ph.hist_level * 256 + tid, sm.hist[tid]);
+  }
+}
+
+// PH_LSM_STATS: lstats[row][slice] = (max, sum exp(x - max)) of the slice (top_k > 0: over the logits the warper keeps)
 __device__ __noinline__ void lsm_stats_phase(const Phase& ph, int gteam, int n_teams, int tid, ScanSmem& sm,
                                              BigTeamSync sync) {
   const int n_items = ph.T * ph.n_slices;
@@ -753,15 +780,18 @@ __device__ __noinline__ void lsm_stats_phase(const Phase& ph, int gteam, int n_t
     const int row = ph.row_sel ? ld_vol(ph.row_sel) : t;
     int lo, hi;
     slice_bounds(ph.V, ph.n_slices, s, lo, hi);
+    const unsigned int theta = ph.top_k > 0 ? topk_threshold_key(ph.hist + (long)row * 512, ph.top_k, tid & 31) : 0u;
     stage_slice(sm, ph.logits + (long)row * ph.ldl, lo, hi, tid, sync);
     const float it = ph.inv_temp != 0.f ? ph.inv_temp : 1.f;     // T > 0 acceptance: statistics of logits / temperature
     float m = -INFINITY;
 #pragma unroll 1
-    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) m = fmaxf(m, bf2f(sm.x[i]) * it);
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM)
+      if (bf16_key(sm.x[i]) >= theta) m = fmaxf(m, bf2f(sm.x[i]) * it);
     m = bteam_max_f(m, sm, tid, sync);
     float l = 0.f;
 #pragma unroll 1
-    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM) l += expf(bf2f(sm.x[i]) * it - m);
+    for (int i = tid; i < hi - lo; i += PG_BIG_TEAM)
+      if (bf16_key(sm.x[i]) >= theta) l += expf(bf2f(sm.x[i]) * it - m);
     l = bteam_sum_f(l, sm, tid, sync);
     if (tid == 0) ph.lstats[t * ph.n_slices + s] = make_float2(m, l);
   }

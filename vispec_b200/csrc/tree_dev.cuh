@@ -262,6 +262,54 @@ __device__ __forceinline__ float philox_uniform(unsigned int seed, unsigned int 
   return (float)(r.x >> 8) * (1.0f / 16777216.0f);        // [0, 1)
 }
 
+// ---- top-k logits warper (utils.py:39-55 -> transformers TopKLogitsWarper: drop every logit below the k-th largest of its
+// row; ties with the k-th value stay).  Logits are bf16, so the threshold is found exactly by a two-level radix select on
+// the order-preserving 16-bit key: a histogram of the high byte over the row, then of the low byte inside the selected bin.
+__device__ __forceinline__ unsigned int bf16_key(bf16 v) {
+  const unsigned int b = __bfloat16_as_ushort(v);
+  return (b & 0x8000u) ? (~b & 0xffffu) : (b | 0x8000u);
+}
+// (one warp) the bin that holds the k-th largest entry of a 256-bin histogram, counting from the top bin; `above` = entries
+// in higher bins.  k >= 1 and k <= total count.
+__device__ __forceinline__ int hist_select(const unsigned int* h, unsigned int k, int lane, unsigned int& above) {
+  const uint4 a = __ldcg(reinterpret_cast<const uint4*>(h + lane * 8)), b = __ldcg(reinterpret_cast<const uint4*>(h + lane * 8 + 4));
+  const unsigned int c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  unsigned int s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j];
+  unsigned int incl = s;                                         // entries in this lane's bins and above
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  const unsigned int A = incl - s;
+  const bool mine = A < k && k <= incl;
+  const unsigned int m = __ballot_sync(0xffffffffu, mine);
+  int bin = 0;
+  unsigned int ab = A;
+  if (mine) {
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      if (ab + c[j] >= k) { bin = lane * 8 + j; break; }
+      ab += c[j];
+    }
+  }
+  const int src = m ? __ffs(m) - 1 : 0;                          // (m == 0 only if k exceeds the count: keep everything)
+  bin = __shfl_sync(0xffffffffu, bin, src);
+  above = __shfl_sync(0xffffffffu, ab, src);
+  if (!m) { bin = 0; above = 0; }
+  return bin;
+}
+// (one warp) key of the k-th largest logit of a row from its two histograms
+__device__ __forceinline__ unsigned int topk_threshold_key(const unsigned int* hist_row, int k, int lane) {
+  unsigned int above, above2;
+  const int b1 = hist_select(hist_row, (unsigned int)k, lane, above);
+  const int b2 = hist_select(hist_row + 256, (unsigned int)k - above, lane, above2);
+  return ((unsigned int)b1 << 8) | (unsigned int)b2;
+}
+
+
 struct SampleSmem {
   float px[32 * VS_RETRIEVE_LD];      // target probability of candidate (leaf, depth) under its prefix node
   float uni[32 * VS_RETRIEVE_LD];
@@ -272,6 +320,7 @@ struct SampleSmem {
   int removed[VS_RETRIEVE_LD * 8];    // tokens rejected at the failing depth (at most top_k)
   int n_removed, row, accept, best, slice, picked;
   float target;
+  unsigned int rowTheta[32];          // top-k warper: key of the k-th largest logit of each tree row (0 = keep everything)
 };
 
 // logits [T][ldl] bf16; lstats [T][n_slices] (max, sum exp) of logits * inv_temp.  512 threads of CTA 0.
@@ -279,7 +328,7 @@ template <class Sync>
 __device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int* st, const bf16* logits, long ldl, int V,
                                                         const float2* lstats, int n_slices, float inv_temp,
                                                         const float* uni_override, int* out_rec, SampleSmem& sm, int tid,
-                                                        int nthreads, Sync sync) {
+                                                        int nthreads, Sync sync, int top_k = 0, unsigned int* hist = nullptr) {
   const int n_leaves = st[VS_ST_N_LEAVES];
   const int max_depth = st[VS_ST_MAX_DEPTH];
   const int T = tb.total + 1;
@@ -296,7 +345,14 @@ __device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int*
     sm.rowM[tid] = m;
     sm.rowL[tid] = l;
   }
+  // top-k warper: the statistics above already cover the kept logits only; the same threshold gates the candidates'
+  // probabilities and the residual sampling below (one warp per row)
+  for (int r = tid >> 5; r < 32; r += nthreads >> 5) {
+    const unsigned int th = (top_k > 0 && r < T) ? topk_threshold_key(hist + (long)r * 512, top_k, tid & 31) : 0u;
+    if ((tid & 31) == 0) sm.rowTheta[r] = th;
+  }
   sync();
+  auto kept = [&](int row_, bf16 v) -> bool { return bf16_key(v) >= sm.rowTheta[row_]; };
   // candidate tokens, their probabilities under the prefix node, and the uniforms
   for (int idx = tid; idx < n_leaves * VS_RETRIEVE_LD; idx += nthreads) {
     const int j = idx / VS_RETRIEVE_LD, i = idx % VS_RETRIEVE_LD;
@@ -306,8 +362,9 @@ __device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int*
     float p = 0.f;
     if (i >= 1 && tok >= 0) {
       const int row = tb.retrieve[j * VS_RETRIEVE_LD + i - 1];
-      const float x = __bfloat162float(logits[(long)row * ldl + tok]) * inv_temp;
-      p = expf(x - sm.rowM[row]) / sm.rowL[row];
+      const bf16 lv = logits[(long)row * ldl + tok];
+      const float x = __bfloat162float(lv) * inv_temp;
+      p = kept(row, lv) ? expf(x - sm.rowM[row]) / sm.rowL[row] : 0.f;
     }
     sm.px[idx] = p;
     sm.uni[idx] = uni_override ? uni_override[idx] : philox_uniform(seed, cycle, (unsigned int)idx);
@@ -370,7 +427,7 @@ __device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int*
     float mass = ml.x == -INFINITY ? 0.f : ml.y * expf(ml.x - M);
     for (int r = 0; r < sm.n_removed; ++r) {
       const int x = sm.removed[r];
-      if (x >= lo && x < hi) mass -= expf(__bfloat162float(lr[x]) * inv_temp - M);
+      if (x >= lo && x < hi && kept(row, lr[x])) mass -= expf(__bfloat162float(lr[x]) * inv_temp - M);
     }
     sm.slice_mass[tid] = fmaxf(mass, 0.f);
   }
@@ -395,7 +452,7 @@ __device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int*
     const int e0 = lo + tid * chunk, e1 = min(hi, e0 + chunk);
     float local = 0.f;
     for (int e = e0; e < e1; ++e) {
-      bool rem = false;
+      bool rem = !kept(row, lr[e]);
       for (int r = 0; r < sm.n_removed; ++r) rem = rem || sm.removed[r] == e;
       if (!rem) local += expf(__bfloat162float(lr[e]) * inv_temp - M);
     }
@@ -412,7 +469,7 @@ __device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int*
     for (int w = 0; w < (tid >> 5); ++w) base += sm.warp_tot[w];
     float cum = base + incl - local;                              // mass before this thread's first element
     for (int e = e0; e < e1; ++e) {
-      bool rem = false;
+      bool rem = !kept(row, lr[e]);
       for (int r = 0; r < sm.n_removed; ++r) rem = rem || sm.removed[r] == e;
       if (rem) continue;
       cum += expf(__bfloat162float(lr[e]) * inv_temp - M);
@@ -422,7 +479,7 @@ __device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int*
     if (tid == 0 && sm.picked == 0x7fffffff) {                    // rounding at the very end of the slice: last kept token
       int e = hi - 1;
       for (;; --e) {
-        bool rem = false;
+        bool rem = !kept(row, lr[e]);
         for (int r = 0; r < sm.n_removed; ++r) rem = rem || sm.removed[r] == e;
         if (!rem || e == lo) break;
       }
@@ -430,6 +487,8 @@ __device__ __forceinline__ void tree_accept_sample_body(const TreeBufs& tb, int*
     }
   }
   sync();
+  if (top_k > 0)                                                   // leave the histograms zero for the next launch
+    for (int i = tid; i < T * 512; i += nthreads) hist[i] = 0u;
   if (tid == 0) {
     const int a = sm.accept, best = sm.best, next_tok = sm.picked;
     const int* rowp = tb.retrieve + best * VS_RETRIEVE_LD;

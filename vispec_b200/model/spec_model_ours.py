@@ -156,24 +156,24 @@ class SpecModel:
             st[L.ST_RNG_SEED] = int(torch.randint(0, 2 ** 31 - 1, (1,)))
             st[L.ST_RNG_CTR] = 0
 
-    def accept_sampling_program(self, temperature: float) -> Program:
+    def accept_sampling_program(self, temperature: float, top_k: int = 0) -> Program:
         """The T > 0 acceptance + next-token sampling on the verify logits, for the stage-by-stage route."""
-        p = self._accept_progs.get(temperature)
+        p = self._accept_progs.get((temperature, top_k))
         if p is None:
             eng_t, eng_d = self.base_model_engine, self.spec_layer.engine
-            p = Program(eng_t.device)
+            p = Program(eng_t.device, top_k=top_k)
             p.add("accept_sampling", C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.logits), eng_t.cfg.vocab,
                   eng_t.cfg.vocab, C.c_float(temperature), None, L.ptr(eng_d.out_rec))
-            self._accept_progs[temperature] = p.commit()
+            self._accept_progs[(temperature, top_k)] = p.commit()
         return p
 
     def cycle_program(self, trace: bool = False, pf_ahead: Optional[int] = None, inflight: Optional[int] = None,
-                      attn_fused: bool = True, temperature: float = 0.0) -> Program:
+                      attn_fused: bool = True, temperature: float = 0.0, top_k: int = 0) -> Program:
         """The whole draft+verify cycle (spec_model_ours.py:484-547 loop body) as one persistent-kernel launch.
         attn_fused: single-phase attention on TMA-staged K/V (any context the scratch was sized for); False selects the
         two-phase A/B program, which needs a -DVS_TWO_PHASE_ATTN=1 build of the library."""
         eng_t, eng_d = self.base_model_engine, self.spec_layer.engine
-        p = Program(eng_t.device, pf_ahead=pf_ahead, trace=trace, attn_fused=attn_fused)
+        p = Program(eng_t.device, pf_ahead=pf_ahead, trace=trace, attn_fused=attn_fused, top_k=top_k)
         p.register_tiled(eng_t.tiled + eng_d.tiled)
         if inflight is not None:
             p.set_option("inflight", inflight)
@@ -373,9 +373,11 @@ class SpecModel:
                 # its scores in registers up to 4 granules per split and parks them beyond, csrc/attn_ring.cuh)
                 fused = True
                 temp = logits_processor.temperature if logits_processor is not None else 0.0
-                prog = self._cycle_progs.get((fused, temp))
+                tk = getattr(logits_processor, "top_k", 0) if logits_processor is not None else 0
+                key = (fused, temp) if not tk else (fused, temp, tk)
+                prog = self._cycle_progs.get(key)
                 if prog is None:
-                    prog = self._cycle_progs[(fused, temp)] = self.cycle_program(attn_fused=fused, temperature=temp)
+                    prog = self._cycle_progs[key] = self.cycle_program(attn_fused=fused, temperature=temp, top_k=tk)
                 prog.run(st)
                 self._rec_host[slot].copy_(self._rec_dev[0], non_blocking=True)
                 self._rec_evt[slot].record()

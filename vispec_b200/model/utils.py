@@ -34,28 +34,36 @@ class Timer:
 
 
 class TemperatureProcessor:
-    """What utils.py:39-55 builds for the evaluation scripts' sampling runs: a LogitsProcessorList holding one
-    TemperatureLogitsWarper.  Callable like it (`proc(None, logits) -> logits / temperature`); the CUDA path reads
-    `.temperature`."""
+    """What utils.py:39-55 builds for the sampling runs: a LogitsProcessorList holding a TemperatureLogitsWarper and,
+    for top_k > 0, a TopKLogitsWarper (every logit below the k-th largest of its row becomes -inf; ties with the k-th
+    value stay).  Callable like it (`proc(None, logits)`); the CUDA path reads `.temperature` and `.top_k`."""
 
-    def __init__(self, temperature: float):
+    def __init__(self, temperature: float, top_k: int = 0):
         self.temperature = float(temperature)
+        self.top_k = int(top_k)
 
     def __call__(self, input_ids, scores):
-        return scores / self.temperature
+        scores = scores / self.temperature
+        if self.top_k > 0:
+            k = min(self.top_k, scores.shape[-1])
+            kth = torch.topk(scores, k, dim=-1).values[..., -1:]
+            scores = scores.masked_fill(scores < kth, float("-inf"))
+        return scores
 
 
 def prepare_logits_processor(temperature: float = 0.0, repetition_penalty: float = 0.0, top_p: float = 0.0,
                              top_k: int = 0):
     """utils.py:39-55.  The reference returns an (empty) processor list for temperature <= 1e-5 and callers only build
-    one for temperature > 1e-5 (spec_model_ours.py:272-277); here: None for greedy, a TemperatureProcessor for
-    sampling.  top-p / top-k / repetition-penalty warpers are not on the B200 path."""
+    one for temperature > 1e-5 (spec_model_ours.py:272-277); here: None for greedy, a TemperatureProcessor (temperature
+    + optional top-k) for sampling.  The nucleus (top-p) and repetition-penalty warpers are not on the B200 path: no
+    evaluation script sets them, and the reference's own nucleus filter raises on the 3-D tree logits of
+    evaluate_posterior (tests/golden/warpers_sampling.pt records it)."""
     if temperature <= 1e-5:
         return None
-    if repetition_penalty > 1.0 or 1e-8 <= top_p < 1.0 or top_k > 0:
-        raise NotImplementedError("only temperature sampling is implemented on the B200 path "
-                                  "(top_p / top_k / repetition_penalty warpers are not)")
-    return TemperatureProcessor(temperature)
+    if repetition_penalty > 1.0 or 1e-8 <= top_p < 1.0:
+        raise NotImplementedError("temperature and top_k sampling are implemented on the B200 path "
+                                  "(top_p / repetition_penalty warpers are not)")
+    return TemperatureProcessor(temperature, int(top_k) if top_k and top_k > 0 else 0)
 
 
 def _temp_bits(logits_processor) -> int:
@@ -170,7 +178,7 @@ def evaluate_posterior(logits: torch.Tensor, candidates: torch.Tensor, logits_pr
     eng_t, eng_d = model.base_model_engine, model.spec_layer.engine
     if logits_processor is not None:
         model.sampling_setup(logits_processor)
-        model.accept_sampling_program(logits_processor.temperature).run()
+        model.accept_sampling_program(logits_processor.temperature, getattr(logits_processor, "top_k", 0)).run()
     else:
         L.check(eng_d.lib.vs_accept_greedy(C.byref(eng_d.tb), L.ptr(eng_t.state), L.ptr(eng_t.amax), L.ptr(eng_d.out_rec),
                                            _stream()), "vs_accept_greedy")
