@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS_MAX; ++i) {
-      mbar_init(&full_w[i], 1);
-      mbar_init(&full_x[i], 1);
+      mbar_init(&full_w[i], 2);     // ONE "stage full" barrier: the weight and the activation producer both arrive on it with
+      mbar_init(&full_x[i], 1);     // their byte counts (the MMA warp waits once per stage instead of twice); full_x is unused
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
             for (int s = 0; s < spp; ++s) {
               const int j0 = slab_stage(s, rot, spp) * kc;
               const int nj = min(kc, nk - j0);
-              MMA_WAIT(mbar_wait_sleep(&full_w[stage], par, spin); mbar_wait_sleep(&full_x[stage], par, spin));
+              MMA_WAIT(mbar_wait_full(&full_w[stage], par, spin));
               tc_fence_after();
               const uint32_t base = smem_u32(smem) + stage * STAGE_BYTES;
               MMA_ISSUE {
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
             const uint32_t d_tmem = tmem_base + acc * 64;
             bool first = true;
             for (; c < seg_end; ++c) {
-              MMA_WAIT(mbar_wait_sleep(&full_w[stage], par, spin); mbar_wait_sleep(&full_x[stage], par, spin));
+              MMA_WAIT(mbar_wait_full(&full_w[stage], par, spin));
               tc_fence_after();
               const uint32_t base = smem_u32(smem) + stage * STAGE_BYTES;
               const uint64_t da = make_desc_u32(base);
@@ -430,17 +430,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
             const int nj = min(kc, nk - j0);
             mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
             if (hdr.debug & 1) {
-              mbar_arrive(&full_x[stage]);
+              mbar_arrive(&full_w[stage]);
               if (++stage == NS) { stage = 0; par ^= 1; }
               continue;
             }
-            mbar_expect_tx(&full_x[stage], nj * X_STAGE);
+            mbar_expect_tx(&full_w[stage], nj * X_STAGE);
             uint8_t* dst = smem + stage * STAGE_BYTES + x_off;
             if (tm3 && nj == kc) {
-              tma_load_3d(tm3, &full_x[stage], dst, 0, 0, j0, HINT_EVICT_LAST);      // {64, 32, kc} box: kc blocks at once
+              tma_load_3d(tm3, &full_w[stage], dst, 0, 0, j0, HINT_EVICT_LAST);      // {64, 32, kc} box: kc blocks at once
             } else {
               for (int jj = 0; jj < nj; ++jj)
-                tma_load_2d(tm, &full_x[stage], dst + jj * X_STAGE, (j0 + jj) * BK, 0, HINT_EVICT_LAST);
+                tma_load_2d(tm, &full_w[stage], dst + jj * X_STAGE, (j0 + jj) * BK, 0, HINT_EVICT_LAST);
             }
             if (++stage == NS) { stage = 0; par ^= 1; }
           }
@@ -449,8 +449,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
           int kc = r.x % ph.nk;
           for (int c = r.x; c < r.y; ++c) {
             mbar_wait_sleep(&empty[stage], par ^ 1, hdr.spin_ns);
-            mbar_expect_tx(&full_x[stage], X_STAGE);
-            tma_load_2d(tm, &full_x[stage], smem + stage * STAGE_BYTES + W_STAGE, kc * BK, 0, HINT_EVICT_LAST);
+            mbar_expect_tx(&full_w[stage], X_STAGE);
+            tma_load_2d(tm, &full_w[stage], smem + stage * STAGE_BYTES + W_STAGE, kc * BK, 0, HINT_EVICT_LAST);
             if (++stage == NS) { stage = 0; par ^= 1; }
             if (++kc == ph.nk) kc = 0;
           }

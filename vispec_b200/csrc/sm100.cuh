@@ -169,6 +169,23 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
     __nanosleep(ns);
   }
 }
+// "stage full" wait of the MMA issuer: the hardware-suspended try_wait first (a barrier that is already complete costs
+// ~90 cycles against ~150 for test_wait -- the run-ahead ring is full at the start of every GEMM phase, so this is the
+// common case exactly when the issuer has to catch up), the sleeping poll only when the data is not there yet
+__device__ __forceinline__ void mbar_wait_full(uint64_t* bar, uint32_t parity, unsigned ns) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (!ok) mbar_wait_sleep(bar, parity, ns);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
