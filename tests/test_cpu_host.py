@@ -157,3 +157,35 @@ def test_generate_tree_buffers_matches_reference_goldens():
             ref = torch.tensor(g[k])
             assert b[k].shape == ref.shape and torch.equal(b[k].to(ref.dtype), ref), (name, k)
         assert b["tree_attn_mask"].dtype == torch.float32 and b["retrieve_indices"].dtype == torch.long
+
+
+def test_logits_processor_matches_oracle_warpers():
+    """prepare_logits_processor (utils.py:39-55): None for greedy, temperature (+ top-k) for sampling -- the host-side
+    callable (used for the first token, utils.py:284-288) against oracle.warp_logits, which is pinned against the
+    reference's own processor list; the nucleus and repetition-penalty warpers are not on the B200 path."""
+    from oracle import vispec_oracle as vo
+    from vispec_b200.model import utils as vu
+    assert vu.prepare_logits_processor(temperature=0.0) is None
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(5, 977, generator=g) * 3).to(torch.bfloat16).float()      # bf16 values: ties at the k-th value occur
+    for temperature, top_k in ((1.0, 0), (0.7, 0), (0.7, 1), (1.3, 40), (1.0, 5000)):
+        proc = vu.prepare_logits_processor(temperature=temperature, top_k=top_k)
+        assert proc.temperature == temperature and proc.top_k == top_k
+        got = proc(None, x)
+        ref = vo.warp_logits(x, temperature, 0.0, top_k)
+        assert torch.equal(torch.isinf(got), torch.isinf(ref))
+        torch.testing.assert_close(got[~torch.isinf(got)], ref[~torch.isinf(ref)], rtol=0, atol=0)
+    with pytest.raises(NotImplementedError):
+        vu.prepare_logits_processor(temperature=1.0, top_p=0.9)
+    with pytest.raises(NotImplementedError):
+        vu.prepare_logits_processor(temperature=1.0, repetition_penalty=1.2)
+
+
+def test_sass_has_tma_tensor_loads_and_tcgen05():
+    """The evidence the profiling guide names: tcgen05.mma (UTCHMMA), TMEM loads (LDTM), TMA tensor / bulk loads
+    (UTMALDG / UBLKCP) in the shipped library -- incl. the 4-D tensor-map loads of the attention's KV producer."""
+    from vispec_b200 import build as b
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", b.build()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "UTMALDG.2D", "UTMALDG.4D", "UTMALDG.3D"):
+        assert mnemonic in sass, mnemonic
