@@ -165,6 +165,7 @@ def tree_decoding(model, tree_candidates, past_key_values, tree_position_ids, in
                                                position_ids=position_ids)
     logits = tree_logits[0, retrieve_indices.to(tree_logits.device)]
     logits._vs_model = model                 # lets evaluate_posterior use the device-side arg-max of this verify
+    logits._vs_prev_len = int(input_ids.shape[1])     # kv length before the tree rows were appended
     return logits, hidden_state, outputs
 
 
@@ -176,6 +177,11 @@ def evaluate_posterior(logits: torch.Tensor, candidates: torch.Tensor, logits_pr
     if model is None:
         raise TypeError("evaluate_posterior expects the logits returned by vispec_b200's tree_decoding")
     eng_t, eng_d = model.base_model_engine, model.spec_layer.engine
+    # the verify call left the device-side kv length at prev + tree rows (as the reference's KVCache does); the accept
+    # kernels count from the length BEFORE the tree: PREV_LEN = prev, CUR_LEN = prev + accepted + 1
+    prev_len = getattr(logits, "_vs_prev_len", None)
+    if prev_len is not None:
+        eng_t.set_len(prev_len)
     if logits_processor is not None:
         model.sampling_setup(logits_processor)
         model.accept_sampling_program(logits_processor.temperature, getattr(logits_processor, "top_k", 0)).run()
