@@ -564,18 +564,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
 #ifdef VS_PROGRAM_CLK
             if (b == 0 && wtid == 0) g_clk[32 + (p & 15)] = clock64();      // "end" of the GEMM phase: this CTA's tiles are drained
 #endif
-            if (ph.tpi == 2 * EPI_TPI) epi_phase_wide(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
-            else epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
+            epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
           }
         } break;
         case PH_GEMM2:
           slab_epilogue(ph, epoch, b, G, wtid, tmem_base, acc, acc_par, tfull, tempty, *reinterpret_cast<SlabRed*>(team_base),
                         (hdr.debug & 8) != 0);
           break;
-        case PH_EPI:
-          if (ph.tpi == 2 * EPI_TPI) epi_phase_wide(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
-          else epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync);
-          break;
+        case PH_EPI: epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_ROWS: rows_phase(ph, gteam, n_teams, tt); break;
 #if VS_TWO_PHASE_ATTN

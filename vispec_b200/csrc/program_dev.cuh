@@ -141,9 +141,10 @@ __device__ __forceinline__ int epi_tile_of(int item, int groups) {
   return groups == 1 ? item : (groups == 2 ? item >> 1 : (groups == 4 ? item >> 2 : item / 3));
 }
 // Indices are clamped instead of predicated so that the loads are plain back-to-back instructions.
-template <int TPT>
+template <int TPT, int KIND>
 __device__ __forceinline__ void epi_load_ops(const Phase& ph, int item, int tt, EpiOps<TPT>& o) {
-  const int T = ph.T, N = ph.N, epi = ph.epi;
+  const int T = ph.T, N = ph.N;
+  constexpr int epi = KIND;
   const int groups = (T + (2 * TPT) - 1) / (2 * TPT);
   const int col = tt & 63, half = tt >> 6;
   const int tile = epi_tile_of(item, groups);
@@ -193,11 +194,14 @@ __device__ __forceinline__ void epi_load_ops(const Phase& ph, int item, int tt, 
 // TPT tokens per thread, items of 2 * TPT token rows: 4 by default; 8 (`ph.tpi` = 16) for the epilogues whose item count
 // at 4 would not fit one round over the teams (gate|up: 172 tiles x 4 groups = 688 items on 592 teams; LM heads) -- an item
 // is a latency chain, twice the rows per thread cost far less than a second round.
-template <int TPT>
+// KIND: the epilogue (GemmEpilogue) as a compile-time constant -- one compact function per kind instead of one function
+// with all four bodies interleaved (every phase runs its code cold: what is fetched should be what is executed)
+template <int TPT, int KIND>
 __device__ __forceinline__ void epi_phase_t(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
                                             TeamSync sync) {
   // everything an item needs from the descriptor, once (the descriptor lives in shared memory)
-  const int T = ph.T, N = ph.N, nk = ph.nk, maxseg = ph.maxseg, epi = ph.epi;
+  const int T = ph.T, N = ph.N, nk = ph.nk, maxseg = ph.maxseg;
+  constexpr int epi = KIND;
   const int per_lo = ph.per_lo, rem = ph.rem;
   const unsigned int m_hi = ph.magic_per_hi, m_lo = ph.magic_per_lo, m_nk = ph.magic_nk;
   const float* partials = ph.partials;
@@ -224,7 +228,7 @@ __device__ __forceinline__ void epi_phase_t(const Phase& ph, unsigned int epoch,
 
     // ---- all operand loads that do not depend on the reduction, issued before anything is consumed
     EpiOps<TPT> ops;
-    epi_load_ops<TPT>(ph, item, tt, ops);
+    epi_load_ops<TPT, KIND>(ph, item, tt, ops);
     const bool is_q = tile < ph.n_q_tiles;
     const bool is_k = !is_q && tile < ph.n_q_tiles + ph.n_k_tiles;
     const bool rope = heads && ph.rope && (is_q || is_k);
@@ -378,13 +382,33 @@ __device__ __forceinline__ void epi_phase_t(const Phase& ph, unsigned int epoch,
   }
   CLK(6);
 }
-__device__ __noinline__ void epi_phase(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
-                                       TeamSync sync) {
-  epi_phase_t<EPI_TPT>(ph, epoch, gteam, n_teams, tt, red, sync);
-}
-__device__ __noinline__ void epi_phase_wide(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
-                                            TeamSync sync) {
-  epi_phase_t<2 * EPI_TPT>(ph, epoch, gteam, n_teams, tt, red, sync);
+#define VS_EPI_FN(name, TPT_, KIND_)                                                                                   \
+  __device__ __noinline__ void name(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,  \
+                                    TeamSync sync) {                                                                  \
+    epi_phase_t<TPT_, KIND_>(ph, epoch, gteam, n_teams, tt, red, sync);                                               \
+  }
+VS_EPI_FN(epi_phase_store, EPI_TPT, EPI_STORE)
+VS_EPI_FN(epi_phase_resid, EPI_TPT, EPI_RESID)
+VS_EPI_FN(epi_phase_swiglu, EPI_TPT, EPI_SWIGLU)
+VS_EPI_FN(epi_phase_heads, EPI_TPT, EPI_HEADS)
+VS_EPI_FN(epi_phase_store_wide, 2 * EPI_TPT, EPI_STORE)
+VS_EPI_FN(epi_phase_swiglu_wide, 2 * EPI_TPT, EPI_SWIGLU)
+#undef VS_EPI_FN
+__device__ __forceinline__ void epi_phase(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
+                                          TeamSync sync) {
+  const bool wide = ph.tpi == 2 * EPI_TPI;
+  switch (ph.epi) {
+    case EPI_RESID: epi_phase_resid(ph, epoch, gteam, n_teams, tt, red, sync); break;
+    case EPI_SWIGLU:
+      if (wide) epi_phase_swiglu_wide(ph, epoch, gteam, n_teams, tt, red, sync);
+      else epi_phase_swiglu(ph, epoch, gteam, n_teams, tt, red, sync);
+      break;
+    case EPI_HEADS: epi_phase_heads(ph, epoch, gteam, n_teams, tt, red, sync); break;
+    default:
+      if (wide) epi_phase_store_wide(ph, epoch, gteam, n_teams, tt, red, sync);
+      else epi_phase_store(ph, epoch, gteam, n_teams, tt, red, sync);
+      break;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
