@@ -148,28 +148,48 @@ __device__ __forceinline__ void attn_fused_phase(const Phase& ph, unsigned int e
     else attn_ring_phase<false, false>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
   }
 }
-__device__ __noinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team_base) {
+// One compact function per tree operation (each runs once per cycle on CTA 0, cold: what is fetched should be what is
+// executed -- as one function with every body inlined this was 91 KB of code).
+__device__ __noinline__ void tree_op_level0(const Phase& ph, int wtid) { tree_level0_body(ph.tb, ph.state, wtid); }
+__device__ __noinline__ void tree_op_expand(const Phase& ph, int wtid, TreeSmem& sm) {
+  tree_expand_body(ph.tb, ph.state, ph.level, sm, wtid, WorkerSync());
+}
+__device__ __noinline__ void tree_op_build(const Phase& ph, int wtid, TreeSmem& sm) {
+  tree_build_body(ph.tb, ph.state, ph.sample_token_dev, ph.sample_token_host, sm, wtid, PG_WORKERS, WorkerSync());
+}
+__device__ __noinline__ void tree_op_accept(const Phase& ph, int wtid, TreeSmem& sm) {
+  tree_accept_body(ph.tb, ph.state, ph.amax, ph.out_rec, sm, wtid, WorkerSync());
+}
+__device__ __noinline__ void tree_op_accept_sample(const Phase& ph, int wtid, uint8_t* team_base) {
+  tree_accept_sample_body(ph.tb, ph.state, ph.logits, ph.ldl, ph.V, ph.lstats, ph.n_slices, ph.inv_temp, ph.uni_override,
+                          ph.out_rec, *reinterpret_cast<SampleSmem*>(team_base), wtid, PG_WORKERS, WorkerSync(), ph.top_k,
+                          ph.hist);
+}
+__device__ __noinline__ void tree_op_merge_argmax(const Phase& ph, int wtid) { merge_argmax(ph, wtid); }
+__device__ __noinline__ void tree_op_merge_topk(const Phase& ph, int wtid, uint8_t* team_base) {
+  merge_topk(ph, wtid, reinterpret_cast<unsigned long long*>(team_base), PG_BIG_TEAMS * BIG_SMEM / 8, WorkerSync());
+}
+__device__ __forceinline__ void tree_phase(const Phase& ph, int wtid, uint8_t* team_base) {
   // the tree bodies read device state with plain loads: drop whatever this SM's L1 still holds from an earlier phase of
   // this launch (gpu-scope fence = CCTL.IVALL) before anyone reads
   if (wtid == 0) __threadfence();
   named_bar_sync(1, PG_WORKERS);
   TreeSmem& sm = *reinterpret_cast<TreeSmem*>(team_base);
   if (ph.keys && (ph.tree_op == TREE_ACCEPT || ph.tree_op == TREE_MERGE_ARGMAX)) {
-    merge_argmax(ph, wtid);
+    tree_op_merge_argmax(ph, wtid);
     named_bar_sync(1, PG_WORKERS);
   }
   if (ph.keys && (ph.tree_op == TREE_LEVEL0 || ph.tree_op == TREE_EXPAND || ph.tree_op == TREE_MERGE_TOPK))
-    merge_topk(ph, wtid, reinterpret_cast<unsigned long long*>(team_base), PG_BIG_TEAMS * BIG_SMEM / 8, WorkerSync());
-  if (ph.tree_op == TREE_LEVEL0) tree_level0_body(ph.tb, ph.state, wtid);
-  else if (ph.tree_op == TREE_EXPAND) tree_expand_body(ph.tb, ph.state, ph.level, sm, wtid, WorkerSync());
-  else if (ph.tree_op == TREE_BUILD)
-    tree_build_body(ph.tb, ph.state, ph.sample_token_dev, ph.sample_token_host, sm, wtid, PG_WORKERS, WorkerSync());
-  else if (ph.tree_op == TREE_ACCEPT) tree_accept_body(ph.tb, ph.state, ph.amax, ph.out_rec, sm, wtid, WorkerSync());
-  else if (ph.tree_op == TREE_COMMIT) tree_commit_body(ph.state, wtid);
-  else if (ph.tree_op == TREE_ACCEPT_SAMPLE)
-    tree_accept_sample_body(ph.tb, ph.state, ph.logits, ph.ldl, ph.V, ph.lstats, ph.n_slices, ph.inv_temp, ph.uni_override,
-                            ph.out_rec, *reinterpret_cast<SampleSmem*>(team_base), wtid, PG_WORKERS, WorkerSync(), ph.top_k,
-                            ph.hist);
+    tree_op_merge_topk(ph, wtid, team_base);
+  switch (ph.tree_op) {
+    case TREE_LEVEL0: tree_op_level0(ph, wtid); break;
+    case TREE_EXPAND: tree_op_expand(ph, wtid, sm); break;
+    case TREE_BUILD: tree_op_build(ph, wtid, sm); break;
+    case TREE_ACCEPT: tree_op_accept(ph, wtid, sm); break;
+    case TREE_COMMIT: tree_commit_body(ph.state, wtid); break;
+    case TREE_ACCEPT_SAMPLE: tree_op_accept_sample(ph, wtid, team_base); break;
+    default: break;
+  }
 }
 
 // Every CTA of a slab GEMM needs ALL activation blocks of the phase.  Walking the k-chunks in the same order on every CTA
