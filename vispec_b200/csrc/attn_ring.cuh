@@ -409,13 +409,15 @@ __device__ __forceinline__ unsigned int attn_ring_item(const AttnArgs& p, int n_
     rm0 = fmaxf(rm0, __shfl_xor_sync(0xffffffffu, rm0, 2));
     rm1 = fmaxf(rm1, __shfl_xor_sync(0xffffffffu, rm1, 1));
     rm1 = fmaxf(rm1, __shfl_xor_sync(0xffffffffu, rm1, 2));
-    const float sm0 = rm0 == -INFINITY ? 0.f : rm0, sm1 = rm1 == -INFINITY ? 0.f : rm1;
+    // (ex2.approx as in the streamed variant: the sums only feed the softmax denominator, whose relative error of ~2^-22
+    // is far below the bf16 rounding of the probabilities; 16 inlined expf were 2.5 KB of cold straight-line code)
+    const float b0 = rm0 == -INFINITY ? 0.f : -rm0 * ATT_LOG2E, b1 = rm1 == -INFINITY ? 0.f : -rm1 * ATT_LOG2E;
 #pragma unroll
     for (int u = 0; u < ATT_RING_NG; ++u)
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
-        rl0 += expf(sreg[u][a][0] - sm0) + expf(sreg[u][a][1] - sm0);
-        rl1 += expf(sreg[u][a][2] - sm1) + expf(sreg[u][a][3] - sm1);
+        rl0 += att_ex2(fmaf(sreg[u][a][0], ATT_LOG2E, b0)) + att_ex2(fmaf(sreg[u][a][1], ATT_LOG2E, b0));
+        rl1 += att_ex2(fmaf(sreg[u][a][2], ATT_LOG2E, b1)) + att_ex2(fmaf(sreg[u][a][3], ATT_LOG2E, b1));
       }
     rl0 += __shfl_xor_sync(0xffffffffu, rl0, 1);
     rl0 += __shfl_xor_sync(0xffffffffu, rl0, 2);
