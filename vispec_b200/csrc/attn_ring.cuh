@@ -176,6 +176,16 @@ __device__ __forceinline__ void att_ring_produce(const AttnArgs& a, const CUtens
 // ---------------------------------------------------------------------------------------------------------------------
 // shared tails (same exchanges as attn_dev.cuh, on this shared-memory layout)
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr float ATT_LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float att_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp for softmax STATISTICS (row maxima / denominators): ex2.approx, relative error ~2^-22 -- far below the bf16 rounding of
+// the probabilities that are divided by the result; the probabilities themselves use expf.  exp(-inf) == 0.
+__device__ __forceinline__ float att_exp_stat(float x) { return att_ex2(x * ATT_LOG2E); }
+
 // split statistics -> head-wide softmax denominators; on entry sm.red / sm.red2 hold every warp's (max, sum exp) per row.
 // The exchange is ONE L2 round trip: every split stores its (m, l) per row as two 8-byte words that carry the launch tag in
 // their upper half (an aligned 8-byte store is single-copy atomic: value and flag arrive together, no fence, no counter),
@@ -207,7 +217,7 @@ __device__ __forceinline__ void att_ring_exchange_stats(const AttnArgs& p, AttnR
 #pragma unroll
     for (int w = 0; w < ATT_WARPS; ++w) {                           // fixed order
       const float mw = sm.red[w][tid];
-      if (mw != -INFINITY) l += sm.red2[w][tid] * expf(mw - m);
+      if (mw != -INFINITY) l += sm.red2[w][tid] * att_exp_stat(mw - m);
     }
     att_ll_store(ll + ((long)split * VS_TOK + tid) * 2, m, l, tag);
   }
@@ -221,7 +231,7 @@ __device__ __forceinline__ void att_ring_exchange_stats(const AttnArgs& p, AttnR
         const float2 st = att_ll_wait(ll + ((long)(part + 8 * j) * VS_TOK + q) * 2, tag);
         if (st.x != -INFINITY) {
           const float mn = fmaxf(m, st.x);
-          l = l * expf(m - mn) + st.y * expf(st.x - mn);
+          l = l * att_exp_stat(m - mn) + st.y * att_exp_stat(st.x - mn);
           m = mn;
         }
       }
@@ -230,8 +240,8 @@ __device__ __forceinline__ void att_ring_exchange_stats(const AttnArgs& p, AttnR
     for (int o = 1; o < 8; o <<= 1) {
       const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
       const float mn = fmaxf(m, mo);
-      const float a = m == -INFINITY ? 0.f : l * expf(m - mn);
-      const float b = mo == -INFINITY ? 0.f : lo * expf(mo - mn);
+      const float a = m == -INFINITY ? 0.f : l * att_exp_stat(m - mn);
+      const float b = mo == -INFINITY ? 0.f : lo * att_exp_stat(mo - mn);
       l = a + b;
       m = mn;
     }
@@ -289,12 +299,6 @@ __device__ __forceinline__ void att_ring_reduce_output(const AttnArgs& p, const 
 // read; `bars`: full[ATT_SLOTS] | empty[ATT_SLOTS] of this team; `fifo0`: FIFO index of this item's first K granule.
 // Returns the number of FIFO entries consumed (2 n).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr float ATT_LOG2E = 1.4426950408889634f;
-__device__ __forceinline__ float att_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <bool STREAM, bool EAGER, class Sync>
 __device__ __forceinline__ unsigned int attn_ring_item(const AttnArgs& p, int n_ctx, AttnRingSmem& sm, uint64_t* bars,
@@ -475,8 +479,8 @@ __device__ __forceinline__ unsigned int attn_ring_item(const AttnArgs& p, int n_
       const float mo0 = __shfl_xor_sync(0xffffffffu, rm0, o), lo0 = __shfl_xor_sync(0xffffffffu, rl0, o);
       const float mo1 = __shfl_xor_sync(0xffffffffu, rm1, o), lo1 = __shfl_xor_sync(0xffffffffu, rl1, o);
       const float mn0 = fmaxf(rm0, mo0), mn1 = fmaxf(rm1, mo1);
-      rl0 = (rm0 == -INFINITY ? 0.f : rl0 * expf(rm0 - mn0)) + (mo0 == -INFINITY ? 0.f : lo0 * expf(mo0 - mn0));
-      rl1 = (rm1 == -INFINITY ? 0.f : rl1 * expf(rm1 - mn1)) + (mo1 == -INFINITY ? 0.f : lo1 * expf(mo1 - mn1));
+      rl0 = (rm0 == -INFINITY ? 0.f : rl0 * att_exp_stat(rm0 - mn0)) + (mo0 == -INFINITY ? 0.f : lo0 * att_exp_stat(mo0 - mn0));
+      rl1 = (rm1 == -INFINITY ? 0.f : rl1 * att_exp_stat(rm1 - mn1)) + (mo1 == -INFINITY ? 0.f : lo1 * att_exp_stat(mo1 - mn1));
       rm0 = mn0;
       rm1 = mn1;
     }
