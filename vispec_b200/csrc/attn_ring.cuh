@@ -90,13 +90,13 @@ __device__ __forceinline__ AttRingCut att_ring_cut(int kv_len, int split, int n_
 // ---------------------------------------------------------------------------------------------------------------------
 // KV producer (one lane of the CTA's KV warp): the granule FIFO of both attention teams for ONE attention phase.
 // `fifo[t]`: granules issued to team t so far in this launch (slot = index & 3, mbarrier parity = (index >> 2) & 1).
-// Granules that hold rows >= n_ctx were written by this launch (q|k|v epilogue): they wait for `need_tail` grid
-// barriers (`bars_passed`: the shared-memory word the workers' barrier thread updates) and are ordered behind the generic-proxy writes by a proxy fence; everything else is issued as soon as a slot
+// Granules that hold rows >= n_ctx were written by this launch (q|k|v epilogue): they wait for `bars_before` grid
+// barriers and are ordered behind the generic-proxy writes by a proxy fence; everything else is issued as soon as a slot
 // is free.
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void att_ring_produce(const AttnArgs& a, const CUtensorMap* mapK, const CUtensorMap* mapV, int two_loads,
                                                  int n_ctx, uint8_t* team_base, int team_stride, uint64_t* bars,
-                                                 unsigned int* fifo, const volatile unsigned int* bars_passed, unsigned int need_tail,
+                                                 unsigned int* fifo, const unsigned int* grid_ctr, unsigned int need_tail,
                                                  bool tail_ok, int b, int G, int pf_dist) {
   const int n_splits = a.pv_splits;
   const int kv_len = n_ctx + a.n_new;
@@ -142,7 +142,7 @@ __device__ __forceinline__ void att_ring_produce(const AttnArgs& a, const CUtens
       const bool is_v = i >= n[t];
       const int g = g_lo[t] + (is_v ? i - n[t] : i);
       if (g >= tail_g && !tail_ok) {
-        if (*bars_passed < need_tail) continue;
+        if (ld_relaxed_u32(grid_ctr) < need_tail) continue;
         fence_proxy_async();
         tail_ok = true;
       }

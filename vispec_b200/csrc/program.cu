@@ -221,13 +221,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
   uint64_t* tfull = empty + NS_MAX;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  volatile unsigned int* bar_seen = reinterpret_cast<volatile unsigned int*>(tmem_slot + 1);   // grid barriers passed (workers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, b = blockIdx.x;
 
   if (threadIdx.x == 0) {
-    *bar_seen = 0u;
     for (int i = 0; i < NS_MAX; ++i) {
       mbar_init(&full_w[i], 2);     // ONE "stage full" barrier: the weight and the activation producer both arrive on it with
       mbar_init(&full_x[i], 1);     // their byte counts (the MMA warp waits once per stage instead of twice); full_x is unused
@@ -437,8 +435,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         // the token tile is produced by earlier phases of this launch: wait until all of them completed everywhere
         // (relaxed polling, no L1 invalidation storm; the tile itself is read by the TMA unit from L2, ordered behind the
         // observed counter value by the proxy fence)
-        const unsigned int need = (unsigned int)ph.bars_before;
-        while (*bar_seen < need) __nanosleep(20);         // relayed by the workers' barrier thread through shared memory
+        const unsigned int need = (unsigned int)ph.bars_before * (unsigned int)G;
+        while (ld_relaxed_u32(hdr.counters) < need) __nanosleep(64);
         fence_proxy_async();
         if (ph.type == PH_GEMM2) {
           const int kc = ph.s_kc, nk = ph.nk;
@@ -490,9 +488,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       for (int p = 0; p < hdr.n_phases; ++p) {
         const Phase& ph = hdr.phases[p];
         if (ph.type != PH_ATTN_FUSED) continue;
-        const unsigned int need_start = (unsigned int)ph.pf_bars;          // grid barriers passed (relayed by the workers)
-        const unsigned int need_tail = (unsigned int)ph.bars_before;
-        while (*bar_seen < need_start) __nanosleep(100);
+        const unsigned int need_start = (unsigned int)ph.pf_bars * (unsigned int)G;
+        const unsigned int need_tail = (unsigned int)ph.bars_before * (unsigned int)G;
+        while (ld_relaxed_u32(hdr.counters) < need_start) __nanosleep(100);
 #ifdef VS_PROGRAM_CLK
         if (b == 0) g_clk[20] = clock64();
 #endif
@@ -504,7 +502,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         if (b == 0) g_clk[21] = clock64() + (n_ctx & 0);
 #endif
         att_ring_produce(a, hdr.maps + ph.tmK, hdr.maps + ph.tmV, ph.kv_two_loads, n_ctx, team_base, BIG_SMEM, att_bars, fifo,
-                         bar_seen, need_tail, tail_ok, b, G, hdr.attn_pf);
+                         hdr.counters, need_tail, tail_ok, b, G, hdr.attn_pf);
 #ifdef VS_PROGRAM_CLK
         if (b == 0) g_clk[23] = clock64();
 #endif
@@ -619,8 +617,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       if (hdr.trace_cta && wtid == 0) hdr.trace_cta[(long)pl * G + b] = global_timer();   // this CTA's items are done
       if (has_next) {
         if (!pair && ph.type == PH_GEMM && ph.no_barrier) named_bar_sync(1, PG_WORKERS);   // only the staged descriptor needs it
-        else grid_barrier(hdr.counters, (unsigned int)(ph.bars_before + 1) * (unsigned int)G, wtid, bar_seen,
-                          (unsigned int)(ph.bars_before + 1));
+        else grid_barrier(hdr.counters, (unsigned int)(ph.bars_before + 1) * (unsigned int)G, wtid);
       }
       if (hdr.trace && b == 0 && wtid == 0) hdr.trace[pl] = global_timer();
 #ifdef VS_PROGRAM_CLK

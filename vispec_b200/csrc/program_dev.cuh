@@ -61,16 +61,12 @@ __device__ __forceinline__ int ld_vol(const int* p) { return __ldcg(p); }
 #ifndef VS_BARRIER_ACQUIRE
 #define VS_BARRIER_ACQUIRE 0
 #endif
-// `seen` (shared memory): the number of grid barriers this CTA has passed, for the producer warps of the same CTA -- they
-// watch one shared-memory word instead of each polling the global counter with an L2 round trip of its own.
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target, int wtid, volatile unsigned int* seen,
-                                             unsigned int n_passed) {
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target, int wtid) {
   named_bar_sync(1, PG_WORKERS);
   if (wtid == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     while (ld_relaxed_u32(ctr) < target) {
     }
-    *seen = n_passed;
 #if VS_BARRIER_ACQUIRE
     (void)ld_acquire_u32(ctr);     // one acquire (and one L1 invalidation) per barrier, after the relaxed spin
 #endif
