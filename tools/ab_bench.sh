@@ -3,7 +3,7 @@
 for spec in "$@"; do
   name=${spec%%=*}; path=${spec#*=}
   if [ "$path" = "base" ]; then unset VS_LIB_PATH; else export VS_LIB_PATH=$PWD/$path; fi
-  timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-fixture > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err || tail -c 800 gpurun_out/ab_$name.err
+  timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-fixture > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err || tail -c 800 gpurun_out/ab_$name.err
   python - "$name" <<'PY'
 import json, sys
 name = sys.argv[1]
