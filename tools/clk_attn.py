@@ -49,6 +49,8 @@ names = ["item start", "Q in smem", "first K granule landed", "S done + statisti
 print("  SM clock during the phase: %.0f MHz" % ((ck[32 + (N_ATTN & 15)] - t0) / p.read_trace_us()[N_ATTN]))
 print("  KV producer (cycles after the barrier of phase 0): start allowed %d, kv length read %d, first K issued %d, first V issued %d, all issued %d"
       % tuple(ck[i] - t0 for i in (20, 21, 22, 24, 23)))
+print("  dispatch (cycles after t0): barrier released %d, loop top %d, before switch %d, kv length known %d, phase function entered %d, item start %d"
+      % tuple(ck[i] - t0 for i in (52 + ((N_ATTN - 1) & 3), 56, 57, 59, 58, 0)))
 prev = t0
 for i in range(12):
     if ck[i] == 0: continue

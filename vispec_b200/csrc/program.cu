@@ -116,6 +116,9 @@ template <bool STREAM, bool EAGER>
 __device__ __noinline__ void attn_ring_phase(const Phase& ph, int n_ctx, AttnRingSmem& sm, uint64_t* bars, unsigned int& fifo,
                                              unsigned int epoch, int gteam, int tt, BigTeamSync tsync) {
   const int sp = ph.attn.pv_splits;
+#ifdef VS_PROGRAM_CLK
+  if (blockIdx.x == 0 && tt == 0 && gteam == 0) g_clk[58] = clock64();
+#endif
   fifo += attn_ring_item<STREAM, EAGER>(ph.attn, n_ctx, sm, bars, fifo, gteam / sp, gteam % sp, sp, ph.tile_cnt, epoch, tt, tsync);
 }
 // kv length of a prefix_stable phase: the same device int for every layer of a verify step and unchanged since the launch
@@ -135,6 +138,9 @@ __device__ __forceinline__ void attn_fused_phase(const Phase& ph, unsigned int e
     }
   }
   const int kv_len = n_ctx + a.n_new;
+#ifdef VS_PROGRAM_CLK
+  if (blockIdx.x == 0 && tt == 0 && gteam == 0) g_clk[59] = clock64();
+#endif
   if (kv_len > a.score_ld) __trap();              // the score scratch bounds the context
   AttnRingSmem& sm = *reinterpret_cast<AttnRingSmem*>(tsm);
   // up to 2 * ATT_RING_NG granules per split the scores stay in registers; longer contexts park them (uniform over the items)
@@ -526,8 +532,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     KvLenCache kvc{nullptr, 0};
     uint64_t* att_bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR_OFF) + bteam * 2 * ATT_SLOTS;
     const unsigned int epoch = ld_relaxed_u32(hdr.counters + 2);     // launches completed before this one
-    // Phase descriptors are staged through shared memory: the words of phase p+1 are loaded while phase p runs and
-    // stored just before the barrier, so no phase starts with a chain of L2 round trips for its own arguments.
+    // Phase descriptors are staged through shared memory: the words of phase p+1 are copied (cp.async) while phase p
+    // runs and waited for just before the barrier, so no phase starts with a chain of L2 round trips for its own arguments.
     uint8_t* phbuf = smem + PHBUF_OFF;
     {
       const unsigned int* src = reinterpret_cast<const unsigned int*>(hdr.phases);
@@ -538,6 +544,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
     int cur = 0;                                    // slot of the staged descriptor of phase p
     for (int p = 0; p < hdr.n_phases;) {
       const Phase& ph = *reinterpret_cast<const Phase*>(phbuf + cur * PHASE_SLOT);
+#ifdef VS_PROGRAM_CLK
+      if (b == 0 && wtid == 0 && ph.type == PH_ATTN_FUSED) g_clk[56] = clock64();
+#endif
       // A GEMM whose epilogue waits on per-tile counters (no grid barrier in between) runs together with that epilogue as
       // ONE body: its descriptor carries the epilogue's fields as well (vs_program_commit), the PH_EPI descriptor that
       // follows is skipped: no descriptor switch, no CTA-wide barrier and no dispatch between the two.  (Loading the
@@ -545,9 +554,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
       // the GEMM phase delay the first accumulator drain.)
       const bool pair = ph.type == PH_GEMM && ph.no_barrier && p + 1 < hdr.n_phases;
       const int step = pair ? 2 : 1;
-      unsigned int nxt0 = 0;
+      // the next descriptor goes global -> shared as an asynchronous copy: held in a register across the body it was
+      // spilled, and the spill store waited for the load (an L2 round trip at the top of every phase)
       const bool has_next = p + step < hdr.n_phases;
-      if (has_next && wtid < PHASE_WORDS) nxt0 = reinterpret_cast<const unsigned int*>(hdr.phases + p + step)[wtid];
+      if (has_next && wtid < PHASE_WORDS)
+        cp_async4(phbuf + (cur ^ 1) * PHASE_SLOT + 4 * wtid, reinterpret_cast<const unsigned int*>(hdr.phases + p + step) + wtid);
+#ifdef VS_PROGRAM_CLK
+      if (b == 0 && wtid == 0 && ph.type == PH_ATTN_FUSED) g_clk[57] = clock64();
+#endif
       switch (ph.type) {
         case PH_GEMM: {
           const int2 rg = *reinterpret_cast<const int2*>(hdr.tables + ph.range_off + 2 * b);
@@ -612,13 +626,15 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         default: break;
       }
       const int pl = p + step - 1;                  // the last phase this body executed
-      if (has_next && wtid < PHASE_WORDS)
-        reinterpret_cast<unsigned int*>(phbuf + (cur ^ 1) * PHASE_SLOT)[wtid] = nxt0;
+      if (has_next) cp_async_wait_all();            // the staged descriptor (made visible by the barrier below)
       if (hdr.trace_cta && wtid == 0) hdr.trace_cta[(long)pl * G + b] = global_timer();   // this CTA's items are done
       if (has_next) {
         if (!pair && ph.type == PH_GEMM && ph.no_barrier) named_bar_sync(1, PG_WORKERS);   // only the staged descriptor needs it
         else grid_barrier(hdr.counters, (unsigned int)(ph.bars_before + 1) * (unsigned int)G, wtid);
       }
+#ifdef VS_PROGRAM_CLK
+      if (b == 0 && wtid == 0) g_clk[52 + (pl & 3)] = clock64();
+#endif
       if (hdr.trace && b == 0 && wtid == 0) hdr.trace[pl] = global_timer();
 #ifdef VS_PROGRAM_CLK
       if (b == 0 && wtid == 0) g_clk[32 + (pl & 15)] = clock64();        // end of the barrier of phase pl
