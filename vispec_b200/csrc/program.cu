@@ -218,7 +218,9 @@ __device__ __forceinline__ int slab_stage(int s, int rot, int spp) {
 
 __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHeader hdr) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the shared array (not through an integer cast): the compiler keeps the
+  // address space, so everything below is LDS / STS on 32-bit addresses instead of generic loads on 64-bit pointers
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* team_base = smem + RING_BYTES;
   const int NS = hdr.ns, STAGE_BYTES = hdr.stage_bytes;      // ring geometry of this program (see RING_BYTES)
   uint64_t* full_w = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
