@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmArgs p,
                const int n_tiles, const int n_units) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   float* ct = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* empty = full + STAGES;

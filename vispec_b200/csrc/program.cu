@@ -48,6 +48,20 @@
 #ifndef VS_TWO_PHASE_ATTN
 #define VS_TWO_PHASE_ATTN 0
 #endif
+// Register split between the warpgroups of the program kernel (setmaxnreg): 640 threads cap the kernel at 96 registers
+// per thread; the role warps (one warpgroup) give 32 of theirs back and every worker thread takes 8.  ptxas then allocates
+// the worker code on 104 registers (LDL / STL of the kernel 474 -> 316) -- same-box A/B 226.3 -> 230.8 tok/s; 56 / 104 and
+// 40 / 104 measure the same within noise, 32 / 112 spills inside the producer loops.
+#ifndef VS_SETMAXNREG
+#define VS_SETMAXNREG 1
+#endif
+#ifndef VS_ROLE_REGS
+#define VS_ROLE_REGS 64
+#endif
+#ifndef VS_WORKER_REGS
+#define VS_WORKER_REGS 104
+#endif
+static_assert(128 * (96 - VS_ROLE_REGS) >= 512 * (VS_WORKER_REGS - 96), "the role warpgroup must release what the workers take");
 
 namespace vs {
 
@@ -113,22 +127,22 @@ __device__ __noinline__ void attn_pv_phase(const Phase& ph, int gteam, int n_tea
 // `fifo`: FIFO index of the team's next granule (advances identically on the producer side).  The arguments are read
 // from the staged phase descriptor in shared memory (no private copy in local memory).
 template <bool STREAM, bool EAGER>
-__device__ __noinline__ void attn_ring_phase(const Phase& ph, int n_ctx, AttnRingSmem& sm, uint64_t* bars, unsigned int& fifo,
-                                             unsigned int epoch, int gteam, int tt, BigTeamSync tsync) {
+__device__ __noinline__ unsigned int attn_ring_phase(const Phase& ph, int n_ctx, AttnRingSmem& sm, uint64_t* bars,
+                                                     unsigned int fifo, unsigned int epoch, int gteam, int tt, BigTeamSync tsync) {
   const int sp = ph.attn.pv_splits;
 #ifdef VS_PROGRAM_CLK
   if (blockIdx.x == 0 && tt == 0 && gteam == 0) g_clk[58] = clock64();
 #endif
-  fifo += attn_ring_item<STREAM, EAGER>(ph.attn, n_ctx, sm, bars, fifo, gteam / sp, gteam % sp, sp, ph.tile_cnt, epoch, tt, tsync);
+  return fifo + attn_ring_item<STREAM, EAGER>(ph.attn, n_ctx, sm, bars, fifo, gteam / sp, gteam % sp, sp, ph.tile_cnt, epoch, tt, tsync);
 }
 // kv length of a prefix_stable phase: the same device int for every layer of a verify step and unchanged since the launch
 // started, so one L2 round trip serves all of them
 struct KvLenCache { const int* ptr; int val; };
-__device__ __forceinline__ void attn_fused_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
-                                                 uint64_t* bars, unsigned int& fifo, KvLenCache& kvc, BigTeamSync tsync) {
+__device__ __forceinline__ unsigned int attn_fused_phase(const Phase& ph, unsigned int epoch, int gteam, int tt, uint8_t* tsm,
+                                                         uint64_t* bars, unsigned int fifo, KvLenCache& kvc, BigTeamSync tsync) {
   const AttnArgs& a = ph.attn;
   const int sp = a.pv_splits;
-  if (gteam >= a.n_heads * sp) return;            // one resident item per team: the items of a head wait for each other
+  if (gteam >= a.n_heads * sp) return fifo;       // one resident item per team: the items of a head wait for each other
   int n_ctx = a.n_ctx_host;
   if (a.n_ctx) {
     if (a.prefix_stable && kvc.ptr == a.n_ctx) n_ctx = kvc.val;
@@ -147,12 +161,11 @@ __device__ __forceinline__ void attn_fused_phase(const Phase& ph, unsigned int e
   const int n_gran = (kv_len + ATT_GRAN - 1) / ATT_GRAN;
   const bool stream = (n_gran + sp - 1) / sp > 2 * ATT_RING_NG;
   if (a.eager) {
-    if (stream) attn_ring_phase<true, true>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
-    else attn_ring_phase<false, true>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
-  } else {
-    if (stream) attn_ring_phase<true, false>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
-    else attn_ring_phase<false, false>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
+    if (stream) return attn_ring_phase<true, true>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
+    return attn_ring_phase<false, true>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
   }
+  if (stream) return attn_ring_phase<true, false>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
+  return attn_ring_phase<false, false>(ph, n_ctx, sm, bars, fifo, epoch, gteam, tt, tsync);
 }
 // One compact function per tree operation (each runs once per cycle on CTA 0, cold: what is fetched should be what is
 // executed -- as one function with every body inlined this was 91 KB of code).
@@ -261,6 +274,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // register split between the warpgroups (VS_SETMAXNREG above): 128 * (96 - VS_ROLE_REGS) >= 512 * (VS_WORKER_REGS - 96)
+  if (warp < 4) {
+#if VS_SETMAXNREG
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(VS_ROLE_REGS));
+#endif
   if (warp == 0) {
     // ===================== weight producer =====================
     // Walks every GEMM phase of the program in order.  Weights never depend on activations, so this thread runs ahead of
@@ -516,7 +534,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
 #endif
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+#if VS_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(VS_WORKER_REGS));
+#endif
     // ===================== workers (16 warps: four teams of 128 threads / two attention teams of 256) =====================
     const int wtid = threadIdx.x - 4 * 32;          // 0..511
     const int team = wtid >> 7, tt = wtid & 127;    // small team
@@ -604,8 +626,12 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
           }
         } break;
         case PH_GEMM2:
-          slab_epilogue(ph, epoch, b, G, wtid, tmem_base, acc, acc_par, tfull, tempty, *reinterpret_cast<SlabRed*>(team_base),
-                        (hdr.debug & 8) != 0);
+        {
+          const int st = slab_epilogue(ph, epoch, b, G, wtid, tmem_base, acc | (acc_par << 1), tfull, tempty,
+                                       *reinterpret_cast<SlabRed*>(team_base), (hdr.debug & 8) != 0);
+          acc = st & 1;
+          acc_par = st >> 1;
+        }
           break;
         case PH_EPI: epi_phase(ph, epoch, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
         case PH_NORM: norm_phase(ph, gteam, n_teams, tt, reinterpret_cast<float*>(tsm), tsync); break;
@@ -614,7 +640,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) program_kernel(const ProgramHea
         case PH_ATTN_S: attn_s_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
         case PH_ATTN_PV: attn_pv_phase(ph, gbteam, n_bteams, btt, bsm, bsync); break;
 #endif
-        case PH_ATTN_FUSED: attn_fused_phase(ph, epoch, gbteam, btt, bsm, att_bars, att_fifo, kvc, bsync); break;
+        case PH_ATTN_FUSED: att_fifo = attn_fused_phase(ph, epoch, gbteam, btt, bsm, att_bars, att_fifo, kvc, bsync); break;
         case PH_ARGMAX: argmax_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_LSM_STATS: lsm_stats_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;
         case PH_TOPK_HIST: topk_hist_phase(ph, gbteam, n_bteams, btt, *reinterpret_cast<ScanSmem*>(bsm), bsync); break;

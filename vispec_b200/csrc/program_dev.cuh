@@ -424,9 +424,12 @@ struct SlabRed {
   float rstd[VS_TOK];
 };
 
-__device__ __noinline__ void slab_epilogue(const Phase& ph, unsigned int epoch, int b, int G, int wtid, uint32_t tmem_base,
-                                           int& acc, int& acc_par, uint64_t* tfull, uint64_t* tempty, SlabRed& red,
-                                           bool backoff = false) {
+// (the accumulator cursor goes in and out BY VALUE, packed acc | acc_par << 1: a reference into a noinline function pins
+// the caller's variable to local memory for the whole kernel)
+__device__ __noinline__ int slab_epilogue(const Phase& ph, unsigned int epoch, int b, int G, int wtid, uint32_t tmem_base,
+                                          int acc_state, uint64_t* tfull, uint64_t* tempty, SlabRed& red,
+                                          bool backoff = false) {
+  int acc = acc_state & 1, acc_par = acc_state >> 1;
   const int wwarp = wtid >> 5, lane = wtid & 31, quarter = wwarp & 3, cg = wwarp >> 2;
   const int T = ph.T, epi = ph.epi;
   const int passes = ph.s_passes, n_tiles = ph.s_ntiles, rows_alloc = ph.s_rows_alloc, pair = ph.s_pair;
@@ -612,6 +615,7 @@ __device__ __noinline__ void slab_epilogue(const Phase& ph, unsigned int epoch, 
         if (t0 + i < T) X[(long)(t0 + i) * ldd + n_keep[j]] = f2bf(wj[j] * rbf(yv[j][i] * red.rstd[t0 + i]));
     }
   }
+  return acc | (acc_par << 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
