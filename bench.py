@@ -45,7 +45,7 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one program_kernel launch from the committed `ncu --set full` capture
 # (profiles/README.md); None until a capture of the current kernel exists
-NCU_TRAFFIC_BYTES = 16.815e9 + 0.136e9        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)
+NCU_TRAFFIC_BYTES = 16.810e9 + 0.120e9        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)
 NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_full_program_kernel.csv"
 N_PRE, N_IMG, N_POST = 5, 576, 123          # 576 image + 128 text tokens = 704
 GEN_TOKENS = 256

@@ -185,18 +185,10 @@ __device__ __forceinline__ float att_ex2(float x) {
 // exp for softmax STATISTICS (row maxima / denominators): ex2.approx, relative error ~2^-22 -- far below the bf16 rounding of
 // the probabilities that are divided by the result; the probabilities themselves use expf.  exp(-inf) == 0.
 __device__ __forceinline__ float att_exp_stat(float x) { return att_ex2(x * ATT_LOG2E); }
-// exp(x) for the PROBABILITIES, x <= 0 (score minus row maximum; -inf for masked keys): 2^(t + lo) with t = RN(x * log2 e)
-// and lo = the rounding error of that product + x * (log2 e - RN(log2 e)), recovered by two FMAs -- about 1 ulp, like expf,
-// without expf's range handling (7 instructions instead of ~12, inlined 8 to 16 times per item).  exp(-inf) == 0 through
-// the clamp (2^-173 flushes to 0).
-__device__ __forceinline__ float att_exp_prob(float x) {
-  x = fmaxf(x, -120.f);
-  const float t = x * ATT_LOG2E;
-  float lo = fmaf(x, ATT_LOG2E, -t);
-  lo = fmaf(x, 1.925963033500558e-08f, lo);
-  const float e = att_ex2(t);
-  return fmaf(e, lo * 0.6931471805599453f, e);
-}
+// The PROBABILITIES use expf itself: a cheaper exp of the same accuracy (ex2.approx with the product's rounding error
+// recovered by two FMAs, <= 2 ulp, 7 instructions) was 1 % faster at 8192 keys, but it is not BIT-identical to expf in every
+// element, and on random-init weights one flipped bf16 rounding is enough to part the generated tokens from the
+// reference's (bench.py gpu_eager_baseline: common prefix 4 of 256 instead of 256 of 256).  Reverted.
 
 // split statistics -> head-wide softmax denominators; on entry sm.red / sm.red2 hold every warp's (max, sum exp) per row.
 // The exchange is ONE L2 round trip: every split stores its (m, l) per row as two 8-byte words that carry the launch tag in
@@ -540,7 +532,7 @@ __device__ __forceinline__ unsigned int attn_ring_item(const AttnArgs& p, int n_
   // exp(-inf) == 0: masked keys and keys past kv_len need no branch (a fully masked ROW has gm == -inf and is NaN, as in
   // the reference's softmax)
   auto prob2 = [&](float sa, float sb, float gm, float gl, float gr) -> uint32_t {
-    const float ea = att_exp_prob(sa - gm), eb = att_exp_prob(sb - gm);
+    const float ea = expf(sa - gm), eb = expf(sb - gm);
     return EAGER ? pack_bf2_rn(att_div(ea, gl, gr), att_div(eb, gl, gr)) : pack_bf2_rn(ea, eb);
   };
   if (!STREAM) {
