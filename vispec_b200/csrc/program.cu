@@ -51,7 +51,8 @@
 // Register split between the warpgroups of the program kernel (setmaxnreg): 640 threads cap the kernel at 96 registers
 // per thread; the role warps (one warpgroup) give 32 of theirs back and every worker thread takes 8.  ptxas then allocates
 // the worker code on 104 registers (LDL / STL of the kernel 474 -> 316) -- same-box A/B 226.3 -> 230.8 tok/s; 56 / 104 and
-// 40 / 104 measure the same within noise, 32 / 112 spills inside the producer loops.
+// 48 / 104 measure the same within noise; 32 / 112 spills inside the producer loops: attention 491 -> 478 us per cycle but
+// 230.6 -> 228.6 tok/s overall.
 #ifndef VS_SETMAXNREG
 #define VS_SETMAXNREG 1
 #endif
