@@ -383,17 +383,38 @@ __device__ __forceinline__ void epi_phase_t(const Phase& ph, unsigned int epoch,
   }
   CLK(6);
 }
-#define VS_EPI_FN(name, TPT_, KIND_)                                                                                   \
-  __device__ __noinline__ void name(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,  \
-                                    TeamSync sync) {                                                                  \
+// (-DVS_EPI_INLINE=mask, A/B: bit 0 inlines the residual epilogue into the kernel body, bit 1 the SwiGLU ones, bit 2 the
+// q|k|v one -- inside a noinline function every global load carries two R2UR of the memory descriptor)
+#ifndef VS_EPI_INLINE
+#define VS_EPI_INLINE 0
+#endif
+#define VS_EPI_FN(name, TPT_, KIND_, ATTR_)                                                                            \
+  __device__ ATTR_ void name(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,         \
+                             TeamSync sync) {                                                                         \
     epi_phase_t<TPT_, KIND_>(ph, epoch, gteam, n_teams, tt, red, sync);                                               \
   }
-VS_EPI_FN(epi_phase_store, EPI_TPT, EPI_STORE)
-VS_EPI_FN(epi_phase_resid, EPI_TPT, EPI_RESID)
-VS_EPI_FN(epi_phase_swiglu, EPI_TPT, EPI_SWIGLU)
-VS_EPI_FN(epi_phase_heads, EPI_TPT, EPI_HEADS)
-VS_EPI_FN(epi_phase_store_wide, 2 * EPI_TPT, EPI_STORE)
-VS_EPI_FN(epi_phase_swiglu_wide, 2 * EPI_TPT, EPI_SWIGLU)
+#define VS_EPI_ATTR(bit) VS_EPI_ATTR_##bit
+#if VS_EPI_INLINE & 1
+#define VS_EPI_ATTR_0 __forceinline__
+#else
+#define VS_EPI_ATTR_0 __noinline__
+#endif
+#if VS_EPI_INLINE & 2
+#define VS_EPI_ATTR_1 __forceinline__
+#else
+#define VS_EPI_ATTR_1 __noinline__
+#endif
+#if VS_EPI_INLINE & 4
+#define VS_EPI_ATTR_2 __forceinline__
+#else
+#define VS_EPI_ATTR_2 __noinline__
+#endif
+VS_EPI_FN(epi_phase_store, EPI_TPT, EPI_STORE, __noinline__)
+VS_EPI_FN(epi_phase_resid, EPI_TPT, EPI_RESID, VS_EPI_ATTR(0))
+VS_EPI_FN(epi_phase_swiglu, EPI_TPT, EPI_SWIGLU, VS_EPI_ATTR(1))
+VS_EPI_FN(epi_phase_heads, EPI_TPT, EPI_HEADS, VS_EPI_ATTR(2))
+VS_EPI_FN(epi_phase_store_wide, 2 * EPI_TPT, EPI_STORE, __noinline__)
+VS_EPI_FN(epi_phase_swiglu_wide, 2 * EPI_TPT, EPI_SWIGLU, VS_EPI_ATTR(1))
 #undef VS_EPI_FN
 __device__ __forceinline__ void epi_phase(const Phase& ph, unsigned int epoch, int gteam, int n_teams, int tt, float* red,
                                           TeamSync sync) {
