@@ -189,3 +189,21 @@ def test_sass_has_tma_tensor_loads_and_tcgen05():
     sass = subprocess.run(["cuobjdump", "-sass", b.build()], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "UTMALDG.2D", "UTMALDG.4D", "UTMALDG.3D"):
         assert mnemonic in sass, mnemonic
+
+
+def test_sass_program_kernel_code_generation_guards():
+    """Two code-generation properties of the persistent kernel that were worth 5 % together and are invisible in the
+    source: its shared-memory accesses are LDS / STS, not generic loads on 64-bit pointers (the
+    shared base must be derived from the shared array by pointer arithmetic, never through an integer cast), and the
+    register split between the role and the worker warpgroups (setmaxnreg) is in the binary."""
+    from vispec_b200 import build as b
+    import re
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", b.build()], capture_output=True, text=True).stdout
+    start = sass.index("program_kernel")
+    nxt = re.search(r"Function : ", sass[start:])
+    body = sass[start:start + nxt.start()] if nxt else sass[start:]
+    n_lds = len(re.findall(r"\bLDS\b", body))
+    n_generic = len(re.findall(r"\bLD\.E\b", body))
+    assert n_lds > 800 and n_lds > 3 * n_generic, (n_lds, n_generic)
+    assert "USETMAXREG.DEALLOC" in body and "USETMAXREG.TRY_ALLOC" in body
